@@ -1,0 +1,400 @@
+// MixedInferenceCore: init (tensor plan, weight arena, fusion, CUDA-graph capture) and run.
+// Counterpart of core/src/ic2/core.cpp:294-410 (init) and :97-245 (run).
+#include <algorithm>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "engine.h"
+
+using namespace snnb;
+
+namespace snn {
+
+using namespace dp;
+
+MixedInferenceCore::~MixedInferenceCore() {
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (cuGraphExec) cudaGraphExecDestroy(cuGraphExec);
+    if (cuGraph) cudaGraphDestroy(cuGraph);
+    for (auto* t : ownedTensors) snnb_tensor_free(t);
+    if (arena) cudaFree(arena);
+    if (scratchArena) cudaFree(scratchArena);
+    if (ioStage) cudaFree(ioStage);
+    if (argmaxDev) cudaFree(argmaxDev);
+}
+
+std::unique_ptr<MixedInferenceCore> MixedInferenceCore::create(snnb_context* ctx, const std::string& modelFileName, const ShaderGenOptions& options,
+                                                               std::string& err) {
+    std::unique_ptr<MixedInferenceCore> core(new MixedInferenceCore());
+    core->ctx     = ctx;
+    core->options = options;
+    try {
+        core->layers = loadFromJsonModel(modelFileName);
+        core->graph  = generateInferenceGraph(core->layers, options);
+    } catch (std::exception& e) {
+        err = e.what();
+        return nullptr;
+    }
+    if (!core->init(err)) return nullptr;
+    return core;
+}
+
+static bool allZeroPadding(const PaddingSpec& p) {
+    uint32_t o[4];
+    p.offsets(3, true, o); // kernel size only matters for "same"
+    const bool keyword_same = !(p.t == "valid" || p.t == "none" || (!p.t.empty() && std::all_of(p.t.begin(), p.t.end(), ::isdigit)));
+    return !keyword_same && o[0] == 0 && o[1] == 0 && o[2] == 0 && o[3] == 0;
+}
+
+bool MixedInferenceCore::init(std::string& err) {
+    const int N = (int) options.batch;
+    std::unordered_map<GenericModelLayer*, int> order;
+    for (size_t i = 0; i < graph.sorted.size(); ++i) order[graph.sorted[i]] = (int) i;
+
+    for (auto* L : graph.sorted) {
+        if (L->isInputLayer) inputLayers.push_back(L);
+        if (L->nextLayers.empty()) outputLayers.push_back(L);
+        if (L->typeName == "YOLO") yolo = static_cast<YOLOLayer*>(L);
+    }
+    std::stable_sort(inputLayers.begin(), inputLayers.end(), [](GenericModelLayer* a, GenericModelLayer* b) {
+        return static_cast<InputLayerLayer*>(a)->_desc.inputIndex < static_cast<InputLayerLayer*>(b)->_desc.inputIndex;
+    });
+    if (inputLayers.empty()) {
+        err = "model has no InputLayer";
+        return false;
+    }
+
+    // ---- fusion passes (engine-level; off => one kernel per reference layer, every layer output observable) ----
+    // `alias[L]` = the layer whose output tensor stands in for L's (L launches nothing).
+    std::unordered_map<GenericModelLayer*, GenericModelLayer*> alias;
+    if (options.fuse) {
+        for (auto* L : graph.sorted) {
+            // (1) Pad -> Conv2D/Depthwise with zero own padding: the consumer's gather applies the offsets (and mode) itself.
+            if (L->typeName == "Pad" && L->nextLayers.size() == 1 && L->prevLayers.size() == 1) {
+                auto* pad  = static_cast<PadLayer*>(L);
+                auto* next = L->nextLayers[0];
+                PaddingSpec* np = nullptr;
+                if (next->typeName == "Conv2D" && static_cast<Conv2DLayer*>(next)->_desc.kernelSize > 1) np = &static_cast<Conv2DLayer*>(next)->_desc.padding;
+                if (next->typeName == "SeparableConv2D" && pad->mode == "constant") np = &static_cast<SeparableConv2DLayer*>(next)->_desc.padding;
+                if (np && allZeroPadding(*np)) {
+                    uint32_t o[4];
+                    pad->padding.offsets(0, false, o);
+                    np->t = std::to_string(o[0]), np->b = std::to_string(o[1]), np->l = std::to_string(o[2]), np->r = std::to_string(o[3]);
+                    np->mode       = pad->mode;
+                    L->fusedAway   = true;
+                    alias[L]       = L->prevLayers[0];
+                }
+            }
+            // (2) Conv2D(linear) -> Add(+act): the conv's epilogue adds the other operand and applies the Add's activation.
+            if (L->typeName == "Add" && L->prevLayers.size() == 2) {
+                auto* add = static_cast<AddLayer*>(L);
+                GenericModelLayer* a = L->prevLayers[0];
+                GenericModelLayer* b = L->prevLayers[1];
+                auto fusable = [&](GenericModelLayer* c, GenericModelLayer* other) {
+                    if (c->typeName != "Conv2D" || c->nextLayers.size() != 1 || c->fusedAway) return false;
+                    auto* conv = static_cast<Conv2DLayer*>(c);
+                    if (conv->_desc.activation.id != SNNB_ACT_NONE || conv->residual || conv->fusedAct >= 0) return false;
+                    return order[other] < order[c] && c != other; // the other operand must be complete before the conv runs
+                };
+                GenericModelLayer* conv = nullptr;
+                GenericModelLayer* other = nullptr;
+                if (fusable(b, a))
+                    conv = b, other = a;
+                else if (fusable(a, b))
+                    conv = a, other = b;
+                if (conv) {
+                    conv->fusedAct   = add->activation.id;
+                    conv->fusedAlpha = add->activation.alpha;
+                    conv->prevLayers.push_back(other); // bookkeeping only: residual operand
+                    L->fusedAway     = true;           // the Add launches nothing; its tensor is written by the conv
+                    alias[conv]      = L;              // conv output == add output
+                }
+            }
+            // (3) Flatten of a 1x1xC tensor without activation is the identity.
+            if (L->typeName == "Flatten" && L->inputDims.size() == 1 && L->inputDims[0].width * L->inputDims[0].height == 1 &&
+                static_cast<FlattenLayer*>(L)->activation.id == SNNB_ACT_NONE) {
+                L->fusedAway = true;
+                alias[L]     = L->prevLayers[0];
+            }
+        }
+    }
+
+    // ---- tensors: one output per executing layer (core.cpp:356-374 allocates one texture per stage) ----
+    std::unordered_map<GenericModelLayer*, snnb_tensor*> outOf;
+    auto resolve = [&](GenericModelLayer* L) -> GenericModelLayer* {
+        std::unordered_set<GenericModelLayer*> seen;
+        while (alias.count(L) && !seen.count(L)) {
+            seen.insert(L);
+            L = alias[L];
+        }
+        return L;
+    };
+    for (size_t i = 0; i < graph.sorted.size(); ++i) {
+        GenericModelLayer* L = graph.sorted[i];
+        if (L->typeName == "YOLO") continue; // host op
+        GenericModelLayer* owner = resolve(L);
+        if (owner != L && !(L->typeName == "Conv2D")) continue; // Pad/Flatten aliases own nothing
+        if (outOf.count(owner)) continue;
+        // dims of the tensor = dims of `owner` (for conv->add fusion both agree)
+        const Dims& d = graph.outputDims[order[owner]];
+        snnb_tensor* t = nullptr;
+        if (tensor_alloc(ctx, N, (int) d.height, (int) d.width, (int) d.depth, &t)) {
+            err = get_error();
+            return false;
+        }
+        ownedTensors.push_back(t);
+        outOf[owner] = t;
+    }
+    for (auto* L : graph.sorted) {
+        if (L->typeName == "YOLO") {
+            for (auto* p : L->prevLayers) L->inputs.push_back(outOf.at(resolve(p)));
+            continue;
+        }
+        GenericModelLayer* owner = resolve(L);
+        L->output                = outOf.count(owner) ? outOf[owner] : nullptr;
+        if (L->fusedAway) continue;
+        size_t nin = L->prevLayers.size();
+        if (L->typeName == "Conv2D" && static_cast<Conv2DLayer*>(L)->fusedAct >= 0) {
+            nin -= 1; // last prev is the residual operand
+            L->residual = outOf.at(resolve(L->prevLayers.back()));
+        }
+        for (size_t k = 0; k < nin; ++k) L->inputs.push_back(outOf.at(resolve(L->prevLayers[k])));
+        if (L->typeName == "Conv2D") static_cast<Conv2DLayer*>(L)->algo = options.convAlgo;
+        if (L->typeName == "Dense") {
+            auto* dl = static_cast<DenseLayer*>(L);
+            if (L->inputs[0]->h * L->inputs[0]->w != 1) {
+                if (tensor_alloc(ctx, N, 1, 1, (int) dl->numInputPlanes, &dl->flat)) {
+                    err = get_error();
+                    return false;
+                }
+                ownedTensors.push_back(dl->flat);
+            }
+            if ((uint32_t) (L->inputs[0]->h * L->inputs[0]->w * L->inputs[0]->c) != dl->numInputPlanes) {
+                err = L->name + ": Dense expects " + std::to_string(dl->numInputPlanes) + " inputs, graph provides " +
+                      std::to_string(L->inputs[0]->h * L->inputs[0]->w * L->inputs[0]->c);
+                return false;
+            }
+        }
+        if ((L->typeName == "Add" || L->typeName == "Concatenate") && L->inputs.size() != 2) {
+            err = L->name + ": expects exactly two inputs";
+            return false;
+        }
+    }
+
+    // ---- weights: fold + pack on the host, then ONE device arena (broadcastable with a single NCCL call) ----
+    std::vector<std::pair<GenericModelLayer*, PackedHost>> packed;
+    size_t total = 0, scratchTotal = 0;
+    for (auto* L : graph.sorted) {
+        PackedHost p;
+        try {
+            L->packWeights(p);
+        } catch (std::exception& e) {
+            err = L->name + ": " + e.what();
+            return false;
+        }
+        if (p.kind) {
+            total += p.device_bytes();
+            packed.emplace_back(L, std::move(p));
+        }
+        if (L->typeName == "InstanceNorm") {
+            static_cast<InstanceNormLayer*>(L)->computeScratch(N);
+            scratchTotal += (L->scratchBytes() + 255) & ~(size_t) 255;
+        }
+    }
+    arenaBytes = total ? total : 256;
+    if (cudaMalloc(&arena, arenaBytes) != cudaSuccess) {
+        err = "cudaMalloc(weight arena) failed";
+        return false;
+    }
+    {
+        char* cur = (char*) arena;
+        for (auto& pr : packed) {
+            if (place_weights(ctx, pr.second, cur, &pr.first->weights)) {
+                err = get_error();
+                return false;
+            }
+            cur += pr.first->weights.bytes;
+        }
+    }
+    if (scratchTotal) {
+        if (cudaMalloc(&scratchArena, scratchTotal) != cudaSuccess) {
+            err = "cudaMalloc(scratch) failed";
+            return false;
+        }
+        char* cur = (char*) scratchArena;
+        for (auto* L : graph.sorted)
+            if (L->scratchBytes()) {
+                L->scratch = (float*) cur;
+                cur += (L->scratchBytes() + 255) & ~(size_t) 255;
+            }
+    }
+
+    // ---- io staging (stable addresses so the captured graph stays valid) ----
+    size_t maxFloats = 1;
+    for (auto* L : inputLayers) maxFloats = std::max(maxFloats, L->output->pixels() * (size_t) L->output->c);
+    for (auto* L : outputLayers)
+        if (L->output) maxFloats = std::max(maxFloats, L->output->pixels() * (size_t) L->output->c);
+    ioStageBytes = maxFloats * sizeof(float);
+    if (cudaMalloc(&ioStage, ioStageBytes) != cudaSuccess || cudaMalloc(&argmaxDev, sizeof(int) * N) != cudaSuccess) {
+        err = "cudaMalloc(io staging) failed";
+        return false;
+    }
+    {
+        GenericModelLayer* last = nullptr;
+        for (auto* L : outputLayers)
+            if (L->output) {
+                last = L;
+                break;
+            }
+        isClassifier = last && last->output->h == 1 && last->output->w == 1 && last->output->c > 1;
+    }
+
+    // ---- one eager pass: counts launches and warms everything up; then optionally capture ----
+    const uint64_t before = ctx->launches;
+    if (enqueueForward(false)) {
+        err = get_error();
+        return false;
+    }
+    launchesPerForward = (int) (ctx->launches - before);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        err = std::string("first forward pass failed: ") + cudaGetErrorString(cudaGetLastError());
+        return false;
+    }
+    if (options.useCudaGraph) {
+        const uint64_t keep = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            err = "cudaStreamBeginCapture failed";
+            return false;
+        }
+        const int rc = enqueueForward(false);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &cuGraph);
+        ctx->launches = keep;
+        if (rc || e != cudaSuccess) {
+            err = rc ? get_error() : "cudaStreamEndCapture failed";
+            return false;
+        }
+        if (cudaGraphInstantiate(&cuGraphExec, cuGraph, 0) != cudaSuccess) {
+            err = "cudaGraphInstantiate failed";
+            return false;
+        }
+    }
+    return true;
+}
+
+int MixedInferenceCore::enqueueForward(bool) {
+    ExecOptions eo;
+    eo.convAlgo = options.convAlgo;
+    for (auto* L : graph.sorted) {
+        if (L->fusedAway || L->isInputLayer || L->typeName == "YOLO") continue;
+        if (int rc = L->run(ctx, eo)) return rc;
+    }
+    return 0;
+}
+
+int MixedInferenceCore::forward() {
+    if (cuGraphExec) {
+        SNNB_CUDA_OK(cudaGraphLaunch(cuGraphExec, ctx->stream));
+        ctx->launches += (uint64_t) launchesPerForward;
+        return 0;
+    }
+    return enqueueForward(false);
+}
+
+int MixedInferenceCore::setInput(int idx, const float* host) {
+    SNNB_REQUIRE(idx >= 0 && idx < (int) inputLayers.size() && host, "setInput: bad argument");
+    snnb_tensor* t     = inputLayers[idx]->output;
+    const size_t bytes = t->pixels() * t->c * sizeof(float);
+    SNNB_CUDA_OK(cudaMemcpyAsync(ioStage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_split_f32(ctx, ioStage, t);
+}
+
+int MixedInferenceCore::getOutput(int idx, float* host, size_t capacityFloats) {
+    SNNB_REQUIRE(idx >= 0 && idx < (int) outputLayers.size() && host, "getOutput: bad argument");
+    GenericModelLayer* L = outputLayers[idx];
+    if (L->typeName == "YOLO") { // rows of image 0 .. N-1 are fetched with snnb_model_get_boxes
+        set_error("getOutput: output %d is a YOLO detection list; use snnb_model_get_boxes", idx);
+        return 2;
+    }
+    snnb_tensor* t      = L->output;
+    const size_t floats = t->pixels() * t->c;
+    SNNB_REQUIRE(capacityFloats >= floats, "getOutput: buffer too small (%zu < %zu floats)", capacityFloats, floats);
+    if (launch_merge_f32(ctx, t, ioStage)) return 1;
+    SNNB_CUDA_OK(cudaMemcpyAsync(host, ioStage, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int MixedInferenceCore::run(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1) {
+    if (setInput(0, hostInput)) return 1;
+    if (forward()) return 1;
+    if (yolo) {
+        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        if (yolo->decode(ctx, boxes)) return 1;
+    }
+    int outIdx = -1;
+    for (size_t i = 0; i < outputLayers.size(); ++i)
+        if (outputLayers[i]->typeName != "YOLO") {
+            outIdx = (int) i;
+            break;
+        }
+    if (classes1 && isClassifier && outIdx >= 0) {
+        if (launch_argmax(ctx, outputLayers[outIdx]->output, argmaxDev)) return 1;
+        SNNB_CUDA_OK(cudaMemcpyAsync(classes1, argmaxDev, sizeof(int) * options.batch, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (hostOutput && outIdx >= 0) {
+        if (getOutput(outIdx, hostOutput, capacityFloats)) return 1;
+    } else {
+        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (classes1 && isClassifier && outIdx >= 0)
+        for (uint32_t i = 0; i < options.batch; ++i) classes1[i] += 1; // core.cpp:228-233: argmax + 1
+    return 0;
+}
+
+int MixedInferenceCore::layerOutput(int layerId, float* host, size_t capacityFloats) {
+    SNNB_REQUIRE(layerId >= 0 && layerId < (int) layers.size() && host, "layerOutput: bad argument");
+    GenericModelLayer* L = layers[layerId].get();
+    SNNB_REQUIRE(L->output, "layerOutput: layer %d (%s) has no device tensor", layerId, L->name.c_str());
+    SNNB_REQUIRE(!(L->typeName == "Conv2D" && static_cast<Conv2DLayer*>(L)->fusedAct >= 0),
+                 "layerOutput: layer %d (%s) was fused into its Add; load the model with fuse=0 to observe it", layerId, L->name.c_str());
+    const size_t floats = L->output->pixels() * L->output->c;
+    SNNB_REQUIRE(capacityFloats >= floats, "layerOutput: buffer too small (%zu < %zu floats)", capacityFloats, floats);
+    return snnb_tensor_download_nhwc(ctx, L->output, host);
+}
+
+int MixedInferenceCore::timeLayers(std::vector<float>& ms) {
+    ms.assign(layers.size(), 0.0f);
+    std::vector<cudaEvent_t> ev(graph.sorted.size() + 1);
+    for (auto& e : ev) SNNB_CUDA_OK(cudaEventCreate(&e));
+    ExecOptions eo;
+    eo.convAlgo = options.convAlgo;
+    SNNB_CUDA_OK(cudaEventRecord(ev[0], ctx->stream));
+    for (size_t i = 0; i < graph.sorted.size(); ++i) {
+        GenericModelLayer* L = graph.sorted[i];
+        if (!(L->fusedAway || L->isInputLayer || L->typeName == "YOLO"))
+            if (int rc = L->run(ctx, eo)) return rc;
+        SNNB_CUDA_OK(cudaEventRecord(ev[i + 1], ctx->stream));
+    }
+    SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < graph.sorted.size(); ++i) {
+        float t = 0;
+        SNNB_CUDA_OK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        ms[graph.sorted[i]->layerId] = t;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return 0;
+}
+
+int MixedInferenceCore::dumpOutputs(const std::string& dir) {
+    for (auto& l : layers) {
+        if (!l->output || l->fusedAway) continue;
+        std::string path = dir + "/" + l->name + " pass[0].dump"; // vulkanBackend.cpp:108-143 naming
+        if (snnb_tensor_dump(ctx, l->output, path.c_str())) return 1;
+    }
+    return 0;
+}
+
+} // namespace snn

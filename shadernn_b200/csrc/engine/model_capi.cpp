@@ -1,0 +1,147 @@
+// extern "C" surface for the whole-model engine (snnb_model_*). See include/snnb.h.
+#include <cstring>
+
+#include "engine.h"
+
+using namespace snnb;
+
+struct snnb_model {
+    std::unique_ptr<snn::MixedInferenceCore> core;
+};
+
+static void copyStr(char* dst, int cap, const std::string& s) {
+    if (!dst || cap <= 0) return;
+    strncpy(dst, s.c_str(), (size_t) cap - 1);
+    dst[cap - 1] = 0;
+}
+
+extern "C" {
+
+int snnb_model_load_json(snnb_context* ctx, const char* json_path, const snnb_model_options* opt, snnb_model** out) {
+    SNNB_REQUIRE(ctx && json_path && out, "snnb_model_load_json: null argument");
+    snn::dp::ShaderGenOptions o;
+    if (opt) {
+        o.batch              = opt->batch > 0 ? (uint32_t) opt->batch : 1;
+        o.desiredInputWidth  = opt->input_width > 0 ? (uint32_t) opt->input_width : 0;
+        o.desiredInputHeight = opt->input_height > 0 ? (uint32_t) opt->input_height : 0;
+        o.convAlgo           = opt->conv_algo;
+        o.useCudaGraph       = opt->use_cuda_graph != 0;
+        o.fuse               = opt->fuse != 0;
+    }
+    SNNB_CUDA_OK(cudaSetDevice(ctx->device));
+    std::string err;
+    std::unique_ptr<snn::MixedInferenceCore> core;
+    try {
+        core = snn::MixedInferenceCore::create(ctx, json_path, o, err);
+    } catch (std::exception& e) { err = e.what(); }
+    if (!core) {
+        set_error("snnb_model_load_json(%s): %s", json_path, err.c_str());
+        return 1;
+    }
+    auto* m = new snnb_model();
+    m->core = std::move(core);
+    *out    = m;
+    return 0;
+}
+
+int snnb_model_destroy(snnb_model* m) {
+    delete m;
+    return 0;
+}
+
+int snnb_model_num_layers(const snnb_model* m) { return m ? (int) m->core->layers.size() : -1; }
+
+int snnb_model_layer_info(const snnb_model* m, int i, char* name, int name_cap, char* type, int type_cap, int* n, int* h, int* w, int* c) {
+    SNNB_REQUIRE(m && i >= 0 && i < (int) m->core->layers.size(), "snnb_model_layer_info: bad index");
+    auto* L = m->core->layers[i].get();
+    copyStr(name, name_cap, L->name);
+    copyStr(type, type_cap, L->typeName);
+    // dims from the graph (valid for fused-away layers too)
+    for (size_t k = 0; k < m->core->graph.sorted.size(); ++k)
+        if (m->core->graph.sorted[k] == L) {
+            const auto& d = m->core->graph.outputDims[k];
+            if (n) *n = (int) m->core->options.batch;
+            if (h) *h = (int) d.height;
+            if (w) *w = (int) d.width;
+            if (c) *c = (int) d.depth;
+        }
+    return 0;
+}
+
+int snnb_model_num_inputs(const snnb_model* m) { return m ? (int) m->core->inputLayers.size() : -1; }
+int snnb_model_num_outputs(const snnb_model* m) { return m ? (int) m->core->outputLayers.size() : -1; }
+
+static int dimsOf(const snnb_tensor* t, int* n, int* h, int* w, int* c) {
+    SNNB_REQUIRE(t, "tensor not materialised");
+    return snnb_tensor_dims(t, n, h, w, c);
+}
+int snnb_model_input_dims(const snnb_model* m, int idx, int* n, int* h, int* w, int* c) {
+    SNNB_REQUIRE(m && idx >= 0 && idx < (int) m->core->inputLayers.size(), "snnb_model_input_dims: bad index");
+    return dimsOf(m->core->inputLayers[idx]->output, n, h, w, c);
+}
+int snnb_model_output_dims(const snnb_model* m, int idx, int* n, int* h, int* w, int* c) {
+    SNNB_REQUIRE(m && idx >= 0 && idx < (int) m->core->outputLayers.size(), "snnb_model_output_dims: bad index");
+    auto* L = m->core->outputLayers[idx];
+    if (L->typeName == "YOLO") {
+        if (n) *n = (int) m->core->options.batch;
+        if (h) *h = 100;
+        if (w) *w = 6;
+        if (c) *c = 1;
+        return 0;
+    }
+    return dimsOf(L->output, n, h, w, c);
+}
+
+int snnb_model_run(snnb_model* m, const float* host_input, float* host_output, size_t out_capacity, int* classes) {
+    SNNB_REQUIRE(m && host_input, "snnb_model_run: null argument");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
+    return m->core->run(host_input, host_output, out_capacity, classes);
+}
+int snnb_model_set_input(snnb_model* m, int idx, const float* host_input) {
+    SNNB_REQUIRE(m, "snnb_model_set_input: null model");
+    return m->core->setInput(idx, host_input);
+}
+int snnb_model_forward(snnb_model* m) {
+    SNNB_REQUIRE(m, "snnb_model_forward: null model");
+    return m->core->forward();
+}
+int snnb_model_get_output(snnb_model* m, int idx, float* host_output, size_t cap) {
+    SNNB_REQUIRE(m, "snnb_model_get_output: null model");
+    return m->core->getOutput(idx, host_output, cap);
+}
+int snnb_model_layer_output(snnb_model* m, int layer, float* host, size_t cap) {
+    SNNB_REQUIRE(m, "snnb_model_layer_output: null model");
+    return m->core->layerOutput(layer, host, cap);
+}
+int snnb_model_dump_outputs(snnb_model* m, const char* dir) {
+    SNNB_REQUIRE(m && dir, "snnb_model_dump_outputs: null argument");
+    return m->core->dumpOutputs(dir);
+}
+int snnb_model_time_layers(snnb_model* m, float* times_ms, int capacity) {
+    SNNB_REQUIRE(m && times_ms && capacity >= (int) m->core->layers.size(), "snnb_model_time_layers: bad argument");
+    std::vector<float> ms;
+    if (m->core->timeLayers(ms)) return 1;
+    for (size_t i = 0; i < ms.size(); ++i) times_ms[i] = ms[i];
+    return 0;
+}
+int snnb_model_launches_per_forward(const snnb_model* m) { return m ? m->core->launchesPerForward : -1; }
+
+int snnb_model_get_boxes(snnb_model* m, int n, float* rows6, int max_rows, int* count) {
+    SNNB_REQUIRE(m && count, "snnb_model_get_boxes: null argument");
+    SNNB_REQUIRE(n >= 0 && n < (int) m->core->boxes.size(), "snnb_model_get_boxes: no detections for image %d (model has no YOLO layer, or run() not called)", n);
+    const auto& rows = m->core->boxes[n].rows;
+    int k            = 0;
+    for (; k < (int) rows.size() && k < max_rows && k < 100; ++k)
+        for (int j = 0; j < 6; ++j) rows6[k * 6 + j] = rows[k][j];
+    *count = k;
+    return 0;
+}
+
+int snnb_model_weight_arena(snnb_model* m, void** device_ptr, size_t* bytes) {
+    SNNB_REQUIRE(m && device_ptr && bytes, "snnb_model_weight_arena: null argument");
+    *device_ptr = m->core->arena;
+    *bytes      = m->core->arenaBytes;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,863 @@
+// CUDA-core (SIMT) kernels for sm_100a: the HBM-bound operators (depthwise, pooling, add, norms, layout ops)
+// and the generic direct/implicit-GEMM fp32 convolution used where the tcgen05 path does not apply
+// (IC = 3 stems, 1-channel ESPCN layers, reflect/replicate padding).
+//
+// All activation tensors are split-bf16 NHWC (see snnb_internal.h): every kernel reads hi+lo, computes in fp32
+// and writes hi/lo. Channel groups of 8 (= one 16-byte vector per plane) are the unit of work; channels in
+// [C, Cp) are written as zero so they never pollute a consumer.
+//
+// Semantics follow the reference's Vulkan compute shaders (cited per kernel; paths relative to the reference repo
+// core/data/assets/shaders/).
+#include "snnb_internal.h"
+
+namespace snnb {
+
+// ------------------------------------------------------------------------------------------------------------
+// split-bf16 helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// 8 channels: v[i] = hi[i] + lo[i]
+__device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t off, float v[8]) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    v[0] = bf16lo_to_f32(h.x) + bf16lo_to_f32(l.x);
+    v[1] = bf16hi_to_f32(h.x) + bf16hi_to_f32(l.x);
+    v[2] = bf16lo_to_f32(h.y) + bf16lo_to_f32(l.y);
+    v[3] = bf16hi_to_f32(h.y) + bf16hi_to_f32(l.y);
+    v[4] = bf16lo_to_f32(h.z) + bf16lo_to_f32(l.z);
+    v[5] = bf16hi_to_f32(h.z) + bf16hi_to_f32(l.z);
+    v[6] = bf16lo_to_f32(h.w) + bf16lo_to_f32(l.w);
+    v[7] = bf16hi_to_f32(h.w) + bf16hi_to_f32(l.w);
+}
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    h                 = *reinterpret_cast<uint32_t*>(&hh);
+    float ra          = a - bf16lo_to_f32(h);
+    float rb          = b - bf16hi_to_f32(h);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(ra, rb);
+    l                 = *reinterpret_cast<uint32_t*>(&ll);
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t off, const float v[8]) {
+    uint4 h, l;
+    split2(v[0], v[1], h.x, l.x);
+    split2(v[2], v[3], h.y, l.y);
+    split2(v[4], v[5], h.z, l.z);
+    split2(v[6], v[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+}
+
+__device__ __forceinline__ float load1(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t off) {
+    return __bfloat162float(hi[off]) + __bfloat162float(lo[off]);
+}
+__device__ __forceinline__ void store1(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t off, float v) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[off]         = h;
+    lo[off]         = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// Activations: ids of conv2dVulkan.cpp:57-71; math of shadertemplate_vk_conv2d.comp:290-340 (SiLU computed
+// correctly per element — the reference's 4-pixel kernel reuses pixel 1's sigmoid).
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+    switch (act) {
+    case SNNB_ACT_RELU: return fmaxf(v, 0.0f);
+    case SNNB_ACT_RELU6: return fminf(fmaxf(v, 0.0f), 6.0f);
+    case SNNB_ACT_TANH: return tanhf(v);
+    case SNNB_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    case SNNB_ACT_LEAKY_RELU: return fmaxf(v, v * alpha);
+    case SNNB_ACT_SILU: return v * 1.0f / (1.0f + expf(-v));
+    default: return v;
+    }
+}
+
+// Source coordinate under a padding mode (vk_conv2d.comp:168-218): returns -1 for "reads zero".
+__device__ __forceinline__ int src_coord(int s, int n, int mode) {
+    if (mode == SNNB_PAD_REPLICATE) return min(max(s, 0), n - 1);
+    if (mode == SNNB_PAD_REFLECT) {
+        s = (s < 0) ? -s : s;
+        s = (s >= n) ? 2 * n - 2 - s : s;
+        return s;
+    }
+    return (s >= 0 && s < n) ? s : -1;
+}
+
+struct TV { // kernel-side tensor view
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    int N, H, W, C, Cp;
+};
+static TV view(const snnb_tensor* t) { return TV {t->hi, t->lo, t->n, t->h, t->w, t->c, t->cp}; }
+
+#define SNNB_LAUNCH_CHECK(ctx)                                                                          \
+    do {                                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess) {                                                                        \
+            set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e));   \
+            return 1;                                                                                   \
+        }                                                                                               \
+        (ctx)->launches++;                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// Conv2D, fp32 CUDA-core implicit GEMM (shadertemplate_vk_conv2d.comp:148-347; 1x1: vk_conv2d_1x1.comp:68-211).
+//   M = N*OH*OW pixels, Ngemm = OC, K = k*k*IC with k index = (ky*k + kx)*IC + ic.
+// Block tile 64 pixels x 64 oc, K chunk 16, 128 threads, 4x8 outputs per thread.
+// A is gathered from the split-bf16 input (vector path when IC % 8 == 0, scalar otherwise), B is the packed
+// fp32 weight matrix [K][OCw] with BN folded. Epilogue: + bias (+ residual) -> activation -> split -> store.
+// ------------------------------------------------------------------------------------------------------------
+struct ConvKParams {
+    TV in, out, res;
+    const float* w;
+    const float* bias;
+    int ocw;
+    int k, stride, pad_x, pad_y, pad_mode, act;
+    float alpha;
+    int OH, OW, K;
+    int has_res;
+};
+
+constexpr int CV_BM = 64, CV_BN = 64, CV_BK = 16;
+
+__global__ void __launch_bounds__(128) conv2d_simt_kernel(const ConvKParams p) {
+    __shared__ __align__(16) float As[CV_BK][CV_BM + 4];
+    __shared__ __align__(16) float Bs[CV_BK][CV_BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 7, ty = tid >> 3; // 8 x 16
+    const long long M   = (long long) p.in.N * p.OH * p.OW;
+    const long long m0  = (long long) blockIdx.x * CV_BM;
+    const int oc0       = blockIdx.y * CV_BN;
+    const int IC        = p.in.C;
+
+    // the pixel this thread gathers A for
+    const int a_px  = tid & 63;
+    const int a_kh  = tid >> 6; // which half (8 k's) of the 16-wide chunk
+    const long long am = m0 + a_px;
+    const bool a_valid = am < M;
+    int an = 0, aoy = 0, aox = 0;
+    if (a_valid) {
+        an        = (int) (am / ((long long) p.OH * p.OW));
+        int rem   = (int) (am - (long long) an * p.OH * p.OW);
+        aoy       = rem / p.OW;
+        aox       = rem - aoy * p.OW;
+    }
+    const int iy0 = aoy * p.stride - p.pad_y, ix0 = aox * p.stride - p.pad_x;
+    const bool vec_path = (IC % 8) == 0;
+
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < p.K; k0 += CV_BK) {
+        // ---- A chunk: As[kk][pixel] ----
+        float av[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[j] = 0.0f;
+        const int kbase = k0 + a_kh * 8;
+        if (a_valid && kbase < p.K) {
+            if (vec_path) {
+                const int tap = kbase / IC, ic = kbase - tap * IC;
+                const int ky = tap / p.k, kx = tap - ky * p.k;
+                const int sy = src_coord(iy0 + ky, p.in.H, p.pad_mode), sx = src_coord(ix0 + kx, p.in.W, p.pad_mode);
+                if (sy >= 0 && sx >= 0) load8(p.in.hi, p.in.lo, (((size_t) an * p.in.H + sy) * p.in.W + sx) * p.in.Cp + ic, av);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int kk = kbase + j;
+                    if (kk < p.K) {
+                        const int tap = kk / IC, ic = kk - tap * IC;
+                        const int ky = tap / p.k, kx = tap - ky * p.k;
+                        const int sy = src_coord(iy0 + ky, p.in.H, p.pad_mode), sx = src_coord(ix0 + kx, p.in.W, p.pad_mode);
+                        if (sy >= 0 && sx >= 0) av[j] = load1(p.in.hi, p.in.lo, (((size_t) an * p.in.H + sy) * p.in.W + sx) * p.in.Cp + ic);
+                    }
+                }
+            }
+        }
+        // ---- B chunk: Bs[kk][oc] ----
+        float4 bv[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int idx = tid + r * 128;
+            const int row = idx >> 4, c4 = idx & 15;
+            const int kk = k0 + row;
+            bv[r]        = (kk < p.K) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t) kk * p.ocw + oc0) + c4) : make_float4(0, 0, 0, 0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) As[a_kh * 8 + j][a_px] = av[j];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int idx = tid + r * 128;
+            *reinterpret_cast<float4*>(&Bs[idx >> 4][(idx & 15) * 4]) = bv[r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CV_BK; ++kk) {
+            const float4 a  = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+            const float aa[4] = {a.x, a.y, a.z, a.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+    }
+
+    // ---- epilogue ----
+    const int oc = oc0 + tx * 8;
+    if (oc >= p.out.Cp) return;
+    float bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = p.bias[oc + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const size_t off = (size_t) m * p.out.Cp + oc;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = acc[i][j] + bias[j];
+        if (p.has_res) {
+            float r[8];
+            load8(p.res.hi, p.res.lo, off, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (oc + j < p.out.C) ? apply_act(v[j], p.act, p.alpha) : 0.0f;
+        store8(p.out.hi, p.out.lo, off, v);
+    }
+}
+
+int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a) {
+    ConvKParams p;
+    p.in      = view(a.in);
+    p.out     = view(a.out);
+    p.has_res = a.residual != nullptr;
+    p.res     = a.residual ? view(a.residual) : view(a.out);
+    p.w       = a.w->w_f32;
+    p.bias    = a.w->bias;
+    p.ocw     = a.w->ocw;
+    p.k = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y, p.pad_mode = a.pad_mode, p.act = a.act, p.alpha = a.alpha;
+    p.OH = a.out->h, p.OW = a.out->w;
+    p.K  = a.k * a.k * a.in->c;
+    const long long M = (long long) a.out->n * a.out->h * a.out->w;
+    dim3 grid((unsigned) ((M + CV_BM - 1) / CV_BM), (unsigned) ((a.out->cp + CV_BN - 1) / CV_BN));
+    conv2d_simt_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Depthwise k x k (shadertemplate_vk_depthwise.comp:64-139): window clipped to the input (== zero padding),
+// bias, folded BN, activation. One thread = 8 channels x DW_TX consecutive output columns; the k x (stride*(TX-1)+k)
+// input patch is streamed through registers row by row so every input vector is loaded once per thread.
+// Weights fp32 [k*k][Cp].
+// ------------------------------------------------------------------------------------------------------------
+struct DwParams {
+    TV in, out;
+    const float* w;
+    const float* bias;
+    int k, stride, pad_x, pad_y, act;
+    float alpha;
+};
+
+template <int K, int S, int TX>
+__global__ void __launch_bounds__(128) depthwise_kernel(const DwParams p) {
+    const int CG            = p.out.Cp >> 3;
+    const int strips        = (p.out.W + TX - 1) / TX;
+    const long long total   = (long long) p.out.N * p.out.H * strips * CG;
+    const long long gid     = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int cg    = (int) (gid % CG);
+    long long r     = gid / CG;
+    const int strip = (int) (r % strips);
+    r /= strips;
+    const int oy = (int) (r % p.out.H);
+    const int n  = (int) (r / p.out.H);
+    const int c  = cg * 8;
+    const int ox0 = strip * TX;
+
+    float wreg[K * K][8];
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (size_t) t * p.in.Cp + c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (size_t) t * p.in.Cp + c) + 1);
+        wreg[t][0] = w0.x, wreg[t][1] = w0.y, wreg[t][2] = w0.z, wreg[t][3] = w0.w;
+        wreg[t][4] = w1.x, wreg[t][5] = w1.y, wreg[t][6] = w1.z, wreg[t][7] = w1.w;
+    }
+    float acc[TX][8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + 1);
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+            acc[t][0] = b0.x, acc[t][1] = b0.y, acc[t][2] = b0.z, acc[t][3] = b0.w;
+            acc[t][4] = b1.x, acc[t][5] = b1.y, acc[t][6] = b1.z, acc[t][7] = b1.w;
+        }
+    }
+    constexpr int COLS = S * (TX - 1) + K;
+    const int ix0 = ox0 * S - p.pad_x, iy0 = oy * S - p.pad_y;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= p.in.H) continue;
+        const size_t rowoff = ((size_t) n * p.in.H + iy) * p.in.W;
+#pragma unroll
+        for (int cx = 0; cx < COLS; ++cx) {
+            const int ix = ix0 + cx;
+            if (ix < 0 || ix >= p.in.W) continue;
+            float v[8];
+            load8(p.in.hi, p.in.lo, (rowoff + ix) * p.in.Cp + c, v);
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+                const int kx = cx - t * S; // compile-time after unrolling
+                if (kx >= 0 && kx < K) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(wreg[ky * K + kx][j], v[j], acc[t][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TX; ++t) {
+        const int ox = ox0 + t;
+        if (ox >= p.out.W) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c + j < p.out.C) ? apply_act(acc[t][j], p.act, p.alpha) : 0.0f;
+        store8(p.out.hi, p.out.lo, (((size_t) n * p.out.H + oy) * p.out.W + ox) * p.out.Cp + c, v);
+    }
+}
+
+// generic (any k / stride): one thread = 8 channels x 1 output pixel
+__global__ void __launch_bounds__(128) depthwise_generic_kernel(const DwParams p) {
+    const int CG          = p.out.Cp >> 3;
+    const long long total = (long long) p.out.N * p.out.H * p.out.W * CG;
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int cg = (int) (gid % CG);
+    long long r  = gid / CG;
+    const int ox = (int) (r % p.out.W);
+    r /= p.out.W;
+    const int oy = (int) (r % p.out.H);
+    const int n  = (int) (r / p.out.H);
+    const int c  = cg * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = p.bias[c + j];
+    const int ix0 = ox * p.stride - p.pad_x, iy0 = oy * p.stride - p.pad_y;
+    for (int ky = 0; ky < p.k; ++ky) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= p.in.H) continue;
+        for (int kx = 0; kx < p.k; ++kx) {
+            const int ix = ix0 + kx;
+            if (ix < 0 || ix >= p.in.W) continue;
+            float v[8];
+            load8(p.in.hi, p.in.lo, (((size_t) n * p.in.H + iy) * p.in.W + ix) * p.in.Cp + c, v);
+            const float* wp = p.w + (size_t) (ky * p.k + kx) * p.in.Cp + c;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(__ldg(wp + j), v[j], acc[j]);
+        }
+    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < p.out.C) ? apply_act(acc[j], p.act, p.alpha) : 0.0f;
+    store8(p.out.hi, p.out.lo, (((size_t) n * p.out.H + oy) * p.out.W + ox) * p.out.Cp + c, v);
+}
+
+int launch_depthwise(snnb_context* ctx, const ConvArgs& a) {
+    DwParams p;
+    p.in = view(a.in), p.out = view(a.out);
+    p.w = a.w->w_f32, p.bias = a.w->bias;
+    p.k = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y, p.act = a.act, p.alpha = a.alpha;
+    const int CG = a.out->cp >> 3;
+    if (a.k == 3 && (a.stride == 1 || a.stride == 2)) {
+        constexpr int TX      = 4;
+        const int strips      = (a.out->w + TX - 1) / TX;
+        const long long total = (long long) a.out->n * a.out->h * strips * CG;
+        const unsigned blocks = (unsigned) ((total + 127) / 128);
+        if (a.stride == 1)
+            depthwise_kernel<3, 1, TX><<<blocks, 128, 0, ctx->stream>>>(p);
+        else
+            depthwise_kernel<3, 2, TX><<<blocks, 128, 0, ctx->stream>>>(p);
+    } else {
+        const long long total = (long long) a.out->n * a.out->h * a.out->w * CG;
+        depthwise_generic_kernel<<<(unsigned) ((total + 127) / 128), 128, 0, ctx->stream>>>(p);
+    }
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Max / average pooling (vk_maxpool2d.comp:42-71, vk_avgpool2d.comp:42-69): window origin o*stride (never padded
+// top/left, maxpool2dVulkan.cpp:57-60), taps clipped to the input, max starts at -100000, avg divides by the
+// number of valid taps. One thread = 8 channels x 1 output pixel.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int stride, int avg) {
+    const int CG          = out.Cp >> 3;
+    const long long total = (long long) out.N * out.H * out.W * CG;
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int cg = (int) (gid % CG);
+    long long r  = gid / CG;
+    const int ox = (int) (r % out.W);
+    r /= out.W;
+    const int oy = (int) (r % out.H);
+    const int n  = (int) (r / out.H);
+    const int c  = cg * 8;
+    const int sx = ox * stride, sy = oy * stride;
+    const int efx = min(k, in.W - sx), efy = min(k, in.H - sy);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = avg ? 0.0f : -100000.0f;
+    float num = 0.0f;
+    for (int fy = 0; fy < efy; ++fy)
+        for (int fx = 0; fx < efx; ++fx) {
+            float v[8];
+            load8(in.hi, in.lo, (((size_t) n * in.H + sy + fy) * in.W + sx + fx) * in.Cp + c, v);
+            if (avg) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                num += 1.0f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], v[j]);
+            }
+        }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < out.C) ? (avg ? acc[j] / num : acc[j]) : 0.0f;
+    store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
+}
+
+// Global average pool (AveragePooling2D with pool == H == W, stride 1, valid — how the converter emits GAP,
+// tools/convertTool/layers/supportedLayers/averagepooling2d.py:40-55): one warp per (n, 8-channel group).
+__global__ void __launch_bounds__(256) global_avgpool_kernel(TV in, TV out) {
+    const int CG   = out.Cp >> 3;
+    const int warp = (int) (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (warp >= in.N * CG) return;
+    const int n = warp / CG, c = (warp % CG) * 8;
+    const int HW = in.H * in.W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    // sequential-in-pixel-order partial sums per lane, then a fixed-shape tree: deterministic
+    for (int px = lane; px < HW; px += 32) {
+        float v[8];
+        load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (lane == 0) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c + j < out.C) ? acc[j] / (float) HW : 0.0f;
+        store8(out.hi, out.lo, (size_t) n * out.Cp + c, v);
+    }
+}
+
+int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int k, int stride, bool avg) {
+    TV vi = view(in), vo = view(out);
+    if (avg && out->h == 1 && out->w == 1 && k >= in->h && k >= in->w && in->h * in->w >= 16) {
+        const long long warps = (long long) in->n * (out->cp >> 3);
+        global_avgpool_kernel<<<(unsigned) ((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(vi, vo);
+    } else {
+        const long long total = (long long) out->n * out->h * out->w * (out->cp >> 3);
+        pool_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(vi, vo, k, stride, avg ? 1 : 0);
+    }
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Elementwise family, one thread = one 8-channel vector:
+//   add + act (vk_add.comp:41-90), BatchNormalization + act (vk_batchnorm.comp:54-69), activation
+//   (vk_activation.comp:41-85).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_kernel(TV a, TV b, TV out, int act, float alpha) {
+    const size_t total = (size_t) out.N * out.H * out.W * (out.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG = out.Cp >> 3;
+    const int c  = (int) (gid % CG) * 8;
+    float x[8], y[8];
+    load8(a.hi, a.lo, gid * 8, x);
+    load8(b.hi, b.lo, gid * 8, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (c + j < out.C) ? apply_act(x[j] + y[j], act, alpha) : 0.0f;
+    store8(out.hi, out.lo, gid * 8, x);
+}
+
+// BN exactly in the shader's order: s = max(sqrt(var + 1e-3), 1e-4); y = (gamma/s)*(x - mean) + beta.
+// mode 0: BN (scale = gamma/s precomputed on host as `gamma`), mode 1: activation only.
+__global__ void __launch_bounds__(256) chanwise_kernel(TV in, TV out, const float* __restrict__ scale, const float* __restrict__ mean,
+                                                         const float* __restrict__ beta, int mode, int act, float alpha) {
+    const size_t total = (size_t) out.N * out.H * out.W * (out.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG = out.Cp >> 3;
+    const int c  = (int) (gid % CG) * 8;
+    float x[8];
+    load8(in.hi, in.lo, gid * 8, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = x[j];
+        if (mode == 0) v = (__ldg(scale + c + j) * (v - __ldg(mean + c + j))) + __ldg(beta + c + j);
+        x[j] = (c + j < out.C) ? apply_act(v, act, alpha) : 0.0f;
+    }
+    store8(out.hi, out.lo, gid * 8, x);
+}
+
+static unsigned vec_blocks(const snnb_tensor* t, int threads) {
+    const size_t total = t->pixels() * (size_t) (t->cp >> 3);
+    return (unsigned) ((total + threads - 1) / threads);
+}
+
+int launch_add(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out, int act, float alpha) {
+    add_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(a), view(b), view(out), act, alpha);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha) {
+    chanwise_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), w->var /* = BN scale, see pack.cpp */, w->mean, w->beta, 0, act, alpha);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int act, float alpha) {
+    chanwise_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), nullptr, nullptr, nullptr, 1, act, alpha);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Softmax over channels, per pixel (cpulayer.h:175-191: max-subtracted, fp32). One warp per pixel.
+// Argmax over channels per image -> 0-based index of the FIRST maximum (core.cpp:228-233 adds 1 at the API).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) softmax_kernel(TV in, TV out) {
+    const long long px = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane     = threadIdx.x & 31;
+    if (px >= (long long) in.N * in.H * in.W) return;
+    const size_t base = (size_t) px * in.Cp;
+    float mx = -3.402823466e+38f;
+    for (int c = lane; c < in.C; c += 32) mx = fmaxf(mx, load1(in.hi, in.lo, base + c));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int c = lane; c < in.C; c += 32) sum += expf(load1(in.hi, in.lo, base + c) - mx);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int c = lane; c < out.Cp; c += 32) {
+        float v = (c < in.C) ? expf(load1(in.hi, in.lo, base + c) - mx) / sum : 0.0f;
+        store1(out.hi, out.lo, (size_t) px * out.Cp + c, v);
+    }
+}
+int launch_softmax(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out) {
+    const long long px = (long long) in->pixels();
+    softmax_kernel<<<(unsigned) ((px * 32 + 127) / 128), 128, 0, ctx->stream>>>(view(in), view(out));
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) argmax_kernel(TV in, int* __restrict__ idx) {
+    const int n    = (int) (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= in.N) return;
+    const size_t base = (size_t) n * in.H * in.W * in.Cp;
+    float best = -3.402823466e+38f;
+    int bi     = 0x7fffffff;
+    for (int c = lane; c < in.C; c += 32) {
+        float v = load1(in.hi, in.lo, base + c);
+        if (v > best) best = v, bi = c;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi   = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
+    }
+    if (lane == 0) idx[n] = bi;
+}
+int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx) {
+    argmax_kernel<<<(unsigned) (((long long) in->n * 32 + 127) / 128), 128, 0, ctx->stream>>>(view(in), dev_idx);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Layout ops (scalar-per-element kernels: rarely on the hot path).
+// ------------------------------------------------------------------------------------------------------------
+// Flatten, HWC order (cpulayer.h:94-115): out[n, (y*W + x)*C + c] = in[n,y,x,c]
+__global__ void flatten_kernel(TV in, TV out) {
+    const size_t total = (size_t) out.N * out.Cp;
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int n = (int) (gid / out.Cp), f = (int) (gid % out.Cp);
+    float v = 0.0f;
+    if (f < out.C) {
+        const int c = f % in.C, px = f / in.C;
+        v = load1(in.hi, in.lo, ((size_t) n * in.H * in.W + px) * in.Cp + c);
+    }
+    store1(out.hi, out.lo, gid, v);
+}
+int launch_flatten(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out) {
+    const size_t total = (size_t) out->n * out->cp;
+    flatten_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(view(in), view(out));
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Concatenate along channels (vk_concat.comp:39-52).
+__global__ void concat_kernel(TV a, TV b, TV out) {
+    const size_t total = (size_t) out.N * out.H * out.W * out.Cp;
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t px = gid / out.Cp;
+    const int c     = (int) (gid % out.Cp);
+    float v = 0.0f;
+    if (c < a.C)
+        v = load1(a.hi, a.lo, px * a.Cp + c);
+    else if (c < a.C + b.C)
+        v = load1(b.hi, b.lo, px * b.Cp + (c - a.C));
+    store1(out.hi, out.lo, gid, v);
+}
+int launch_concat(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out) {
+    const size_t total = out->pixels() * out->cp;
+    concat_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(view(a), view(b), view(out));
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// UpSampling2D (vk_upsampling2d_nearest.comp:43-64; vk_upsampling2d_bilinear.comp:43-86), 8-channel vectors.
+__global__ void upsample_kernel(TV in, TV out, float inv, int bilinear) {
+    const int CG          = out.Cp >> 3;
+    const long long total = (long long) out.N * out.H * out.W * CG;
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int c  = (int) (gid % CG) * 8;
+    long long r  = gid / CG;
+    const int ox = (int) (r % out.W);
+    r /= out.W;
+    const int oy = (int) (r % out.H);
+    const int n  = (int) (r / out.H);
+    float v[8];
+    if (!bilinear) {
+        const int x1 = min(max((int) floorf((float) ox * inv), 0), in.W - 1);
+        const int y1 = min(max((int) floorf((float) oy * inv), 0), in.H - 1);
+        load8(in.hi, in.lo, (((size_t) n * in.H + y1) * in.W + x1) * in.Cp + c, v);
+    } else {
+        const float offs = 0.5f - 0.5f * inv;
+        const float sx   = fminf(fmaxf((float) ox * inv - offs, 0.0f), (float) (in.W - 1));
+        const float sy   = fminf(fmaxf((float) oy * inv - offs, 0.0f), (float) (in.H - 1));
+        const int x11 = (int) floorf(sx), x12 = x11 + 1, y11 = (int) floorf(sy), y12 = y11 + 1;
+        const float w1 = ((float) x12 - sx) * ((float) y12 - sy), w2 = (sx - (float) x11) * ((float) y12 - sy);
+        const float w3 = (sx - (float) x11) * (sy - (float) y11), w4 = ((float) x12 - sx) * (sy - (float) y11);
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+        auto tap = [&](int xx, int yy, float wgt) {
+            if (xx < 0 || xx >= in.W || yy < 0 || yy >= in.H) return; // out-of-range texel reads 0
+            load8(in.hi, in.lo, (((size_t) n * in.H + yy) * in.W + xx) * in.Cp + c, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j] * wgt;
+        };
+        tap(x11, y11, w1);
+        tap(x12, y11, w2);
+        tap(x12, y12, w3);
+        tap(x11, y12, w4);
+    }
+    store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
+}
+int launch_upsample(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, float scale, bool bilinear) {
+    upsample_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), 1.0f / scale, bilinear ? 1 : 0);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Pad (vk_pad.comp:42-70): constant(0) / replicate / reflect.
+__global__ void pad_kernel(TV in, TV out, int pad_x, int pad_y, int mode) {
+    const int CG          = out.Cp >> 3;
+    const long long total = (long long) out.N * out.H * out.W * CG;
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int c  = (int) (gid % CG) * 8;
+    long long r  = gid / CG;
+    const int ox = (int) (r % out.W);
+    r /= out.W;
+    const int oy = (int) (r % out.H);
+    const int n  = (int) (r / out.H);
+    const int sx = src_coord(ox - pad_x, in.W, mode), sy = src_coord(oy - pad_y, in.H, mode);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (sx >= 0 && sy >= 0) load8(in.hi, in.lo, (((size_t) n * in.H + sy) * in.W + sx) * in.Cp + c, v);
+    store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
+}
+int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int pad_x, int pad_y, int mode) {
+    pad_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), pad_x, pad_y, mode);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// InstanceNorm (+act) (vk_instancenorm.comp:53-175): per (n, c) mean and biased variance over H*W, eps 1e-5.
+// Pass 1: one CTA per (n, 8-channel group): two-pass mean / variance in fp32 with a fixed reduction tree
+// (deterministic), stats -> global. Pass 2: elementwise normalise + act.
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(TV in, float* __restrict__ stats) {
+    __shared__ float red[8][8]; // [warp][channel]
+    __shared__ float meanv[8];
+    const int CG = in.Cp >> 3;
+    const int n = blockIdx.x / CG, c = (blockIdx.x % CG) * 8;
+    const int HW   = in.H * in.W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int px = threadIdx.x; px < HW; px += 256) {
+        float v[8];
+        load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if (lane == 0) red[warp][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        meanv[threadIdx.x] = s / (float) HW;
+    }
+    __syncthreads();
+    float mean[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean[j] = meanv[j], acc[j] = 0.0f;
+    for (int px = threadIdx.x; px < HW; px += 256) {
+        float v[8];
+        load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += (v[j] - mean[j]) * (v[j] - mean[j]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if (lane == 0) red[warp][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        const float var                                  = s / (float) HW;
+        stats[((size_t) n * in.Cp + c + threadIdx.x) * 2 + 0] = meanv[threadIdx.x];
+        stats[((size_t) n * in.Cp + c + threadIdx.x) * 2 + 1] = 1.0f / sqrtf(var + 0.00001f);
+    }
+}
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(TV in, TV out, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int act, float alpha) {
+    const int CG          = out.Cp >> 3;
+    const long long total = (long long) out.N * out.H * out.W * CG;
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int c = (int) (gid % CG) * 8;
+    const int n = (int) (gid / ((long long) out.H * out.W * CG));
+    float v[8];
+    load8(in.hi, in.lo, (size_t) gid * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float mean = stats[((size_t) n * in.Cp + c + j) * 2], rstd = stats[((size_t) n * in.Cp + c + j) * 2 + 1];
+        const float mul = __ldg(gamma + c + j) * rstd;
+        v[j]            = (c + j < out.C) ? apply_act((v[j] - mean) * mul + __ldg(beta + c + j), act, alpha) : 0.0f;
+    }
+    store8(out.hi, out.lo, (size_t) gid * 8, v);
+}
+int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, float* scratch) {
+    // scratch: n*cp*2 floats of (mean, rstd); the engine passes a model-owned buffer (stable under CUDA graphs)
+    float* stats = scratch;
+    if (!stats) {
+        const size_t stat_bytes = (size_t) in->n * in->cp * 2 * sizeof(float);
+        if (ensure_stage(ctx, stat_bytes)) return 1;
+        stats = ctx->stage_dev;
+    }
+    instnorm_stats_kernel<<<(unsigned) (in->n * (in->cp >> 3)), 256, 0, ctx->stream>>>(view(in), stats);
+    SNNB_LAUNCH_CHECK(ctx);
+    instnorm_apply_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), stats, w->gamma, w->beta, act, alpha);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Subpixel: depth_to_space(r) + tanh (vk_subpixel.comp:43-70; component = x%r + r*(y%r), fs_subpixel.glsl:41).
+__global__ void subpixel_kernel(TV in, TV out, int r) {
+    const long long total = (long long) out.N * out.H * out.W;
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int ox = (int) (gid % out.W);
+    long long q  = gid / out.W;
+    const int oy = (int) (q % out.H);
+    const int n  = (int) (q / out.H);
+    const int comp = (ox % r) + r * (oy % r);
+    const float v  = load1(in.hi, in.lo, (((size_t) n * in.H + oy / r) * in.W + ox / r) * in.Cp + comp);
+    float o[8];
+    o[0] = tanhf(v);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) o[j] = 0.0f;
+    store8(out.hi, out.lo, (size_t) gid * out.Cp, o); // out.C == 1, Cp == 8
+}
+int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int r) {
+    const long long total = (long long) out->pixels();
+    subpixel_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(view(in), view(out), r);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// API edge: fp32 NHWC (dense pitch C) <-> split-bf16 (pitch Cp).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void split_kernel(const float* __restrict__ src, TV t) {
+    const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG    = t.Cp >> 3;
+    const size_t px = gid / CG;
+    const int c     = (int) (gid % CG) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? __ldg(src + px * t.C + c + j) : 0.0f;
+    store8(t.hi, t.lo, gid * 8, v);
+}
+__global__ void merge_kernel(TV t, float* __restrict__ dst) {
+    const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG    = t.Cp >> 3;
+    const size_t px = gid / CG;
+    const int c     = (int) (gid % CG) * 8;
+    float v[8];
+    load8(t.hi, t.lo, gid * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (c + j < t.C) dst[px * t.C + c + j] = v[j];
+}
+int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t) {
+    split_kernel<<<vec_blocks(t, 256), 256, 0, ctx->stream>>>(dev_nhwc, view(t));
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc) {
+    merge_kernel<<<vec_blocks(t, 256), 256, 0, ctx->stream>>>(view(t), dev_nhwc);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+} // namespace snnb

@@ -1,0 +1,147 @@
+// Internal types shared by the C-ABI layer (capi.cpp), the host engine (engine/*.cpp) and the CUDA
+// kernels (kernels_*.cu). Not installed; the public surface is include/snnb.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "snnb.h"
+
+namespace snnb {
+
+// ---- error plumbing: status codes + thread-local message (never abort across the C-ABI) ----------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SNNB_CUDA_OK(expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            ::snnb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            return 1;                                                                                   \
+        }                                                                                               \
+    } while (0)
+
+#define SNNB_REQUIRE(cond, ...)          \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::snnb::set_error(__VA_ARGS__); \
+            return 2;                    \
+        }                                \
+    } while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+} // namespace snnb
+
+// ---- device storage -----------------------------------------------------------------------------------------
+// Activations: NHWC, channel pitch Cp = round_up(C, 8), stored as TWO bf16 planes:
+//     hi = bf16_rn(v),  lo = bf16_rn(v - hi)          (v ~ hi + lo to 2^-17 relative: "fp32-faithful")
+// Same 4 bytes/element of HBM traffic as fp32, but each plane is a K-major bf16 operand that TMA can
+// drop into shared memory for tcgen05.mma unmodified; the 3-term product hi*Whi + lo*Whi + hi*Wlo
+// restores ~16 bits of mantissa in the fp32 TMEM accumulator. Channels [C, Cp) are kept at zero.
+struct snnb_tensor {
+    snnb_context* ctx = nullptr;
+    __nv_bfloat16* hi = nullptr; // plane 0; plane 1 (lo) = hi + plane_elems
+    __nv_bfloat16* lo = nullptr;
+    int n = 0, h = 0, w = 0, c = 0, cp = 0;
+    size_t plane_elems = 0;      // n*h*w*cp rounded up to 64 elements (128 B)
+    bool owns = true;
+    size_t pixels() const { return (size_t) n * h * w; }
+};
+
+// Packed weights of one layer (device pointers; owned unless carved from a model arena).
+struct snnb_weights {
+    snnb_context* ctx = nullptr;
+    int kind = 0; // 1 conv, 2 depthwise, 3 dense(conv1x1), 4 channels
+    int in_ch = 0, out_ch = 0, kernel = 1;
+    // SIMT path: fp32 [K = k*k*IC][OCw], OCw = round_up(OC, 64); BN folded in.
+    float* w_f32 = nullptr;
+    int ocw = 0;
+    // tcgen05 path: bf16 hi/lo [OCr][Kp] K-major (k index = (ky*k+kx)*IC + ic), Kp = round_up(K, 8), OCr = round_up(OC, 16).
+    __nv_bfloat16* w_hi = nullptr;
+    __nv_bfloat16* w_lo = nullptr;
+    int kp = 0, ocr = 0;
+    // depthwise: fp32 [k*k][Cp]
+    // folded bias: fp32 [round_up(OC, 64)]
+    float* bias = nullptr;
+    // channel vectors (BatchNormalization / InstanceNorm): fp32 [Cp] each
+    float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
+    void* owned = nullptr; // single allocation backing all of the above (nullptr when arena-backed)
+    size_t bytes = 0;
+};
+
+struct snnb_context {
+    int device          = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count        = 148;
+    uint64_t launches   = 0;
+    // staging for upload/download (grown on demand)
+    float* stage_dev    = nullptr;
+    size_t stage_dev_bytes = 0;
+    float* stage_host   = nullptr; // pinned
+    size_t stage_host_bytes = 0;
+    void* tmap_encode_fn = nullptr; // cuTensorMapEncodeTiled, resolved lazily
+};
+
+struct snnb_timer {
+    snnb_context* ctx = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+namespace snnb {
+
+int ensure_stage(snnb_context* ctx, size_t bytes);
+
+// ---- kernel launchers (kernels_simt.cu) -------------------------------------------------------------------
+struct ConvArgs {
+    const snnb_tensor* in;
+    const snnb_tensor* residual; // nullable
+    snnb_tensor* out;
+    const snnb_weights* w;
+    int k, stride, pad_x, pad_y, pad_mode, act;
+    float alpha;
+};
+int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a);
+int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a); // kernels_umma.cu (tcgen05 + TMA)
+bool conv2d_umma_supported(const ConvArgs& a);
+int launch_depthwise(snnb_context* ctx, const ConvArgs& a);
+int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int k, int stride, bool avg);
+int launch_add(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out, int act, float alpha);
+int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha);
+int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int act, float alpha);
+int launch_softmax(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
+int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx);
+int launch_flatten(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
+int launch_concat(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out);
+int launch_upsample(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, float scale, bool bilinear);
+int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int pad_x, int pad_y, int mode);
+int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, float* scratch = nullptr);
+int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int r);
+int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t);       // fp32 NHWC (pitch C) -> hi/lo
+int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc);       // hi/lo -> fp32 NHWC (pitch C)
+
+// ---- host-side weight folding/packing (pack.cpp) -----------------------------------------------------------
+struct PackedHost {
+    std::vector<float> w_f32;           // [K][OCw]
+    std::vector<__nv_bfloat16> w_hi, w_lo; // [OCr][Kp]
+    std::vector<float> bias;            // [round_up(OC,64)]
+    std::vector<float> gamma, beta, mean, var;
+    int kind = 0, in_ch = 0, out_ch = 0, kernel = 1, ocw = 0, kp = 0, ocr = 0;
+    size_t device_bytes() const;
+};
+void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* bias, const float* g, const float* b, const float* m, const float* v,
+                      PackedHost& out);
+void pack_depthwise_host(int C, int k, const float* w_chw, const float* bias, const float* g, const float* b, const float* m, const float* v,
+                         PackedHost& out);
+void pack_channels_host(int C, const float* g, const float* b, const float* m, const float* v, PackedHost& out);
+// Copy a PackedHost into device memory at `base` (device, 256-B aligned) and point `w` at it. Returns bytes used.
+int place_weights(snnb_context* ctx, const PackedHost& p, char* base, snnb_weights* w);
+
+int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** out);
+
+} // namespace snnb

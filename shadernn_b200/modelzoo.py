@@ -1,0 +1,395 @@
+"""Writers of SNN JSON model files (the format core/src/ic2/modelparser.cpp reads).
+
+Every model JSON in the reference's modelzoo/ is a Git-LFS pointer stub, so the BASELINE configs are
+rebuilt here from the architecture files that DO exist (ncnn .param graphs, demo/modelInferenceESPCN.py) with
+deterministic synthetic weights. This is the writer side of the format, i.e. what tools/convertTool emits
+(h5ToJsonConverter.py:101-114,168-190): either one JSON with embedded weight arrays, or `<model>_layers.json` +
+`<model>_weights.bin` (raw LE fp32 in layer order: kernel, bias (if useBias), gamma, beta, mean, var (if BN)).
+
+Layer dict conventions == the JSON keys; weights live under the private key "_w" until written.
+"""
+import json
+import os
+
+import numpy as np
+
+SEED = 7767517  # the seed every reference op test uses (demo/test/unittest/convolutionTest.cpp:417)
+
+
+class Builder:
+    def __init__(self, seed=SEED):
+        self.layers = []
+        self.rng = np.random.default_rng(seed)
+
+    # -- synthetic weight distributions: He-normal kernels, small biases, BN near identity --
+    def _kernel(self, oc, ic, k, gain=2.0):
+        std = np.sqrt(gain / (k * k * ic))
+        return (self.rng.standard_normal((oc, ic, k, k)) * std).astype(np.float32)
+
+    def _bias(self, c):
+        return self.rng.uniform(-0.1, 0.1, c).astype(np.float32)
+
+    def _bn(self, c):
+        return {
+            "gamma": self.rng.uniform(0.5, 1.5, c).astype(np.float32),
+            "beta": self.rng.uniform(-0.1, 0.1, c).astype(np.float32),
+            "moving_mean": self.rng.uniform(-0.1, 0.1, c).astype(np.float32),
+            "moving_variance": self.rng.uniform(0.5, 1.5, c).astype(np.float32),
+        }
+
+    def _add(self, d, inputs):
+        d["numInputs"] = len(inputs)
+        d["inputId"] = list(inputs)
+        self.layers.append(d)
+        return len(self.layers) - 1
+
+    def planes(self, i):
+        return self.layers[i]["outputPlanes"]
+
+    def input(self, w, h, c, index=0):
+        return self._add({"type": "InputLayer", "name": "input_%d" % (index + 1), "Input Width": w, "Input Height": h, "outputPlanes": c,
+                          "inputPlanes": c, "inputIndex": index}, [])
+
+    def conv(self, x, oc, k, stride=1, padding="same", activation="linear", bias=True, bn=False, alpha=None, mode=None, gain=2.0):
+        ic = self.planes(x)
+        d = {"type": "Conv2D", "name": "conv2d_%d" % len(self.layers), "inputPlanes": ic, "outputPlanes": oc, "kernel_size": k, "strides": stride,
+             "padding": padding, "activation": activation, "useBias": "True" if bias else "False",
+             "useBatchNormalization": "True" if bn else "False"}
+        if mode is not None:
+            d["mode"] = mode
+        if activation == "leakyRelu":
+            d["leakyReluAlpha"] = 0.1 if alpha is None else alpha
+        w = {"kernel": self._kernel(oc, ic, k, gain)}
+        if bias:
+            w["bias"] = self._bias(oc)
+        d["_w"] = w
+        if bn:
+            d["_bn"] = self._bn(oc)
+        return self._add(d, [x])
+
+    def depthwise(self, x, k=3, stride=1, padding="same", activation="linear", bias=False, bn=True):
+        c = self.planes(x)
+        d = {"type": "DepthwiseConv2D", "name": "depthwise_conv2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c, "kernel_size": k,
+             "strides": stride, "padding": padding, "activation": activation, "useBias": "True" if bias else "False",
+             "useBatchNormalization": "True" if bn else "False"}
+        std = np.sqrt(2.0 / (k * k))
+        w = {"kernel_chw": (self.rng.standard_normal((c, k, k)) * std).astype(np.float32)}  # canonical [C][kh][kw]
+        if bias:
+            w["bias"] = self._bias(c)
+        d["_w"] = w
+        if bn:
+            d["_bn"] = self._bn(c)
+        return self._add(d, [x])
+
+    def maxpool(self, x, k, stride=None, padding="valid"):
+        c = self.planes(x)
+        return self._add({"type": "MaxPooling2D", "name": "max_pooling2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c, "pool": [k, k],
+                          "strides": stride if stride is not None else k, "padding": padding}, [x])
+
+    def avgpool(self, x, k, stride=None, padding="valid"):
+        c = self.planes(x)
+        return self._add({"type": "AveragePooling2D", "name": "average_pooling2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c,
+                          "pool_size": [k, k], "stride": stride if stride is not None else k, "padding": padding}, [x])
+
+    def add(self, a, b, activation="linear"):
+        c = self.planes(a)
+        return self._add({"type": "Add", "name": "add_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c, "activation": activation}, [a, b])
+
+    def flatten(self, x, planes):
+        return self._add({"type": "Flatten", "name": "flatten", "inputPlanes": self.planes(x), "outputPlanes": planes}, [x])
+
+    def dense(self, x, n_in, units, activation="softmax", bias=True):
+        std = np.sqrt(1.0 / n_in)
+        w = {"kernel": (self.rng.standard_normal((units, n_in)) * std).astype(np.float32)}  # [out][in] (cpulayer.h:162)
+        if bias:
+            w["bias"] = self._bias(units)
+        return self._add({"type": "Dense", "name": "dense", "inputPlanes": n_in, "outputPlanes": units, "units": units, "activation": activation,
+                          "useBias": "True" if bias else "False", "_w": w}, [x])
+
+    def pad(self, x, t, b, l, r, mode=None):
+        c = self.planes(x)
+        d = {"type": "ZeroPadding2D", "name": "zero_padding2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c, "padding": [[t, b], [l, r]]}
+        if mode:
+            d["mode"] = mode
+        return self._add(d, [x])
+
+    def upsample(self, x, scale=2, interpolation="nearest"):
+        c = self.planes(x)
+        return self._add({"type": "UpSampling2D", "name": "up_sampling2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c, "scaleFactor": scale,
+                          "interpolation": interpolation}, [x])
+
+    def concat(self, a, b):
+        c = self.planes(a) + self.planes(b)
+        return self._add({"type": "Concatenate", "name": "concatenate_%d" % len(self.layers), "inputPlanes": self.planes(a), "outputPlanes": c}, [a, b])
+
+    def instancenorm(self, x, activation="linear"):
+        c = self.planes(x)
+        w = {"scale": self.rng.uniform(0.5, 1.5, c).astype(np.float32), "bias": self.rng.uniform(-0.1, 0.1, c).astype(np.float32)}
+        return self._add({"type": "InstanceNormalization", "name": "instance_norm_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c,
+                          "epsilon": 1e-5, "activation": activation, "_w": w}, [x])
+
+    def batchnorm(self, x, activation="linear"):
+        c = self.planes(x)
+        return self._add({"type": "BatchNormalization", "name": "batch_normalization_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c,
+                          "activation": activation, "_bn": self._bn(c)}, [x])
+
+    def subpixel(self, x, r=2):
+        return self._add({"type": "Lambda", "name": "subpixel", "inputPlanes": self.planes(x), "outputPlanes": 1, "kernel_size": r}, [x])
+
+    def yolo(self, a, b):
+        return self._add({"type": "YOLO", "name": "yolo", "inputPlanes": self.planes(a), "outputPlanes": 6}, [a, b])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# writers
+# ----------------------------------------------------------------------------------------------------------------
+def _tolist(a):
+    return [float(v) for v in np.asarray(a, dtype=np.float32).ravel()]
+
+
+def write_model(layers, path, split=False):
+    """Write `layers` to `path` (JSON). split=True streams the weights to `<stem>_weights.bin` next to it
+    (tools/convertTool onnxToJsonConverter.py:69-73 naming) and names it in numLayers.bin_file_name."""
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    root = {"numLayers": {"count": len(layers)}}
+    binf = None
+    if split:
+        stem = os.path.basename(path)
+        stem = stem[:-len("_layers.json")] if stem.endswith("_layers.json") else os.path.splitext(stem)[0]
+        bin_name = stem + "_weights.bin"
+        root["numLayers"]["bin_file_name"] = bin_name
+        binf = open(os.path.join(os.path.dirname(os.path.abspath(path)), bin_name), "wb")
+
+    def put(arr):
+        binf.write(np.ascontiguousarray(arr, dtype="<f4").tobytes())
+
+    for i, l in enumerate(layers):
+        d = {k: v for k, v in l.items() if not k.startswith("_")}
+        w = l.get("_w")
+        bn = l.get("_bn")
+        t = l["type"]
+        if t == "Conv2D":
+            if split:
+                put(w["kernel"])  # OIHW (modelparser.cpp:621-637)
+                if "bias" in w:
+                    put(w["bias"])
+                d["weights"] = {}
+            else:
+                d["weights"] = {"kernel": _tolist(w["kernel"])}
+                if "bias" in w:
+                    d["weights"]["bias"] = _tolist(w["bias"])
+        elif t in ("DepthwiseConv2D", "Depthwise", "SeparableConv2D"):
+            chw = w["kernel_chw"]
+            if split:
+                put(chw)  # .bin variant is [C][kh][kw] (modelparser.cpp:827-840)
+                if "bias" in w:
+                    put(w["bias"])
+                d["weights"] = {}
+            else:
+                c, k, _ = chw.shape
+                d["weights"] = {"kernel": _tolist(chw.reshape(c, k * k).T)}  # JSON flat = [kh*kw][C] (modelparser.cpp:843-850)
+                if "bias" in w:
+                    d["weights"]["bias"] = _tolist(w["bias"])
+        elif t == "Dense":
+            if split:
+                put(w["kernel"])
+                if "bias" in w:
+                    put(w["bias"])
+                d["weights"] = {}
+            else:
+                d["weights"] = {"kernel": _tolist(w["kernel"])}
+                if "bias" in w:
+                    d["weights"]["bias"] = _tolist(w["bias"])
+        elif t in ("InstanceNormalization", "InstanceNorm"):
+            d["weights"] = {"scale": _tolist(w["scale"]), "bias": _tolist(w["bias"])}  # always embedded (modelparser.cpp:1166-1185)
+        if bn is not None:
+            if split and t != "BatchNormalization":
+                for key in ("gamma", "beta", "moving_mean", "moving_variance"):  # modelparser.cpp:694-726
+                    put(bn[key])
+                d["batchNormalization"] = {}
+            else:
+                d["batchNormalization"] = {k: _tolist(v) for k, v in bn.items()}
+        root["Layer_%d" % i] = d
+    if binf:
+        binf.close()
+    with open(path, "w") as f:
+        json.dump(root, f)
+    return path
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the BASELINE.json configurations
+# ----------------------------------------------------------------------------------------------------------------
+def resnet18(input_hw=(224, 224), classes=10, seed=SEED):
+    """modelzoo/Resnet18/resnet18_cifar10_0223.param: Keras CIFAR variant — bias on every conv, the
+    first block's first conv has no BN/ReLU, 1x1-s2 shortcuts with bias and no BN, Add then ReLU; at 224x224 the
+    trailing AveragePooling2D(1,1) becomes the 7x7 global pool so Dense(512->classes) type-checks."""
+    b = Builder(seed)
+    h, w = input_hw
+    x = b.input(w, h, 3)
+    x = b.conv(x, 64, 7, 2, "same", "relu", bias=True, bn=True)
+    x = b.maxpool(x, 3, 2, "same")
+    # stage 1
+    y = b.conv(x, 64, 3, 1, "same", "linear", bias=True, bn=False)
+    y = b.conv(y, 64, 3, 1, "same", "linear", bias=True, bn=True)
+    x = b.add(y, x, "relu")
+    y = b.conv(x, 64, 3, 1, "same", "relu", bias=True, bn=True)
+    y = b.conv(y, 64, 3, 1, "same", "linear", bias=True, bn=True)
+    x = b.add(y, x, "relu")
+    for oc in (128, 256, 512):
+        y = b.conv(x, oc, 3, 2, "same", "relu", bias=True, bn=True)
+        y = b.conv(y, oc, 3, 1, "same", "linear", bias=True, bn=True)
+        s = b.conv(x, oc, 1, 2, "valid", "linear", bias=True, bn=False)
+        x = b.add(s, y, "relu")
+        y = b.conv(x, oc, 3, 1, "same", "relu", bias=True, bn=True)
+        y = b.conv(y, oc, 3, 1, "same", "linear", bias=True, bn=True)
+        x = b.add(y, x, "relu")
+    final = max(1, h // 32)
+    x = b.avgpool(x, final, 1, "valid")
+    x = b.flatten(x, 512)
+    x = b.dense(x, 512, classes, "softmax")
+    return b.layers
+
+
+def mobilenetv2(input_hw=(224, 224), classes=1000, seed=SEED):
+    """modelzoo/MobileNetV2/mobilenetV2.param (Keras, alpha=1): 3x3-s2 stem, 17 inverted-residual blocks (1x1 expand +BN
+    +ReLU6 -> dw3x3 +BN +ReLU6 -> 1x1 project +BN), stride-2 depthwise behind ZeroPadding2D((0,1),(0,1)) + valid, 10
+    residual adds, 1x1 320->1280 +BN +ReLU6, global average pool, classifier."""
+    b = Builder(seed)
+    h, w = input_hw
+    x = b.input(w, h, 3)
+    x = b.pad(x, 0, 1, 0, 1)
+    x = b.conv(x, 32, 3, 2, "valid", "relu6", bias=False, bn=True)
+    cfg = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+    cin = 32
+    first = True
+    for t, c, n, s in cfg:
+        for i in range(n):
+            stride = s if i == 0 else 1
+            inp = x
+            # the reference graph keeps a 1x1 32->32 "expand" in the very first block (mobilenetV2.param conv2d_1)
+            y = b.conv(x, cin * t if not first else cin, 1, 1, "valid", "relu6", bias=False, bn=True)
+            first = False
+            if stride == 2:
+                y = b.pad(y, 0, 1, 0, 1)
+                y = b.depthwise(y, 3, 2, "valid", "relu6", bias=False, bn=True)
+            else:
+                y = b.depthwise(y, 3, 1, "same", "relu6", bias=False, bn=True)
+            y = b.conv(y, c, 1, 1, "valid", "linear", bias=False, bn=True, gain=1.0)
+            x = b.add(y, inp, "linear") if (stride == 1 and cin == c) else y
+            cin = c
+    x = b.conv(x, 1280, 1, 1, "valid", "relu6", bias=False, bn=True)
+    x = b.avgpool(x, max(1, h // 32), 1, "valid")
+    x = b.flatten(x, 1280)
+    x = b.dense(x, 1280, classes, "softmax")
+    return b.layers
+
+
+def yolov3_tiny(input_hw=(416, 416), head_channels=18, seed=SEED):
+    """modelzoo/Yolov3-tiny/yolov3-tiny_finetuned.param: 3x3 conv +BN +LeakyReLU(0.1) x7 with 2x2-s2 max pools (the last
+    pool is 2x2 stride 1 'same'), 1x1 heads (bias, linear), nearest x2 upsample, concat(128 + 256), YOLO decode over the
+    two heads. head_channels = 3*(5+classes): 18 for the 1-class decode the reference hard-codes (yololayer.cpp:31-38),
+    255 for the COCO heads of the .param file."""
+    b = Builder(seed)
+    h, w = input_hw
+    x = b.input(w, h, 3)
+
+    def cbl(x, oc, k):
+        return b.conv(x, oc, k, 1, "same" if k > 1 else "valid", "leakyRelu", bias=False, bn=True, alpha=0.1)
+
+    x = cbl(x, 16, 3)
+    x = b.maxpool(x, 2, 2, "valid")
+    x = cbl(x, 32, 3)
+    x = b.maxpool(x, 2, 2, "valid")
+    x = cbl(x, 64, 3)
+    x = b.maxpool(x, 2, 2, "valid")
+    x = cbl(x, 128, 3)
+    x = b.maxpool(x, 2, 2, "valid")
+    route_a = cbl(x, 256, 3)
+    x = b.maxpool(route_a, 2, 2, "valid")
+    x = cbl(x, 512, 3)
+    x = b.maxpool(x, 2, 1, "same")
+    x = cbl(x, 1024, 3)
+    route_b = cbl(x, 256, 1)
+    y = cbl(route_b, 512, 3)
+    head13 = b.conv(y, head_channels, 1, 1, "valid", "linear", bias=True, bn=False, gain=1.0)
+    z = cbl(route_b, 128, 1)
+    z = b.upsample(z, 2, "nearest")
+    z = b.concat(z, route_a)
+    z = cbl(z, 256, 3)
+    head26 = b.conv(z, head_channels, 1, 1, "valid", "linear", bias=True, bn=False, gain=1.0)
+    b.yolo(head13, head26)
+    return b.layers
+
+
+def candy(input_hw=(720, 720), seed=SEED):
+    """modelzoo/StyleTransfer/candy-9_simplified-opt.param topology (fast-neural-style): reflect-pad + conv9x9(3->32) ->
+    IN+ReLU -> [reflect-pad + conv3x3 s2] x2 (64, 128) -> 5 residual blocks (pad, conv3x3, IN, ReLU, pad, conv3x3, IN, add)
+    -> [nearest x2, pad, conv3x3, IN, ReLU] x2 (64, 32) -> pad + conv9x9(32->3). Synthetic weights (the real ONNX weights
+    are a next-round item)."""
+    b = Builder(seed)
+    h, w = input_hw
+    x = b.input(w, h, 3)
+
+    def pconv(x, oc, k, stride):
+        p = k // 2
+        x = b.pad(x, p, p, p, p, mode="reflect")
+        return b.conv(x, oc, k, stride, "valid", "linear", bias=True, bn=False, gain=1.0)
+
+    x = b.instancenorm(pconv(x, 32, 9, 1), "relu")
+    x = b.instancenorm(pconv(x, 64, 3, 2), "relu")
+    x = b.instancenorm(pconv(x, 128, 3, 2), "relu")
+    for _ in range(5):
+        y = b.instancenorm(pconv(x, 128, 3, 1), "relu")
+        y = b.instancenorm(pconv(y, 128, 3, 1), "linear")
+        x = b.add(y, x, "linear")
+    x = b.upsample(x, 2, "nearest")
+    x = b.instancenorm(pconv(x, 64, 3, 1), "relu")
+    x = b.upsample(x, 2, "nearest")
+    x = b.instancenorm(pconv(x, 32, 3, 1), "relu")
+    x = pconv(x, 3, 9, 1)
+    return b.layers
+
+
+def espcn(input_hw=(224, 224), seed=SEED):
+    """demo/modelInferenceESPCN.py:49-71: conv5x5(1->16, relu) -> conv3x3(16->16, relu) -> conv3x3(16->4) ->
+    depth_to_space(2) -> tanh (the Subpixel layer applies tanh itself, vk_subpixel.comp:64-66)."""
+    b = Builder(seed)
+    h, w = input_hw
+    x = b.input(w, h, 1)
+    x = b.conv(x, 16, 5, 1, "same", "relu", bias=True)
+    x = b.conv(x, 16, 3, 1, "same", "relu", bias=True)
+    x = b.conv(x, 4, 3, 1, "same", "linear", bias=True)
+    x = b.subpixel(x, 2)
+    return b.layers
+
+
+MODELS = {
+    "espcn": (espcn, (224, 224), 1, (0.0, 1.0)),
+    "resnet18": (resnet18, (224, 224), 3, (-1.0, 1.0)),
+    "mobilenetv2": (mobilenetv2, (224, 224), 3, (0.0, 1.0)),
+    "yolov3tiny": (yolov3_tiny, (416, 416), 3, (-1.0, 1.0)),
+    "candy": (candy, (720, 720), 3, (0.0, 255.0)),
+}
+
+
+def build(name, out_dir, input_hw=None, split=None, **kw):
+    """Generate model `name` under out_dir; returns (json_path, layers). Large models default to the split
+    (.json + _weights.bin) variant; ESPCN embeds its weights so both reader paths are exercised."""
+    fn, hw, _, _ = MODELS[name]
+    hw = tuple(input_hw) if input_hw else hw
+    layers = fn(hw, **kw)
+    if split is None:
+        split = name != "espcn"
+    fname = "%s_%dx%d%s.json" % (name, hw[0], hw[1], "_layers" if split else "")
+    path = os.path.join(out_dir, fname)
+    write_model(layers, path, split=split)
+    return path, layers
+
+
+def synthetic_input(name, batch, input_hw=None, seed=SEED):
+    """Images uniform in the model's normalised range (constants of demo/common/modelInference.cpp)."""
+    _, hw, c, (lo, hi) = MODELS[name]
+    hw = tuple(input_hw) if input_hw else hw
+    rng = np.random.default_rng(seed + 1)
+    return rng.uniform(lo, hi, (batch, hw[0], hw[1], c)).astype(np.float32)
