@@ -159,7 +159,49 @@ int orc_conv2d(const float* x, int N, int H, int W, int IC, const float* w, cons
                     for (int o = 0; o < OC; ++o) acc[o] = bias ? bias[o] : 0.0f;
                     if (acc_double)
                         for (int o = 0; o < OC; ++o) accd[o] = acc[o];
-                    for (int ky = 0; ky < k; ++ky) {
+                    if (!acc_double) {
+                        // fp32 path, blocked over 16 output channels so the accumulators stay in registers; every output
+                        // channel still sums bias, then (ky, kx, ic) in the shader's order.
+                        constexpr int OB = 16;
+                        int sxs[16], sys_[16];
+                        const bool small_k = k <= 16;
+                        if (small_k)
+                            for (int t = 0; t < k; ++t) {
+                                sys_[t] = orc_src_coord(oy * stride - pad_y + t, H, pad_mode);
+                                sxs[t]  = orc_src_coord(ox * stride - pad_x + t, W, pad_mode);
+                            }
+                        for (int ob = 0; ob < OC; ob += OB) {
+                            const int nb = std::min(OB, OC - ob);
+                            float a[OB];
+                            for (int j = 0; j < OB; ++j) a[j] = j < nb ? acc[ob + j] : 0.0f;
+                            for (int ky = 0; ky < k; ++ky) {
+                                const int sy = small_k ? sys_[ky] : orc_src_coord(oy * stride - pad_y + ky, H, pad_mode);
+                                if (sy < 0) continue;
+                                for (int kx = 0; kx < k; ++kx) {
+                                    const int sx = small_k ? sxs[kx] : orc_src_coord(ox * stride - pad_x + kx, W, pad_mode);
+                                    if (sx < 0) continue;
+                                    const float* xp = x + (((size_t) n * H + sy) * W + sx) * IC;
+                                    const float* wk = wp.data() + ((size_t) ky * k + kx) * IC * OC + ob;
+                                    if (nb == OB) {
+                                        for (int i = 0; i < IC; ++i) {
+                                            const float xv  = xp[i];
+                                            const float* wr = wk + (size_t) i * OC;
+#pragma omp simd
+                                            for (int j = 0; j < OB; ++j) a[j] += wr[j] * xv;
+                                        }
+                                    } else {
+                                        for (int i = 0; i < IC; ++i) {
+                                            const float xv  = xp[i];
+                                            const float* wr = wk + (size_t) i * OC;
+                                            for (int j = 0; j < nb; ++j) a[j] += wr[j] * xv;
+                                        }
+                                    }
+                                }
+                            }
+                            for (int j = 0; j < nb; ++j) acc[ob + j] = a[j];
+                        }
+                    }
+                    for (int ky = 0; acc_double && ky < k; ++ky) {
                         int sy = orc_src_coord(oy * stride - pad_y + ky, H, pad_mode);
                         if (sy < 0) continue;
                         for (int kx = 0; kx < k; ++kx) {

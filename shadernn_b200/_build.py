@@ -87,14 +87,5 @@ def build(verbose=False, force=False):
     return LIB
 
 
-def build_oracle():
-    """Build the parity oracle (test infrastructure) and, when /root/reference is present, oracle/_ref."""
-    odir = os.path.join(ROOT, "oracle")
-    r = subprocess.run(["make", "-C", odir, "all"], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("oracle build failed:\n%s\n%s" % (r.stdout[-4000:], r.stderr[-4000:]))
-    return os.path.join(odir, "libsnn_oracle.so")
-
-
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

@@ -20,7 +20,8 @@ def built():
         _build.build()
     from oracle import oracle
     if not os.path.exists(oracle.LIB_PATH):
-        _build.build_oracle()
+        import __graft_entry__
+        __graft_entry__.build_checker()
     return True
 
 
