@@ -415,7 +415,8 @@ class Model:
         if t in ("MaxPooling2D", "AveragePooling2D"):
             pool = l.get("pool", l.get("pool_size"))
             k = int(pool[0] if isinstance(pool, list) else pool)
-            s = l.get("stride", l.get("strides", k))
+            # max pool reads "stride" or "strides"; avg pool ONLY "stride" (modelparser.cpp:312-335 vs :385-391)
+            s = l.get("stride", l.get("strides", k)) if t == "MaxPooling2D" else l.get("stride", k)
             s = int(s[0] if isinstance(s, list) else s)
             pd = l.get("padding")
             pstr = str(int(pd)) if isinstance(pd, (int, float)) else (pd if isinstance(pd, str) else str(int(pd[0][0] if isinstance(pd[0], list) else pd[0])))

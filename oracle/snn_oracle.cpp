@@ -78,7 +78,10 @@ static inline float orc_bn(float v, const float* bn, int C, int c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Output-dimension rules (float math then truncation, genericlayer.cpp:64-90).
+// Output-dimension rules (float math then truncation, genericlayer.cpp:64-90). NB the reference accumulates the
+// translation with std::max starting from 0 (genericlayer.cpp:66,73,75), so a NEGATIVE translation is clamped to 0:
+// a "valid" 3x3 stride-1 conv keeps its input size (the extra columns read out of range = 0), and a global average
+// pool only collapses to 1x1 because the avg-pool reader defaults stride to the pool size (modelparser.cpp:385-391).
 // ---------------------------------------------------------------------------------------------
 // Conv2D: conv2d.cpp:102-113. offsets = {T,B,L,R}; the translation uses offset[0]+offset[1] for BOTH axes.
 int orc_conv_out_dim(int in, int k, int stride, int padT, int padB) {
@@ -89,7 +92,7 @@ int orc_conv_out_dim(int in, int k, int stride, int padT, int padB) {
     } else {
         translation = 1 + (static_cast<float>(padT + padB - 1) - static_cast<float>(k)) / static_cast<float>(stride);
     }
-    float v = scale * in + translation;
+    float v = scale * in + std::max(0.0f, translation);
     return (int) (uint32_t) v;
 }
 // Depthwise: separableconvolution.cpp:77-86 — integer math; width uses T+L, height uses B+R.
@@ -102,7 +105,7 @@ int orc_pool_out_dim(int in, int k, int stride, int valid_like) {
         translation = 1.0f - (static_cast<float>(k) / static_cast<float>(stride));
     else
         translation = 1.0f - 1.0f / static_cast<float>(stride);
-    float v = scale * in + translation;
+    float v = scale * in + std::max(0.0f, translation);
     return (int) (uint32_t) v;
 }
 // "same"/"valid" -> offsets {T,B,L,R}: conv2d.cpp:39-74 (even k: top/left = k/2-1).

@@ -11,7 +11,9 @@ using namespace snnb;
 namespace snn {
 namespace dp {
 
-// genericlayer.cpp:64-90
+// genericlayer.cpp:64-90. The accumulators start at 0 and are combined with std::max, exactly as in the reference: a
+// negative translation (e.g. a "valid" 3x3 stride-1 conv: 1 - 3 = -2) is therefore clamped to 0 and the layer keeps
+// its input size. Kept on purpose - it decides tensor shapes a reference user's downstream code depends on.
 void GenericModelLayer::getOutputDims(uint32_t& width, uint32_t& height, uint32_t& depth) const {
     width = height = depth = 0U;
     float accSW = 0, accSH = 0, accTW = 0, accTH = 0;

@@ -270,10 +270,11 @@ void PoolDesc::parseAvg(ModelParser& parser, int layerId) { // modelparser.cpp:3
     if (!pool) pool = l.find("pool_size");
     if (!pool) throw std::runtime_error("missing key 'pool'/'pool_size'");
     kernelSize = numberOrFirst(*pool);
+    // Only "stride" is read here; the converter's "strides" key is ignored and the stride then defaults to the pool
+    // size (modelparser.cpp:385-391) - which is what turns the converter's global pool (pool_size=[H,H], strides=[1,1],
+    // averagepooling2d.py:40-55) into a 1x1 output.
     if (l.has("stride"))
         stride = numberOrFirst(l.at("stride"));
-    else if (l.has("strides")) // the reader only knows "stride"; accept the max-pool spelling too
-        stride = numberOrFirst(l.at("strides"));
     else
         stride = kernelSize;
     const json::Value& p = l.at("padding");

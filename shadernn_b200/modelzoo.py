@@ -91,6 +91,13 @@ class Builder:
         return self._add({"type": "AveragePooling2D", "name": "average_pooling2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c,
                           "pool_size": [k, k], "stride": stride if stride is not None else k, "padding": padding}, [x])
 
+    def global_avgpool(self, x, size):
+        """What the converter emits for a global pool (averagepooling2d.py:40-55): pool_size=[H,H], strides=[1,1], valid.
+        The reader ignores "strides" for average pools, so the stride defaults to the pool size -> 1x1 output."""
+        c = self.planes(x)
+        return self._add({"type": "AveragePooling2D", "name": "global_average_pooling2d_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c,
+                          "pool_size": [size, size], "strides": [1, 1], "padding": "valid"}, [x])
+
     def add(self, a, b, activation="linear"):
         c = self.planes(a)
         return self._add({"type": "Add", "name": "add_%d" % len(self.layers), "inputPlanes": c, "outputPlanes": c, "activation": activation}, [a, b])
@@ -244,8 +251,7 @@ def resnet18(input_hw=(224, 224), classes=10, seed=SEED):
         y = b.conv(x, oc, 3, 1, "same", "relu", bias=True, bn=True)
         y = b.conv(y, oc, 3, 1, "same", "linear", bias=True, bn=True)
         x = b.add(y, x, "relu")
-    final = max(1, h // 32)
-    x = b.avgpool(x, final, 1, "valid")
+    x = b.global_avgpool(x, max(1, h // 32))
     x = b.flatten(x, 512)
     x = b.dense(x, 512, classes, "softmax")
     return b.layers
@@ -279,7 +285,7 @@ def mobilenetv2(input_hw=(224, 224), classes=1000, seed=SEED):
             x = b.add(y, inp, "linear") if (stride == 1 and cin == c) else y
             cin = c
     x = b.conv(x, 1280, 1, 1, "valid", "relu6", bias=False, bn=True)
-    x = b.avgpool(x, max(1, h // 32), 1, "valid")
+    x = b.global_avgpool(x, max(1, h // 32))
     x = b.flatten(x, 1280)
     x = b.dense(x, 1280, classes, "softmax")
     return b.layers

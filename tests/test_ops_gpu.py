@@ -137,7 +137,7 @@ def test_pooling_reference_grid(ctx):
         assert np.array_equal(got, want)  # sentinels are exactly representable
 
 
-@pytest.mark.parametrize("h,w,c,k,s,valid", [(112, 112, 64, 3, 2, False), (13, 13, 512, 2, 1, False), (26, 26, 256, 2, 2, True), (7, 7, 1280, 7, 1, True),
+@pytest.mark.parametrize("h,w,c,k,s,valid", [(112, 112, 64, 3, 2, False), (13, 13, 512, 2, 1, False), (26, 26, 256, 2, 2, True), (7, 7, 1280, 7, 1, True), (7, 7, 1280, 7, 7, True),
                                              (5, 5, 3, 3, 2, False), (9, 7, 12, 2, 2, True)])
 @pytest.mark.parametrize("avg", [False, True])
 def test_pooling(ctx, h, w, c, k, s, valid, avg):

@@ -126,7 +126,11 @@ def test_dims_rules(built):
     assert oracle.conv_out_dim(56, 1, 2, 0, 0) == 28
     assert oracle.conv_out_dim(8, 1, 1, 0, 0) == 8
     assert oracle.same_padding(4, True) == [1, 2, 1, 2]
-    assert oracle.conv_out_dim(8, 4, 1, 1, 2) == 7  # even k: 1 + (pT+pB-1-k)/s
+    assert oracle.conv_out_dim(9, 4, 2, 1, 2) == 4  # even k: 9/2 + max(0, 1 + (pT+pB-1-k)/s = 0) = 4.5 -> 4
+    # negative translations are clamped at 0 (std::max from 0, genericlayer.cpp:66-75): "valid" convs keep their size
+    assert oracle.conv_out_dim(8, 4, 1, 1, 2) == 8
+    assert oracle.conv_out_dim(10, 3, 1, 0, 0) == 10
+    assert oracle.conv_out_dim(225, 3, 2, 0, 0) == 112  # MobileNetV2: Pad((0,1),(0,1)) + valid 3x3 s2
     assert oracle.same_padding(1, True) == [0, 0, 0, 0]
     assert oracle.same_padding(5, False) == [0, 0, 0, 0]
     # pools: maxpool2d.cpp:26-35
@@ -134,7 +138,8 @@ def test_dims_rules(built):
     assert oracle.pool_out_dim(9, 2, 3, False) == 3     # the reference's pooling grid (poolingTest.cpp:42-44)
     assert oracle.pool_out_dim(416, 2, 2, True) == 208
     assert oracle.pool_out_dim(13, 2, 1, False) == 13   # yolo's last pool: 2x2 s1 same
-    assert oracle.pool_out_dim(7, 7, 1, True) == 1
+    assert oracle.pool_out_dim(7, 7, 7, True) == 1      # global pool: the avg reader defaults stride to the pool size
+    assert oracle.pool_out_dim(7, 7, 1, True) == 7      # ... an explicit stride 1 would NOT collapse (translation clamped at 0)
     # depthwise: separableconvolution.cpp:77-86
     assert oracle.depthwise_out_dim(112, 3, 1, 1, 1) == 112
     assert oracle.depthwise_out_dim(113, 3, 2, 0, 0) == 56
