@@ -146,6 +146,7 @@ def pool2d(x, k, stride, avg, out_hw):
 
 def add(a, b, activation="", alpha=0.0):
     a, b = _f(a), _f(b)
+    assert a.shape == b.shape, ("Add: operand shapes differ", a.shape, b.shape)
     y = np.empty_like(a)
     lib().orc_add(_p(a), _p(b), a.size, ACT[activation], float(alpha), _p(y))
     return y

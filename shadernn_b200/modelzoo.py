@@ -330,7 +330,7 @@ def yolov3_tiny(input_hw=(416, 416), head_channels=18, seed=SEED):
 
 def candy(input_hw=(720, 720), seed=SEED):
     """modelzoo/StyleTransfer/candy-9_simplified-opt.param topology (fast-neural-style): reflect-pad + conv9x9(3->32) ->
-    IN+ReLU -> [reflect-pad + conv3x3 s2] x2 (64, 128) -> 5 residual blocks (pad, conv3x3, IN, ReLU, pad, conv3x3, IN, add)
+    IN+ReLU -> [reflect-pad + conv3x3 s2] x2 (64, 128) -> 5 residual blocks (pad+conv3x3, IN, ReLU, pad+conv3x3, IN, add)
     -> [nearest x2, pad, conv3x3, IN, ReLU] x2 (64, 32) -> pad + conv9x9(32->3). Synthetic weights (the real ONNX weights
     are a next-round item)."""
     b = Builder(seed)
@@ -338,9 +338,10 @@ def candy(input_hw=(720, 720), seed=SEED):
     x = b.input(w, h, 3)
 
     def pconv(x, oc, k, stride):
+        # the converter folds ReflectionPad into the conv: padding [[p,p],[p,p]] + "mode" (modelparser.cpp:584-594). A separate
+        # Pad + "valid" conv would NOT shrink under the reference's dims rule (negative translation clamped at 0).
         p = k // 2
-        x = b.pad(x, p, p, p, p, mode="reflect")
-        return b.conv(x, oc, k, stride, "valid", "linear", bias=True, bn=False, gain=1.0)
+        return b.conv(x, oc, k, stride, [[p, p], [p, p]], "linear", bias=True, bn=False, mode="reflect", gain=1.0)
 
     x = b.instancenorm(pconv(x, 32, 9, 1), "relu")
     x = b.instancenorm(pconv(x, 64, 3, 2), "relu")
