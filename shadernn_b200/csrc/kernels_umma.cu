@@ -1,13 +1,473 @@
-// tcgen05 + TMA implicit-GEMM convolution (placeholder until the kernel lands in this round).
+// Conv2D (1x1 and k x k, stride 1 [stride 2 experimental]) as an implicit GEMM on Blackwell's 5th-generation tensor
+// cores, hand-written for sm_100a: TMA (cp.async.bulk.tensor) stages NHWC activation tiles and packed weights from HBM
+// into 128B-swizzled shared memory, one elected thread issues tcgen05.mma, accumulators live in TMEM and are read back
+// with tcgen05.ld by the epilogue warps (bias + residual + activation + split-bf16 store).
+//
+//   D[M = 128 output pixels, N = n_blk <= 128 output channels] += A[M, K] * B[N, K]^T,   K = (tap, 64-channel block)
+//
+// fp32-faithful arithmetic out of bf16 tensor cores: activations and weights are stored as hi + lo bf16 pairs
+// (snnb_internal.h); every K block issues three MMA groups into the same fp32 TMEM accumulator,
+//       A_hi*B_hi  +  A_lo*B_hi  +  A_hi*B_lo                      (the dropped A_lo*B_lo term is ~2^-18 relative),
+// which keeps ~16 mantissa bits per operand — far inside the 1e-3 per-layer parity budget — at 3 bf16 MMAs per
+// product, i.e. 1.5x the cost of one TF32 pass but with fp32-class accuracy (TF32's 10-bit mantissa would not hold 1e-3).
+//
+// A tile = a (tw x th x tn)-pixel box of the OUTPUT grid (tw*th*tn <= 128): for filter tap (ky,kx) the producer issues
+// ONE 4-D TMA box load at input coordinate (ox0*s + kx - pad_x, oy0*s + ky - pad_y); out-of-range rows/columns are
+// zero-filled by the TMA unit, which is exactly the reference's constant padding (vk_conv2d.comp:168-172), and the
+// channel tail (c >= IC) is zero-filled too, so no im2col buffer and no boundary code exist anywhere.
+//
+// Roles (192 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (one TMEM lane quarter each). Pipelines: smem full/empty ring (UM_STAGES deep) and a
+// double-buffered TMEM accumulator (tmem_full/tmem_empty), so the epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Reference semantics: shadertemplate_vk_conv2d.comp:148-347, vk_conv2d_1x1.comp:68-211 (+ fused vk_add.comp:41-90).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
 #include "snnb_internal.h"
 
 namespace snnb {
 
-bool conv2d_umma_supported(const ConvArgs&) { return false; }
+constexpr int UM_BLOCK_M     = 128;
+constexpr int UM_BLOCK_K     = 64; // bf16 elements: 128 bytes = one SWIZZLE_128B row
+constexpr int UM_MAX_N       = 128;
+constexpr int UM_STAGES      = 3;
+constexpr int UM_A_BYTES     = UM_BLOCK_M * 128;
+constexpr int UM_B_BYTES     = UM_MAX_N * 128;
+constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES; // A_hi, A_lo, B_hi, B_lo = 64 KB
+constexpr int UM_THREADS     = 192;
+constexpr int UM_TMEM_COLS   = 256; // two accumulator buffers of up to 128 fp32 columns
+constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-int launch_conv2d_umma(snnb_context*, const ConvArgs&) {
-    set_error("launch_conv2d_umma: not built");
-    return 3;
+struct UmmaParams {
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    const __nv_bfloat16* res_hi;
+    const __nv_bfloat16* res_lo;
+    const float* bias;
+    int N, OH, OW, OC, OCp;
+    int tw, th, tn, rows_used;
+    int tiles_x, tiles_y, tiles_n, tiles_oc, n_blk;
+    int ksize, stride, pad_x, pad_y;
+    int cblocks, ICp;
+    int act;
+    float alpha;
+    int has_res;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a broken descriptor or protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("conv_umma_kernel: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(m),
+                 "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(m), "r"(bar),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; issued by ONE thread for the whole CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed (implicitly fences).
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused for swizzled K-major) | [32,46) SBO >> 4 (= 1024 B: 8 rows x 128 B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// both operands K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+
+__device__ __forceinline__ float umma_act(float v, int act, float alpha) {
+    switch (act) {
+    case SNNB_ACT_RELU: return fmaxf(v, 0.0f);
+    case SNNB_ACT_RELU6: return fminf(fmaxf(v, 0.0f), 6.0f);
+    case SNNB_ACT_TANH: return tanhf(v);
+    case SNNB_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    case SNNB_ACT_LEAKY_RELU: return fmaxf(v, v * alpha);
+    case SNNB_ACT_SILU: return v * 1.0f / (1.0f + expf(-v));
+    default: return v;
+    }
+}
+__device__ __forceinline__ void um_split2(float a, float b, uint32_t& h, uint32_t& l) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    h                 = *reinterpret_cast<uint32_t*>(&hh);
+    const float ra    = a - __uint_as_float(h << 16);
+    const float rb    = b - __uint_as_float(h & 0xffff0000u);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(ra, rb);
+    l                 = *reinterpret_cast<uint32_t*>(&ll);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
+                 const __grid_constant__ CUtensorMap tmB_lo, const UmmaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base  = smem_base + UM_STAGES * UM_STAGE_BYTES;
+    // barrier slots (8 bytes each): full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), then the TMEM base slot
+    auto full_bar       = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar      = [&](int s) { return bar_base + 8u * (UM_STAGES + s); };
+    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * UM_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * UM_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * UM_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi);
+        tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(&tmB_hi);
+        tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < UM_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), 4); // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int total_tiles = m_tiles * p.tiles_oc;
+    const int num_kb      = p.ksize * p.ksize * p.cblocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = 2u * (uint32_t) p.rows_used * 128u + 2u * (uint32_t) p.n_blk * 128u;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
+                const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
+                const int ix0 = bx * p.tw * p.stride - p.pad_x, iy0 = by * p.th * p.stride - p.pad_y, n0 = bn * p.tn;
+                const int oc0 = oc_idx * p.n_blk;
+                for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
+                    const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sA = smem_base + stage * UM_STAGE_BYTES;
+                        mbar_expect_tx(full_bar(stage), tx_bytes);
+                        tma_load_4d(sA, &tmA_hi, full_bar(stage), cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                        tma_load_4d(sA + UM_A_BYTES, &tmA_lo, full_bar(stage), cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                        tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, full_bar(stage), tap * p.ICp + cb * UM_BLOCK_K, oc0);
+                        tma_load_2d(sA + 2 * UM_A_BYTES + UM_B_BYTES, &tmB_lo, full_bar(stage), tap * p.ICp + cb * UM_BLOCK_K, oc0);
+                        if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t idesc = make_idesc(UM_BLOCK_M, p.n_blk);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+            mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_MAX_N);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase); // TMA bytes have landed
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sA = smem_base + stage * UM_STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(sA), a_lo = make_smem_desc(sA + UM_A_BYTES);
+                    const uint64_t b_hi = make_smem_desc(sA + 2 * UM_A_BYTES), b_lo = make_smem_desc(sA + 2 * UM_A_BYTES + UM_B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) // UMMA_K = 16 bf16 = 32 bytes: advance the start address by 2 (x16 B)
+                        umma_bf16(d_tmem, a_hi + 2u * j, b_hi + 2u * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_lo + 2u * j, b_hi + 2u * j, idesc, 1u);
+#pragma unroll
+                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_lo + 2u * j, idesc, 1u);
+                    umma_commit(empty_bar(stage));                     // smem slot free once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> bias/residual/activation -> split-bf16 -> HBM =====================
+        const int q   = warp & 3; // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+            const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
+            const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
+            const int tx_i = row % p.tw, ty_i = (row / p.tw) % p.th, tn_i = row / (p.tw * p.th);
+            const int ox = bx * p.tw + tx_i, oy = by * p.th + ty_i, n = bn * p.tn + tn_i;
+            const bool valid = row < p.rows_used && ox < p.OW && oy < p.OH && n < p.N;
+            const size_t pix = ((size_t) n * p.OH + oy) * p.OW + ox;
+            const int oc0    = oc_idx * p.n_blk;
+
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * UM_MAX_N);
+            for (int c = 0; c < p.n_blk; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t) c, r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int oc = oc0 + c + g * 8;
+                        if (oc < p.OCp) {
+                            const size_t off = pix * p.OCp + oc;
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + ((oc + j < p.OC) ? __ldg(p.bias + oc + j) : 0.0f);
+                            if (p.has_res) {
+                                const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off));
+                                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off));
+                                const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    v[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+                                    v[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = (oc + j < p.OC) ? umma_act(v[j], p.act, p.alpha) : 0.0f;
+                            uint4 oh, ol;
+                            um_split2(v[0], v[1], oh.x, ol.x);
+                            um_split2(v[2], v[3], oh.y, ol.y);
+                            um_split2(v[4], v[5], oh.z, ol.z);
+                            um_split2(v[6], v[7], oh.w, ol.w);
+                            *reinterpret_cast<uint4*>(p.out_hi + off) = oh;
+                            *reinterpret_cast<uint4*>(p.out_lo + off) = ol;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, UM_TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side: tile-shape selection, tensor maps, launch
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode(snnb_context* ctx) {
+    if (!ctx->tmap_encode_fn) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+        ctx->tmap_encode_fn = fn;
+    }
+    return reinterpret_cast<EncodeTiledFn>(ctx->tmap_encode_fn);
+}
+
+struct TilePlan {
+    int tw = 0, th = 0, tn = 0, tiles_x = 0, tiles_y = 0, tiles_n = 0;
+    double eff = 0.0;
+};
+
+// Pick the output-pixel box (tw x th x tn <= 128) that wastes the fewest MMA rows. Whole images are stacked (tn > 1)
+// only when one image fits in a tile (small feature maps: 7x7, 13x13, 1x1).
+static TilePlan plan_tiles(int N, int OH, int OW, int stride) {
+    TilePlan best;
+    const int max_box = 256 / stride; // TMA boxDim <= 256 (in input elements)
+    for (int tw = 1; tw <= std::min(std::min(OW, UM_BLOCK_M), max_box); ++tw) {
+        const int max_th = std::min(std::min(OH, UM_BLOCK_M / tw), max_box);
+        for (int th = 1; th <= max_th; ++th) {
+            int tn = 1;
+            if (tw == OW && th == OH) tn = std::min(std::min(N, UM_BLOCK_M / (tw * th)), 256);
+            const int tx = (OW + tw - 1) / tw, ty = (OH + th - 1) / th, tnn = (N + tn - 1) / tn;
+            const double eff = (double) N * OH * OW / ((double) tx * ty * tnn * UM_BLOCK_M);
+            // prefer higher efficiency; on ties prefer wider rows (longer contiguous runs per TMA box row)
+            if (eff > best.eff + 1e-9 || (eff > best.eff - 1e-9 && tw > best.tw)) {
+                best.tw = tw, best.th = th, best.tn = tn, best.tiles_x = tx, best.tiles_y = ty, best.tiles_n = tnn, best.eff = eff;
+            }
+        }
+    }
+    return best;
+}
+
+static int plan_n_blk(int OC, int& tiles_oc) {
+    int best_blk = 0, best_tiles = 0;
+    double best_waste = 1e30;
+    for (int t = (OC + UM_MAX_N - 1) / UM_MAX_N; t <= (OC + 15) / 16 && t <= (OC + UM_MAX_N - 1) / UM_MAX_N + 2; ++t) {
+        const int blk = std::min(UM_MAX_N, round_up((OC + t - 1) / t, 16));
+        if (blk * t < OC) continue;
+        const double waste = (double) blk * t / OC + 0.02 * t; // slight preference for fewer, larger tiles
+        if (waste < best_waste) best_waste = waste, best_blk = blk, best_tiles = t;
+    }
+    tiles_oc = best_tiles;
+    return best_blk;
+}
+
+bool conv2d_umma_supported(const ConvArgs& a) {
+    if (!a.w || !a.w->w_hi || !a.w->w_lo) return false;
+    if (!(a.pad_mode == SNNB_PAD_NONE || a.pad_mode == SNNB_PAD_CONSTANT)) return false; // replicate / reflect: SIMT gather
+    static const bool allow_s2 = getenv("SNNB_UMMA_STRIDE2") != nullptr;
+    if (!(a.stride == 1 || (a.stride == 2 && allow_s2))) return false;
+    if (a.in->c < 16) return false; // 3-channel stems / 1-channel ESPCN: K would be >75% zero padding
+    if (a.k < 1 || a.k > 11) return false;
+    if (a.pad_x > 127 || a.pad_y > 127) return false;
+    return true;
+}
+
+static bool g_attr_set = false;
+
+int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
+    EncodeTiledFn encode = get_encode(ctx);
+    SNNB_REQUIRE(encode, "launch_conv2d_umma: cuTensorMapEncodeTiled is unavailable in this driver");
+    const snnb_tensor* in = a.in;
+    snnb_tensor* out      = a.out;
+    UmmaParams p;
+    p.out_hi = out->hi, p.out_lo = out->lo;
+    p.res_hi = a.residual ? a.residual->hi : nullptr, p.res_lo = a.residual ? a.residual->lo : nullptr;
+    p.has_res = a.residual != nullptr;
+    p.bias    = a.w->bias;
+    p.N = out->n, p.OH = out->h, p.OW = out->w, p.OC = out->c, p.OCp = out->cp;
+    const TilePlan tp = plan_tiles(out->n, out->h, out->w, a.stride);
+    SNNB_REQUIRE(tp.tw > 0, "launch_conv2d_umma: no tile plan");
+    p.tw = tp.tw, p.th = tp.th, p.tn = tp.tn, p.rows_used = tp.tw * tp.th * tp.tn;
+    p.tiles_x = tp.tiles_x, p.tiles_y = tp.tiles_y, p.tiles_n = tp.tiles_n;
+    p.n_blk   = plan_n_blk(out->c, p.tiles_oc);
+    p.ksize = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y;
+    p.cblocks = (in->c + UM_BLOCK_K - 1) / UM_BLOCK_K;
+    p.ICp     = round_up(in->c, 8);
+    p.act = a.act, p.alpha = a.alpha;
+    SNNB_REQUIRE(a.w->kp == a.k * a.k * p.ICp, "launch_conv2d_umma: packed weights do not match (kp %d vs %d)", a.w->kp, a.k * a.k * p.ICp);
+
+    CUtensorMap tmA[2], tmB[2];
+    {
+        const cuuint64_t dims[4]    = {(cuuint64_t) in->c, (cuuint64_t) in->w, (cuuint64_t) in->h, (cuuint64_t) in->n};
+        const cuuint64_t strides[3] = {(cuuint64_t) in->cp * 2, (cuuint64_t) in->w * in->cp * 2, (cuuint64_t) in->h * in->w * in->cp * 2};
+        const cuuint32_t box[4]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) (p.tw * a.stride), (cuuint32_t) (p.th * a.stride), (cuuint32_t) p.tn};
+        const cuuint32_t estr[4]    = {1, (cuuint32_t) a.stride, (cuuint32_t) a.stride, 1};
+        __nv_bfloat16* planes[2]    = {in->hi, in->lo};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = encode(&tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d box %u %u %u %u)", (int) r, in->c, in->w, in->h, in->n, box[0],
+                         box[1], box[2], box[3]);
+        }
+    }
+    {
+        const cuuint64_t dims[2]    = {(cuuint64_t) a.w->kp, (cuuint64_t) a.w->ocr};
+        const cuuint64_t strides[1] = {(cuuint64_t) a.w->kp * 2};
+        const cuuint32_t box[2]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) p.n_blk};
+        const cuuint32_t estr[2]    = {1, 1};
+        __nv_bfloat16* planes[2]    = {a.w->w_hi, a.w->w_lo};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (kp %d ocr %d n_blk %d)", (int) r, a.w->kp, a.w->ocr, p.n_blk);
+        }
+    }
+    if (!g_attr_set) {
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        g_attr_set = true;
+    }
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
+    const int grid        = std::min(total_tiles, ctx->sm_count);
+    conv_umma_kernel<<<grid, UM_THREADS, UM_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("conv_umma_kernel launch failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    ctx->launches++;
+    return 0;
 }
 
 } // namespace snnb

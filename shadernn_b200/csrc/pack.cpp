@@ -51,8 +51,11 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
     std::vector<float> scale, shift;
     bn_fold(OC, bias, g, b, m, v, scale, shift);
     const int K = k * k * IC;
+    // tcgen05 operand: row = oc, column = tap*ICp + ic with ICp = round_up(IC, 8), so that every tap starts on a
+    // 16-byte boundary (TMA box start) and the padding columns are zero.
+    const int ICp = round_up(IC, 8);
     out.ocw     = round_up(OC, 64);
-    out.kp      = round_up(K, 8);
+    out.kp      = k * k * ICp;
     out.ocr     = round_up(OC, 16);
     out.w_f32.assign((size_t) K * out.ocw, 0.0f);
     out.w_hi.assign((size_t) out.ocr * out.kp, __float2bfloat16_rn(0.0f));
@@ -66,9 +69,10 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
                     const float wv  = w_oihw[(((size_t) o * IC + i) * k + ky) * k + kx] * scale[o];
                     const int kidx  = (ky * k + kx) * IC + i;
                     out.w_f32[(size_t) kidx * out.ocw + o] = wv;
+                    const int kcol                         = (ky * k + kx) * ICp + i;
                     const __nv_bfloat16 h                  = __float2bfloat16_rn(wv);
-                    out.w_hi[(size_t) o * out.kp + kidx]   = h;
-                    out.w_lo[(size_t) o * out.kp + kidx]   = __float2bfloat16_rn(wv - __bfloat162float(h));
+                    out.w_hi[(size_t) o * out.kp + kcol]   = h;
+                    out.w_lo[(size_t) o * out.kp + kcol]   = __float2bfloat16_rn(wv - __bfloat162float(h));
                 }
     }
 }

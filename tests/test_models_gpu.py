@@ -123,9 +123,12 @@ def test_fused_graph_equals_unfused_and_graph_replay(ctx, model_dir, name, hw, k
     o1, c1 = fused.run(x, want_classes=name != "candy")
     o2, c2 = graph.run(x, want_classes=name != "candy")
     o3, _ = graph.run(x, want_classes=False)  # replay twice: idempotent
-    assert fused.launches_per_forward < plain.launches_per_forward
+    assert fused.launches_per_forward <= plain.launches_per_forward
+    if name != "candy":  # candy has no Conv->Add chains or standalone pads to fuse (adds follow InstanceNorm)
+        assert fused.launches_per_forward < plain.launches_per_forward
     scale = max(1.0, float(np.abs(o0).max()))
-    assert float(np.abs(o1 - o0).max()) / scale < 1e-5  # same kernels, residual added in-register instead of via HBM
+    # same arithmetic, but a fused conv+add skips one split-bf16 rounding (2^-17) of the intermediate per block
+    assert float(np.abs(o1 - o0).max()) / scale < 1e-4
     assert np.array_equal(o2, o1) and np.array_equal(o3, o2)
     if c0 is not None:
         assert np.array_equal(c0, c1) and np.array_equal(c1, c2)
