@@ -311,7 +311,7 @@ int snnb_dense_launch(snnb_context* ctx, const snnb_weights* w, int act, float a
     }
     const bool softmax = act == SNNB_ACT_SOFTMAX;
     ConvArgs a {x, nullptr, out, w, 1, 1, 0, 0, SNNB_PAD_NONE, softmax ? SNNB_ACT_NONE : act, alpha};
-    int rc = launch_conv2d_simt(ctx, a);
+    int rc = conv2d_umma_supported(a) ? launch_conv2d_umma(ctx, a) : launch_conv2d_simt(ctx, a);
     if (!rc && softmax) rc = launch_softmax(ctx, out, out);
     if (flat) {
         cudaStreamSynchronize(ctx->stream);

@@ -180,7 +180,7 @@ int DenseLayer::run(snnb_context* ctx, const ExecOptions&) {
     const bool softmax = activation.id == SNNB_ACT_SOFTMAX;
     ConvArgs a {x, nullptr, output, &weights, 1, 1, 0, 0, SNNB_PAD_NONE, softmax ? SNNB_ACT_NONE : activation.id, activation.alpha};
     // SiLU on the CPU Dense path is a by-value no-op in the reference (cpulayer.h:245-252); we apply the real SiLU.
-    if (launch_conv2d_simt(ctx, a)) return 1;
+    if (conv2d_umma_supported(a) ? launch_conv2d_umma(ctx, a) : launch_conv2d_simt(ctx, a)) return 1;
     if (softmax) return launch_softmax(ctx, output, output);
     return 0;
 }

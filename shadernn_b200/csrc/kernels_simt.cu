@@ -62,16 +62,21 @@ __device__ __forceinline__ void store1(__nv_bfloat16* __restrict__ hi, __nv_bflo
 
 // Activations: ids of conv2dVulkan.cpp:57-71; math of shadertemplate_vk_conv2d.comp:290-340 (SiLU computed
 // correctly per element — the reference's 4-pixel kernel reuses pixel 1's sigmoid).
-__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+__device__ __noinline__ float slow_act(float v, int act) {
     switch (act) {
-    case SNNB_ACT_RELU: return fmaxf(v, 0.0f);
-    case SNNB_ACT_RELU6: return fminf(fmaxf(v, 0.0f), 6.0f);
     case SNNB_ACT_TANH: return tanhf(v);
     case SNNB_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
-    case SNNB_ACT_LEAKY_RELU: return fmaxf(v, v * alpha);
     case SNNB_ACT_SILU: return v * 1.0f / (1.0f + expf(-v));
     default: return v;
     }
+}
+// none / relu / relu6 / leakyRelu are one branch-free max/min pair (slope and clip are loop-invariant); the
+// transcendental ones go out of line. max(v, v*alpha) is the reference's own leakyRelu form (vk_conv2d.comp:325-330).
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+    if (act == SNNB_ACT_TANH || act == SNNB_ACT_SIGMOID || act == SNNB_ACT_SILU) return slow_act(v, act);
+    const float slope = (act == SNNB_ACT_RELU || act == SNNB_ACT_RELU6) ? 0.0f : (act == SNNB_ACT_LEAKY_RELU ? alpha : 1.0f);
+    const float hi    = act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+    return fminf(fmaxf(v, v * slope), hi);
 }
 
 // Source coordinate under a padding mode (vk_conv2d.comp:168-218): returns -1 for "reads zero".

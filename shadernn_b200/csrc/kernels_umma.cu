@@ -1,4 +1,4 @@
-// Conv2D (1x1 and k x k, stride 1 [stride 2 experimental]) as an implicit GEMM on Blackwell's 5th-generation tensor
+// Conv2D (1x1 and k x k, stride 1 and 2) as an implicit GEMM on Blackwell's 5th-generation tensor
 // cores, hand-written for sm_100a: TMA (cp.async.bulk.tensor) stages NHWC activation tiles and packed weights from HBM
 // into 128B-swizzled shared memory, one elected thread issues tcgen05.mma, accumulators live in TMEM and are read back
 // with tcgen05.ld by the epilogue warps (bias + residual + activation + split-bf16 store).
@@ -16,8 +16,8 @@
 // zero-filled by the TMA unit, which is exactly the reference's constant padding (vk_conv2d.comp:168-172), and the
 // channel tail (c >= IC) is zero-filled too, so no im2col buffer and no boundary code exist anywhere.
 //
-// Roles (192 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue (one TMEM lane quarter each). Pipelines: smem full/empty ring (UM_STAGES deep) and a
+// Roles (320 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = epilogue (two warps per TMEM lane quarter, interleaved over 16-column chunks). Pipelines: smem full/empty ring (UM_STAGES deep) and a
 // double-buffered TMEM accumulator (tmem_full/tmem_empty), so the epilogue of tile i overlaps the mainloop of tile i+1.
 //
 // Reference semantics: shadertemplate_vk_conv2d.comp:148-347, vk_conv2d_1x1.comp:68-211 (+ fused vk_add.comp:41-90).
@@ -37,7 +37,8 @@ constexpr int UM_STAGES      = 3;
 constexpr int UM_A_BYTES     = UM_BLOCK_M * 128;
 constexpr int UM_B_BYTES     = UM_MAX_N * 128;
 constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES; // A_hi, A_lo, B_hi, B_lo = 64 KB
-constexpr int UM_THREADS     = 192;
+constexpr int UM_EPI_WARPS   = 8;                       // two warps per TMEM lane quarter, interleaved over 16-column chunks
+constexpr int UM_THREADS     = 64 + 32 * UM_EPI_WARPS; // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int UM_TMEM_COLS   = 256; // two accumulator buffers of up to 128 fp32 columns
 constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -146,7 +147,8 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
 }
 
-__device__ __forceinline__ float umma_act(float v, int act, float alpha) {
+// transcendental activations only (tanh / sigmoid / SiLU): rare, kept out of line so the hot epilogue stays small
+__device__ __noinline__ float umma_act(float v, int act, float alpha) {
     switch (act) {
     case SNNB_ACT_RELU: return fmaxf(v, 0.0f);
     case SNNB_ACT_RELU6: return fminf(fmaxf(v, 0.0f), 6.0f);
@@ -195,7 +197,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), 4); // one arrive per epilogue warp
+            mbar_init(tmem_empty_bar(a), UM_EPI_WARPS); // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -271,55 +273,83 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> bias/residual/activation -> split-bf16 -> HBM =====================
-        const int q   = warp & 3; // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
+        // Lean by construction (the first version spent ~2000 SASS instructions per 16 values on per-element activation
+        // switches, scalar bias loads and channel predicates and throttled the whole pipeline): activations of the
+        // relu family are one branch-free max/min pair, bias is fetched as float4 from a zero-padded vector, and padded
+        // output channels need no mask because their weights, bias and residual are all zero.
+        const int q    = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;          // which interleaved set of 16-column chunks this warp owns
+        const int row  = q * 32 + lane;
+        const bool fast_act = p.act == SNNB_ACT_NONE || p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6 || p.act == SNNB_ACT_LEAKY_RELU;
+        const float slope   = (p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6) ? 0.0f : (p.act == SNNB_ACT_LEAKY_RELU ? p.alpha : 1.0f);
+        const float hi_clip = p.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        const int tx_i = row % p.tw, ty_i = (row / p.tw) % p.th, tn_i = row / (p.tw * p.th);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
             const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
-            const int tx_i = row % p.tw, ty_i = (row / p.tw) % p.th, tn_i = row / (p.tw * p.th);
             const int ox = bx * p.tw + tx_i, oy = by * p.th + ty_i, n = bn * p.tn + tn_i;
             const bool valid = row < p.rows_used && ox < p.OW && oy < p.OH && n < p.N;
-            const size_t pix = ((size_t) n * p.OH + oy) * p.OW + ox;
             const int oc0    = oc_idx * p.n_blk;
+            const size_t base = (((size_t) n * p.OH + oy) * p.OW + ox) * (size_t) p.OCp + oc0;
+            __nv_bfloat16* o_hi       = p.out_hi + base;
+            __nv_bfloat16* o_lo       = p.out_lo + base;
+            const __nv_bfloat16* r_hi = p.res_hi + base;
+            const __nv_bfloat16* r_lo = p.res_lo + base;
+            const float* bias         = p.bias + oc0;
 
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * UM_MAX_N);
-            for (int c = 0; c < p.n_blk; c += 16) {
+            for (int c = half * 16; c < p.n_blk; c += 32) {
                 uint32_t r[16];
                 tmem_ld16(taddr + (uint32_t) c, r);
                 tmem_ld_wait();
                 if (valid) {
+                    float v[16];
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int oc = oc0 + c + g * 8;
-                        if (oc < p.OCp) {
-                            const size_t off = pix * p.OCp + oc;
-                            float v[8];
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c) + j4);
+                        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+                        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+                        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+                        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+                    }
+                    const bool g0 = oc0 + c < p.OCp, g1 = oc0 + c + 8 < p.OCp; // 8-channel groups inside the tensor's pitch
+                    if (p.has_res) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + ((oc + j < p.OC) ? __ldg(p.bias + oc + j) : 0.0f);
-                            if (p.has_res) {
-                                const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off));
-                                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off));
+                        for (int g = 0; g < 2; ++g) {
+                            if (g == 0 ? g0 : g1) {
+                                const uint4 h = __ldg(reinterpret_cast<const uint4*>(r_hi + c + g * 8));
+                                const uint4 l = __ldg(reinterpret_cast<const uint4*>(r_lo + c + g * 8));
                                 const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    v[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-                                    v[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+                                    v[g * 8 + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+                                    v[g * 8 + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
                                 }
                             }
+                        }
+                    }
+                    if (fast_act) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = (oc + j < p.OC) ? umma_act(v[j], p.act, p.alpha) : 0.0f;
+                        for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = (oc0 + c + j < p.OC) ? umma_act(v[j], p.act, p.alpha) : 0.0f; // out-of-line call
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        if (g == 0 ? g0 : g1) {
                             uint4 oh, ol;
-                            um_split2(v[0], v[1], oh.x, ol.x);
-                            um_split2(v[2], v[3], oh.y, ol.y);
-                            um_split2(v[4], v[5], oh.z, ol.z);
-                            um_split2(v[6], v[7], oh.w, ol.w);
-                            *reinterpret_cast<uint4*>(p.out_hi + off) = oh;
-                            *reinterpret_cast<uint4*>(p.out_lo + off) = ol;
+                            um_split2(v[g * 8 + 0], v[g * 8 + 1], oh.x, ol.x);
+                            um_split2(v[g * 8 + 2], v[g * 8 + 3], oh.y, ol.y);
+                            um_split2(v[g * 8 + 4], v[g * 8 + 5], oh.z, ol.z);
+                            um_split2(v[g * 8 + 6], v[g * 8 + 7], oh.w, ol.w);
+                            *reinterpret_cast<uint4*>(o_hi + c + g * 8) = oh;
+                            *reinterpret_cast<uint4*>(o_lo + c + g * 8) = ol;
                         }
                     }
                 }
@@ -396,8 +426,7 @@ static int plan_n_blk(int OC, int& tiles_oc) {
 bool conv2d_umma_supported(const ConvArgs& a) {
     if (!a.w || !a.w->w_hi || !a.w->w_lo) return false;
     if (!(a.pad_mode == SNNB_PAD_NONE || a.pad_mode == SNNB_PAD_CONSTANT)) return false; // replicate / reflect: SIMT gather
-    static const bool allow_s2 = getenv("SNNB_UMMA_STRIDE2") != nullptr;
-    if (!(a.stride == 1 || (a.stride == 2 && allow_s2))) return false;
+    if (!(a.stride == 1 || a.stride == 2)) return false; // stride 2 = TMA traversal stride (elementStrides) on W and H
     if (a.in->c < 16) return false; // 3-channel stems / 1-channel ESPCN: K would be >75% zero padding
     if (a.k < 1 || a.k > 11) return false;
     if (a.pad_x > 127 || a.pad_y > 127) return false;

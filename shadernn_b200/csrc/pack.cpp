@@ -60,7 +60,7 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
     out.w_f32.assign((size_t) K * out.ocw, 0.0f);
     out.w_hi.assign((size_t) out.ocr * out.kp, __float2bfloat16_rn(0.0f));
     out.w_lo.assign((size_t) out.ocr * out.kp, __float2bfloat16_rn(0.0f));
-    out.bias.assign(out.ocw, 0.0f);
+    out.bias.assign(out.ocw + 192, 0.0f); // zero tail: the tcgen05 epilogue reads float4s up to tiles_oc * n_blk
     for (int o = 0; o < OC; ++o) {
         out.bias[o] = shift[o];
         for (int i = 0; i < IC; ++i)

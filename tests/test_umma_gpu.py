@@ -80,7 +80,6 @@ def test_many_tiles_persistent_loop(ctx):
     run_case(ctx, 8, 56, 56, 64, 192, 3, act="relu", seed=9)
 
 
-@pytest.mark.skipif(os.environ.get("SNNB_UMMA_STRIDE2") is None, reason="stride-2 TMA traversal is experimental (set SNNB_UMMA_STRIDE2=1)")
-@pytest.mark.parametrize("k,ic,oc,h", [(3, 64, 128, 56), (1, 64, 128, 56), (3, 128, 256, 29)])
-def test_stride2_experimental(ctx, k, ic, oc, h):
+@pytest.mark.parametrize("k,ic,oc,h", [(3, 64, 128, 56), (1, 64, 128, 56), (3, 128, 256, 29), (3, 256, 512, 14), (1, 256, 512, 14), (5, 32, 32, 21)])
+def test_stride2_tma_traversal_stride(ctx, k, ic, oc, h):
     run_case(ctx, 2, h, h, ic, oc, k, s=2, padding="same" if k > 1 else "valid", act="relu")
