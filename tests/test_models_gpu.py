@@ -17,6 +17,19 @@ pytestmark = pytest.mark.gpu
 EPS = 1e-3
 
 
+def assert_same_boxes(got, ref, tol=3e-3):
+    """Detection lists agree as SETS: equal scores may sort differently (NMS orders by score, yololayer.cpp:73-78)."""
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    used = set()
+    for r in ref:
+        d = np.max(np.abs(got - r) / (np.abs(r) + 1.0), axis=1)
+        for j in np.argsort(d):
+            if int(j) not in used:
+                assert d[j] < tol, (r, got[j], d[j])
+                used.add(int(j))
+                break
+
+
 def layerwise_check(ctx, name, hw, batch, model_dir, eps=EPS, **build_kw):
     path, layers = modelzoo.build(name, model_dir, input_hw=hw, **build_kw)
     x = modelzoo.synthetic_input(name, batch, hw)
@@ -81,11 +94,7 @@ def test_mobilenetv2_layerwise(ctx, model_dir):
 def test_yolov3tiny_layerwise_and_boxes(ctx, model_dir):
     m, om, x, want, worst = layerwise_check(ctx, "yolov3tiny", (416, 416), 1, model_dir)
     m.run(x, want_classes=False)
-    got = m.boxes(0)
-    ref = om.boxes[0]
-    assert got.shape == ref.shape
-    if len(ref):
-        assert np.allclose(got, ref, rtol=1e-3, atol=1e-3)
+    assert_same_boxes(m.boxes(0), om.boxes[0])
 
 
 def test_yolo_decode_with_planted_detection(ctx, model_dir):
@@ -102,9 +111,8 @@ def test_yolo_decode_with_planted_detection(ctx, model_dir):
     m = core.MixedInferenceCore(ctx, path, batch=1)
     m.run(x, want_classes=False)
     got, ref = m.boxes(0), om.boxes[0]
-    assert len(ref) > 0 and got.shape == ref.shape
-    assert np.array_equal(got[:, 0], ref[:, 0])
-    assert np.allclose(got[:, 1:], ref[:, 1:], rtol=2e-3, atol=2e-3)
+    assert len(ref) > 0
+    assert_same_boxes(got, ref)
 
 
 def test_candy_layerwise(ctx, model_dir):
