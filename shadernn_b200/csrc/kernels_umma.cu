@@ -369,6 +369,233 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Small-input-channel convolution (IC <= 8: the 7x7/3x3 RGB stems, ESPCN's 1-channel 5x5) on the same tensor cores.
+//
+// With C padded to 8 bf16 (= one 16-byte vector per pixel and plane) the kw taps of one filter row are CONTIGUOUS in
+// NHWC memory: kw * 16 bytes. So K is ordered (ky | kx, c): one 64-element K block per filter row ky, of which
+// kw*8 <= 64 elements are live - exactly the column order the packed weights already have (pack.cpp), so B needs no
+// new layout: the whole weight panel [n_blk][kh x 64] (hi+lo) is TMA-loaded ONCE per persistent CTA and stays in
+// shared memory. A cannot come from a TMA box (the window of output pixel ox starts at input pixel ox*s - pad, an
+// overlapping strided view), so 8 producer warps build each A stage with plain 16-byte copies global -> swizzled smem
+// (no arithmetic: the operands are already split-bf16), zero vectors where the window leaves the image (constant
+// padding), then fence.proxy.async and hand the stage to the MMA warp through the same full/empty mbarrier ring.
+// Tiles are 128 consecutive output pixels in (n, oy, ox) raster order: no overhang, every MMA row is live.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RG_STAGES        = 3;
+constexpr int RG_PROD_WARPS    = 8;
+constexpr int RG_EPI_WARPS     = 4;
+constexpr int RG_THREADS       = 64 + 32 * (RG_PROD_WARPS + RG_EPI_WARPS);
+constexpr int RG_MAX_KH        = 7;
+constexpr int RG_MAX_N         = 64;
+constexpr int RG_B_PLANE_BYTES = RG_MAX_KH * RG_MAX_N * 128; // [ky][n_blk rows x 128 B]
+constexpr int RG_A_STAGE_BYTES = 2 * UM_A_BYTES;             // A_hi + A_lo
+constexpr int RG_SMEM_BYTES    = 2 * RG_B_PLANE_BYTES + RG_STAGES * RG_A_STAGE_BYTES + 1024 + 256;
+
+struct RowGemmParams {
+    const __nv_bfloat16* in_hi;
+    const __nv_bfloat16* in_lo;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    const float* bias;
+    int N, H, W, OH, OW, OC, OCp, n_blk;
+    int kh, kw, stride, pad_x, pad_y;
+    int act;
+    float alpha;
+    long long M; // N*OH*OW
+};
+
+__global__ void __launch_bounds__(RG_THREADS, 1)
+conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const RowGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sB_hi = smem_base, sB_lo = smem_base + RG_B_PLANE_BYTES;
+    const uint32_t sA0      = smem_base + 2 * RG_B_PLANE_BYTES;
+    const uint32_t bar_base = sA0 + RG_STAGES * RG_A_STAGE_BYTES;
+    auto full_bar       = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar      = [&](int s) { return bar_base + 8u * (RG_STAGES + s); };
+    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * RG_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * RG_STAGES + 2 + a); };
+    const uint32_t b_bar     = bar_base + 8u * (2 * RG_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * RG_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmB_hi);
+        tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < RG_STAGES; ++s) {
+            mbar_init(full_bar(s), RG_PROD_WARPS); // one arrive per producer warp
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), RG_EPI_WARPS);
+        }
+        mbar_init(b_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128); // two accumulator buffers of <= 64 columns
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int total_tiles = (int) ((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M);
+
+    if (warp == 0) {
+        // ---- weight panel: loaded once, resident for the CTA's lifetime ----
+        if (lane == 0) {
+            mbar_expect_tx(b_bar, 2u * (uint32_t) p.kh * (uint32_t) p.n_blk * 128u);
+            for (int ky = 0; ky < p.kh; ++ky) {
+                tma_load_2d(sB_hi + ky * p.n_blk * 128, &tmB_hi, b_bar, ky * p.kw * 8, 0);
+                tma_load_2d(sB_lo + ky * p.n_blk * 128, &tmB_lo, b_bar, ky * p.kw * 8, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ----
+        mbar_wait(b_bar, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t idesc = make_idesc(UM_BLOCK_M, p.n_blk);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+            mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * RG_MAX_N);
+            for (int ky = 0; ky < p.kh; ++ky) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sA = sA0 + stage * RG_A_STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(sA), a_lo = make_smem_desc(sA + UM_A_BYTES);
+                    const uint64_t b_hi = make_smem_desc(sB_hi + ky * p.n_blk * 128), b_lo = make_smem_desc(sB_lo + ky * p.n_blk * 128);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_hi + 2u * j, idesc, (ky > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, a_lo + 2u * j, b_hi + 2u * j, idesc, 1u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_lo + 2u * j, idesc, 1u);
+                    umma_commit(empty_bar(stage));
+                    if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
+                }
+                __syncwarp();
+                if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+            }
+        }
+    } else if (warp < 2 + RG_PROD_WARPS) {
+        // ---- A producers: 256 threads, thread -> (row, plane); per stage 8 x 16-byte chunks of one 128-byte row ----
+        const int t     = threadIdx.x - 64;
+        const int row   = t & 127;
+        const int plane = t >> 7;
+        const __nv_bfloat16* src_plane = plane ? p.in_lo : p.in_hi;
+        const uint32_t row_off  = (uint32_t) plane * UM_A_BYTES + (uint32_t) row * 128u;
+        const uint32_t sw       = (uint32_t) (row & 7);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const long long m = (long long) tile * UM_BLOCK_M + row;
+            const bool live   = m < p.M;
+            int n = 0, oy = 0, ox = 0;
+            if (live) {
+                n             = (int) (m / ((long long) p.OH * p.OW));
+                const int rem = (int) (m - (long long) n * p.OH * p.OW);
+                oy            = rem / p.OW;
+                ox            = rem - oy * p.OW;
+            }
+            const int ix0 = ox * p.stride - p.pad_x, iy0 = oy * p.stride - p.pad_y;
+            for (int ky = 0; ky < p.kh; ++ky) {
+                const int iy       = iy0 + ky;
+                const bool row_ok  = live && iy >= 0 && iy < p.H;
+                const uint4* gsrc  = reinterpret_cast<const uint4*>(src_plane + (((size_t) n * p.H + (row_ok ? iy : 0)) * p.W) * 8);
+                uint4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ix = ix0 + j;
+                    v[j]         = (row_ok && j < p.kw && ix >= 0 && ix < p.W) ? __ldg(gsrc + ix) : make_uint4(0, 0, 0, 0);
+                }
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t dst = sA0 + stage * RG_A_STAGE_BYTES + row_off;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z),
+                                 "r"(v[j].w)
+                                 : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(stage));
+                if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+            }
+        }
+    } else {
+        // ---- epilogue: 4 warps, one TMEM lane quarter each ----
+        const int q   = warp & 3;
+        const int row = q * 32 + lane;
+        const bool fast_act = p.act == SNNB_ACT_NONE || p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6 || p.act == SNNB_ACT_LEAKY_RELU;
+        const float slope   = (p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6) ? 0.0f : (p.act == SNNB_ACT_LEAKY_RELU ? p.alpha : 1.0f);
+        const float hi_clip = p.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+            const long long m = (long long) tile * UM_BLOCK_M + row;
+            const bool valid  = m < p.M;
+            __nv_bfloat16* o_hi = p.out_hi + (size_t) m * p.OCp;
+            __nv_bfloat16* o_lo = p.out_lo + (size_t) m * p.OCp;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * RG_MAX_N);
+            for (int c = 0; c < p.n_blk; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t) c, r);
+                tmem_ld_wait();
+                if (valid) {
+                    float v[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c) + j4);
+                        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+                        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+                        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+                        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+                    }
+                    if (fast_act) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = (c + j < p.OC) ? umma_act(v[j], p.act, p.alpha) : 0.0f;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        if (c + g * 8 < p.OCp) {
+                            uint4 oh, ol;
+                            um_split2(v[g * 8 + 0], v[g * 8 + 1], oh.x, ol.x);
+                            um_split2(v[g * 8 + 2], v[g * 8 + 3], oh.y, ol.y);
+                            um_split2(v[g * 8 + 4], v[g * 8 + 5], oh.z, ol.z);
+                            um_split2(v[g * 8 + 6], v[g * 8 + 7], oh.w, ol.w);
+                            *reinterpret_cast<uint4*>(o_hi + c + g * 8) = oh;
+                            *reinterpret_cast<uint4*>(o_lo + c + g * 8) = ol;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Host side: tile-shape selection, tensor maps, launch
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -423,21 +650,65 @@ static int plan_n_blk(int OC, int& tiles_oc) {
     return best_blk;
 }
 
+static bool rowgemm_supported(const ConvArgs& a) {
+    // small-C stems: IC <= 8 (one 16-byte vector per pixel), one 64-wide K block per filter row, weights resident in smem
+    return a.in->cp == 8 && a.k >= 1 && a.k <= RG_MAX_KH && a.k * 8 <= UM_BLOCK_K && a.out->c <= RG_MAX_N && a.residual == nullptr && a.stride >= 1;
+}
+
 bool conv2d_umma_supported(const ConvArgs& a) {
     if (!a.w || !a.w->w_hi || !a.w->w_lo) return false;
     if (!(a.pad_mode == SNNB_PAD_NONE || a.pad_mode == SNNB_PAD_CONSTANT)) return false; // replicate / reflect: SIMT gather
+    if (rowgemm_supported(a)) return true;
     if (!(a.stride == 1 || a.stride == 2)) return false; // stride 2 = TMA traversal stride (elementStrides) on W and H
-    if (a.in->c < 16) return false; // 3-channel stems / 1-channel ESPCN: K would be >75% zero padding
+    if (a.in->c < 16) return false; // wider small-C cases the row-GEMM variant cannot take: K would be >75% zero padding
     if (a.k < 1 || a.k > 11) return false;
     if (a.pad_x > 127 || a.pad_y > 127) return false;
     return true;
 }
 
-static bool g_attr_set = false;
+static bool g_attr_set = false, g_attr_set_rg = false;
+
+static int launch_conv2d_rowgemm(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
+    const snnb_tensor* in = a.in;
+    snnb_tensor* out      = a.out;
+    RowGemmParams p;
+    p.in_hi = in->hi, p.in_lo = in->lo, p.out_hi = out->hi, p.out_lo = out->lo, p.bias = a.w->bias;
+    p.N = out->n, p.H = in->h, p.W = in->w, p.OH = out->h, p.OW = out->w, p.OC = out->c, p.OCp = out->cp;
+    p.n_blk = round_up(out->c, 16);
+    p.kh = a.k, p.kw = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y, p.act = a.act, p.alpha = a.alpha;
+    p.M = (long long) out->n * out->h * out->w;
+    SNNB_REQUIRE(a.w->kp == a.k * a.k * 8, "launch_conv2d_rowgemm: packed weights do not match (kp %d)", a.w->kp);
+    CUtensorMap tmB[2];
+    const cuuint64_t dims[2]    = {(cuuint64_t) a.w->kp, (cuuint64_t) a.w->ocr};
+    const cuuint64_t strides[1] = {(cuuint64_t) a.w->kp * 2};
+    const cuuint32_t box[2]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) p.n_blk};
+    const cuuint32_t estr[2]    = {1, 1};
+    __nv_bfloat16* planes[2]    = {a.w->w_hi, a.w->w_lo};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, rowgemm) failed: %d", (int) r);
+    }
+    if (!g_attr_set_rg) {
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM_BYTES));
+        g_attr_set_rg = true;
+    }
+    const int total_tiles = (int) ((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M);
+    const int grid        = std::min(total_tiles, ctx->sm_count);
+    conv_rowgemm_kernel<<<grid, RG_THREADS, RG_SMEM_BYTES, ctx->stream>>>(tmB[0], tmB[1], p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("conv_rowgemm_kernel launch failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    ctx->launches++;
+    return 0;
+}
 
 int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     EncodeTiledFn encode = get_encode(ctx);
     SNNB_REQUIRE(encode, "launch_conv2d_umma: cuTensorMapEncodeTiled is unavailable in this driver");
+    if (rowgemm_supported(a)) return launch_conv2d_rowgemm(ctx, a, encode);
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;
     UmmaParams p;

@@ -75,6 +75,18 @@ def test_other_kernel_sizes_and_asymmetric_padding(ctx):
     run_case(ctx, 1, 16, 16, 64, 64, 3, padding="valid")            # reference dims quirk: output stays 16x16
 
 
+@pytest.mark.parametrize("n,h,w,ic,oc,k,s,padding,act", [
+    (2, 224, 224, 3, 64, 7, 2, "same", "relu"),      # ResNet-18 stem
+    (2, 97, 97, 3, 32, 3, 2, "valid", "relu6"),      # MobileNetV2 stem (after ZeroPadding2D)
+    (1, 64, 80, 3, 16, 3, 1, "same", "leakyRelu"),   # YOLOv3-tiny first conv
+    (1, 40, 40, 1, 16, 5, 1, "same", "relu"),        # ESPCN first conv: 1 input channel
+    (1, 33, 29, 4, 24, 3, 1, (1, 0, 1, 0), "tanh"),  # 4 channels, asymmetric padding, transcendental epilogue
+    (3, 9, 9, 8, 40, 1, 1, "valid", ""),             # 8 channels 1x1, OC not a multiple of 16
+])
+def test_small_channel_rowgemm(ctx, n, h, w, ic, oc, k, s, padding, act):
+    run_case(ctx, n, h, w, ic, oc, k, s=s, padding=padding, act=act, seed=k + ic)
+
+
 def test_many_tiles_persistent_loop(ctx):
     # more tiles than SMs, several N tiles, accumulator double-buffering exercised for many iterations
     run_case(ctx, 8, 56, 56, 64, 192, 3, act="relu", seed=9)
