@@ -494,7 +494,9 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
         const uint32_t sw       = (uint32_t) (row & 7);
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // One "step" = (tile, ky). The global loads of step i+1 are issued BEFORE the stores of step i (register double
+        // buffering): 16 independent 16-byte loads in flight per thread hide the L2/HBM latency behind the copy.
+        auto fetch = [&](int tile, int ky, uint4 (&v)[8]) {
             const long long m = (long long) tile * UM_BLOCK_M + row;
             const bool live   = m < p.M;
             int n = 0, oy = 0, ox = 0;
@@ -504,29 +506,36 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
                 oy            = rem / p.OW;
                 ox            = rem - oy * p.OW;
             }
-            const int ix0 = ox * p.stride - p.pad_x, iy0 = oy * p.stride - p.pad_y;
-            for (int ky = 0; ky < p.kh; ++ky) {
-                const int iy       = iy0 + ky;
-                const bool row_ok  = live && iy >= 0 && iy < p.H;
-                const uint4* gsrc  = reinterpret_cast<const uint4*>(src_plane + (((size_t) n * p.H + (row_ok ? iy : 0)) * p.W) * 8);
-                uint4 v[8];
+            const int ix0 = ox * p.stride - p.pad_x, iy = oy * p.stride - p.pad_y + ky;
+            const bool row_ok = live && iy >= 0 && iy < p.H;
+            const uint4* gsrc = reinterpret_cast<const uint4*>(src_plane + (((size_t) n * p.H + (row_ok ? iy : 0)) * p.W) * 8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int ix = ix0 + j;
-                    v[j]         = (row_ok && j < p.kw && ix >= 0 && ix < p.W) ? __ldg(gsrc + ix) : make_uint4(0, 0, 0, 0);
-                }
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t dst = sA0 + stage * RG_A_STAGE_BYTES + row_off;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z),
-                                 "r"(v[j].w)
-                                 : "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(stage));
-                if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+            for (int j = 0; j < 8; ++j) {
+                const int ix = ix0 + j;
+                v[j]         = (row_ok && j < p.kw && ix >= 0 && ix < p.W) ? __ldg(gsrc + ix) : make_uint4(0, 0, 0, 0);
             }
+        };
+        uint4 cur[8], nxt[8];
+        int tile = blockIdx.x, ky = 0;
+        if (tile < total_tiles) fetch(tile, 0, cur);
+        while (tile < total_tiles) {
+            int ntile = tile, nky = ky + 1;
+            if (nky == p.kh) nky = 0, ntile = tile + gridDim.x;
+            if (ntile < total_tiles) fetch(ntile, nky, nxt);
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t dst = sA0 + stage * RG_A_STAGE_BYTES + row_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "r"(cur[j].x), "r"(cur[j].y), "r"(cur[j].z),
+                             "r"(cur[j].w)
+                             : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+            tile = ntile, ky = nky;
         }
     } else {
         // ---- epilogue: 4 warps, one TMEM lane quarter each ----
@@ -637,14 +646,21 @@ static TilePlan plan_tiles(int N, int OH, int OW, int stride) {
     return best;
 }
 
-static int plan_n_blk(int OC, int& tiles_oc) {
+// Output-channel tile width. The kernel is fed from L2, so the cost of one tile is ~ its K blocks x (A bytes + B bytes);
+// the layer takes waves x that. A narrower n_blk re-reads A for more oc tiles but fills more SMs when a layer has few
+// pixel tiles (7x7 and 14x14 maps): pick the width (multiple of 16, <= 128) that minimises waves x bytes per tile.
+static int plan_n_blk(int OC, int m_tiles, int rows_used, int sm_count, int& tiles_oc) {
     int best_blk = 0, best_tiles = 0;
-    double best_waste = 1e30;
-    for (int t = (OC + UM_MAX_N - 1) / UM_MAX_N; t <= (OC + 15) / 16 && t <= (OC + UM_MAX_N - 1) / UM_MAX_N + 2; ++t) {
+    double best_cost = 1e300;
+    const int t_min = (OC + UM_MAX_N - 1) / UM_MAX_N, t_max = (OC + 15) / 16;
+    for (int t = t_min; t <= t_max; ++t) {
         const int blk = std::min(UM_MAX_N, round_up((OC + t - 1) / t, 16));
         if (blk * t < OC) continue;
-        const double waste = (double) blk * t / OC + 0.02 * t; // slight preference for fewer, larger tiles
-        if (waste < best_waste) best_waste = waste, best_blk = blk, best_tiles = t;
+        const long long tiles = (long long) m_tiles * t;
+        const long long waves = (tiles + sm_count - 1) / sm_count;
+        const double cost     = (double) waves * (2.0 * rows_used * 128 + 2.0 * blk * 128 + 4096.0 /* fixed per-K-block overhead */);
+        if (cost < best_cost - 1e-9) best_cost = cost, best_blk = blk, best_tiles = t;
+        if (blk <= 16) break;
     }
     tiles_oc = best_tiles;
     return best_blk;
@@ -721,7 +737,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     SNNB_REQUIRE(tp.tw > 0, "launch_conv2d_umma: no tile plan");
     p.tw = tp.tw, p.th = tp.th, p.tn = tp.tn, p.rows_used = tp.tw * tp.th * tp.tn;
     p.tiles_x = tp.tiles_x, p.tiles_y = tp.tiles_y, p.tiles_n = tp.tiles_n;
-    p.n_blk   = plan_n_blk(out->c, p.tiles_oc);
+    p.n_blk   = plan_n_blk(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, ctx->sm_count, p.tiles_oc);
     p.ksize = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y;
     p.cblocks = (in->c + UM_BLOCK_K - 1) / UM_BLOCK_K;
     p.ICp     = round_up(in->c, 8);
