@@ -515,27 +515,37 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
                 v[j]         = (row_ok && j < p.kw && ix >= 0 && ix < p.W) ? __ldg(gsrc + ix) : make_uint4(0, 0, 0, 0);
             }
         };
-        uint4 cur[8], nxt[8];
-        int tile = blockIdx.x, ky = 0;
-        if (tile < total_tiles) fetch(tile, 0, cur);
-        while (tile < total_tiles) {
-            int ntile = tile, nky = ky + 1;
-            if (nky == p.kh) nky = 0, ntile = tile + gridDim.x;
-            if (ntile < total_tiles) fetch(ntile, nky, nxt);
+        auto publish = [&](const uint4 (&v)[8]) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t dst = sA0 + stage * RG_A_STAGE_BYTES + row_off;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "r"(cur[j].x), "r"(cur[j].y), "r"(cur[j].z),
-                             "r"(cur[j].w)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z),
+                             "r"(v[j].w)
                              : "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-            tile = ntile, ky = nky;
+        };
+        auto advance = [&](int& tile, int& ky) {
+            if (++ky == p.kh) ky = 0, tile += gridDim.x;
+        };
+        // ping-pong register buffers (no copies: a register move would wait for the very loads it is meant to overlap)
+        uint4 bufA[8], bufB[8];
+        int tile = blockIdx.x, ky = 0;
+        if (tile < total_tiles) fetch(tile, ky, bufA);
+        while (tile < total_tiles) {
+            int t1 = tile, k1 = ky;
+            advance(t1, k1);
+            if (t1 < total_tiles) fetch(t1, k1, bufB);
+            publish(bufA);
+            if (t1 >= total_tiles) break;
+            tile = t1, ky = k1;
+            advance(t1, k1);
+            if (t1 < total_tiles) fetch(t1, k1, bufA);
+            publish(bufB);
+            tile = t1, ky = k1;
         }
     } else {
         // ---- epilogue: 4 warps, one TMEM lane quarter each ----
