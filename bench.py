@@ -139,6 +139,7 @@ def run_reference(args, rank, world):
     sample = max(1, min(batch, args.cpu_sample))
     x = modelzoo.synthetic_input(key, sample)
     m = oracle.Model(path)
+    oracle.lib().orc_set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     threads = oracle.lib().orc_num_threads()
     for _ in range(max(1, min(args.warmup, 2))):
         m.run(x)
@@ -240,6 +241,10 @@ def main():
     e2e_ms = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
     parallel.barrier()
 
+    if world > 1:
+        import torch.distributed as dist
+        parallel.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 
@@ -287,6 +292,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle
+        oracle.lib().orc_set_num_threads(os.cpu_count() or 1)
         sample = max(1, min(batch, args.cpu_sample))
         om = oracle.Model(path)
         xs = x[:sample]

@@ -494,9 +494,11 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
         const uint32_t sw       = (uint32_t) (row & 7);
         int stage = 0;
         uint32_t phase = 0;
-        // One "step" = (tile, ky). The global loads of step i+1 are issued BEFORE the stores of step i (register double
-        // buffering): 16 independent 16-byte loads in flight per thread hide the L2/HBM latency behind the copy.
-        auto fetch = [&](int tile, int ky, uint4 (&v)[8]) {
+        // One "step" = (tile, ky) = one smem stage. Copies are cp.async (LDGSTS, 16 bytes, zero-fill when the tap leaves
+        // the image), so no registers are staged and two steps' worth of loads are always in flight per thread; a step
+        // is published to the MMA warp (fence.proxy.async -> mbarrier arrive) once its cp.async group has landed.
+        const uint32_t sdst0 = sA0 + row_off;
+        auto issue = [&](int tile, int ky, int stg) {
             const long long m = (long long) tile * UM_BLOCK_M + row;
             const bool live   = m < p.M;
             int n = 0, oy = 0, ox = 0;
@@ -508,44 +510,38 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
             }
             const int ix0 = ox * p.stride - p.pad_x, iy = oy * p.stride - p.pad_y + ky;
             const bool row_ok = live && iy >= 0 && iy < p.H;
-            const uint4* gsrc = reinterpret_cast<const uint4*>(src_plane + (((size_t) n * p.H + (row_ok ? iy : 0)) * p.W) * 8);
+            const __nv_bfloat16* grow = src_plane + (((size_t) n * p.H + (row_ok ? iy : 0)) * p.W) * 8;
+            const uint32_t dst = sdst0 + stg * RG_A_STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int ix = ix0 + j;
-                v[j]         = (row_ok && j < p.kw && ix >= 0 && ix < p.W) ? __ldg(gsrc + ix) : make_uint4(0, 0, 0, 0);
+                const int ix  = ix0 + j;
+                const bool ok = row_ok && j < p.kw && ix >= 0 && ix < p.W;
+                const void* src = ok ? (const void*) (grow + (size_t) ix * 8) : (const void*) src_plane;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto publish = [&](const uint4 (&v)[8]) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t dst = sA0 + stage * RG_A_STAGE_BYTES + row_off;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z),
-                             "r"(v[j].w)
-                             : "memory");
+        auto publish = [&](int stg) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(stage));
-            if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+            if (lane == 0) mbar_arrive(full_bar(stg));
         };
-        auto advance = [&](int& tile, int& ky) {
-            if (++ky == p.kh) ky = 0, tile += gridDim.x;
-        };
-        // ping-pong register buffers (no copies: a register move would wait for the very loads it is meant to overlap)
-        uint4 bufA[8], bufB[8];
-        int tile = blockIdx.x, ky = 0;
-        if (tile < total_tiles) fetch(tile, ky, bufA);
-        while (tile < total_tiles) {
-            int t1 = tile, k1 = ky;
-            advance(t1, k1);
-            if (t1 < total_tiles) fetch(t1, k1, bufB);
-            publish(bufA);
-            if (t1 >= total_tiles) break;
-            tile = t1, ky = k1;
-            advance(t1, k1);
-            if (t1 < total_tiles) fetch(t1, k1, bufA);
-            publish(bufB);
-            tile = t1, ky = k1;
+        int prev_stage = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int ky = 0; ky < p.kh; ++ky) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                issue(tile, ky, stage);
+                if (prev_stage >= 0) {
+                    asm volatile("cp.async.wait_group 1;" ::: "memory"); // everything but the group just committed has landed
+                    publish(prev_stage);
+                }
+                prev_stage = stage;
+                if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+            }
+        }
+        if (prev_stage >= 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            publish(prev_stage);
         }
     } else {
         // ---- epilogue: 4 warps, one TMEM lane quarter each ----
