@@ -164,6 +164,14 @@ int snnb_model_output_dims(const snnb_model* m, int idx, int* n, int* h, int* w,
  * D2H of output 0 (NHWC fp32, out_capacity floats) and, for classifiers (last layer Dense/softmax), the 1-based
  * class index per image (core.cpp:228-233); classes may be NULL. Synchronous. */
 int snnb_model_run(snnb_model* m, const float* host_input_nhwc, float* host_output, size_t out_capacity, int* classes_1based);
+/* Streaming variant of snnb_model_run for serving loops: submit() enqueues the H2D copy of the batch (on a dedicated copy
+ * stream, double-buffered device staging), the forward pass and the D2H copies of output 0 / class indices into the
+ * caller's buffers, and returns at once with a ticket; wait(ticket) blocks until that submission's results are in host
+ * memory. Up to two submissions may be in flight, so batch i+1's upload overlaps batch i's compute. Host buffers must be
+ * pinned for the copies to be asynchronous and must stay untouched until wait() returns. (The reference's run() is
+ * strictly synchronous, core.cpp:97-245; this is additive.) */
+int snnb_model_submit(snnb_model* m, const float* host_input_nhwc, float* host_output, size_t out_capacity, int* classes_1based, int* ticket);
+int snnb_model_wait(snnb_model* m, int ticket);
 /* Device-resident variant: inputs already uploaded with snnb_model_set_input(); forward only, asynchronous. */
 int snnb_model_set_input(snnb_model* m, int idx, const float* host_input_nhwc);
 int snnb_model_forward(snnb_model* m);

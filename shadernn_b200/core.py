@@ -358,6 +358,15 @@ class MixedInferenceCore:
         """snnb_model_run on raw host addresses (pinned buffers owned by the caller, e.g. bench.py)."""
         check(lib().snnb_model_run(self.h, in_ptr, out_ptr, out_floats, classes_ptr), "snnb_model_run")
 
+    def submit_raw(self, in_ptr, out_ptr, out_floats, classes_ptr=None):
+        """snnb_model_submit on raw (pinned) host addresses; returns the ticket for wait()."""
+        t = C.c_int()
+        check(lib().snnb_model_submit(self.h, in_ptr, out_ptr, out_floats, classes_ptr, C.byref(t)), "snnb_model_submit")
+        return t.value
+
+    def wait(self, ticket):
+        check(lib().snnb_model_wait(self.h, int(ticket)), "snnb_model_wait")
+
     def set_input(self, images, idx=0):
         images = _f32(images)
         check(lib().snnb_model_set_input(self.h, idx, _ptr(images)), "snnb_model_set_input")

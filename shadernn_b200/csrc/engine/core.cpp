@@ -24,6 +24,15 @@ MixedInferenceCore::~MixedInferenceCore() {
     if (scratchArena) cudaFree(scratchArena);
     if (ioStage) cudaFree(ioStage);
     if (argmaxDev) cudaFree(argmaxDev);
+    for (auto& sl : slots) {
+        if (sl.stageIn) cudaFree(sl.stageIn);
+        if (sl.stageOut) cudaFree(sl.stageOut);
+        if (sl.argmax) cudaFree(sl.argmax);
+        if (sl.h2dDone) cudaEventDestroy(sl.h2dDone);
+        if (sl.stageFree) cudaEventDestroy(sl.stageFree);
+        if (sl.resultReady) cudaEventDestroy(sl.resultReady);
+    }
+    if (copyStream) cudaStreamDestroy(copyStream);
 }
 
 std::unique_ptr<MixedInferenceCore> MixedInferenceCore::create(snnb_context* ctx, const std::string& modelFileName, const ShaderGenOptions& options,
@@ -351,6 +360,68 @@ int MixedInferenceCore::run(const float* hostInput, float* hostOutput, size_t ca
     }
     if (classes1 && isClassifier && outIdx >= 0)
         for (uint32_t i = 0; i < options.batch; ++i) classes1[i] += 1; // core.cpp:228-233: argmax + 1
+    return 0;
+}
+
+// ---- streaming (additive to the reference's synchronous run) ---------------------------------------------------------
+int MixedInferenceCore::ensureStreaming() {
+    if (copyStream) return 0;
+    SNNB_CUDA_OK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+    for (auto& sl : slots) {
+        SNNB_CUDA_OK(cudaMalloc(&sl.stageIn, ioStageBytes));
+        SNNB_CUDA_OK(cudaMalloc(&sl.stageOut, ioStageBytes));
+        SNNB_CUDA_OK(cudaMalloc(&sl.argmax, sizeof(int) * options.batch));
+        SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.h2dDone, cudaEventDisableTiming));
+        SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.stageFree, cudaEventDisableTiming));
+        SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.resultReady, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int MixedInferenceCore::submit(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket) {
+    SNNB_REQUIRE(hostInput && ticket, "submit: null argument");
+    SNNB_REQUIRE(!yolo, "submit: detection models decode on the host; use run()");
+    if (ensureStreaming()) return 1;
+    Slot& sl = slots[nextTicket & 1];
+    SNNB_REQUIRE(!sl.busy, "submit: two submissions are already in flight; wait() on ticket %d first", nextTicket - 2);
+    int outIdx = 0;
+    snnb_tensor* in  = inputLayers[0]->output;
+    snnb_tensor* out = outputLayers[outIdx]->output;
+    const size_t inBytes = in->pixels() * in->c * sizeof(float), outFloats = out->pixels() * out->c;
+    SNNB_REQUIRE(!hostOutput || capacityFloats >= outFloats, "submit: output buffer too small (%zu < %zu floats)", capacityFloats, outFloats);
+    // copy stream: wait until the split kernel of the submission that last used this slot has consumed the staging
+    if (sl.everUsed) SNNB_CUDA_OK(cudaStreamWaitEvent(copyStream, sl.stageFree, 0));
+    SNNB_CUDA_OK(cudaMemcpyAsync(sl.stageIn, hostInput, inBytes, cudaMemcpyHostToDevice, copyStream));
+    SNNB_CUDA_OK(cudaEventRecord(sl.h2dDone, copyStream));
+    // compute stream
+    SNNB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, sl.h2dDone, 0));
+    if (launch_split_f32(ctx, sl.stageIn, in)) return 1;
+    SNNB_CUDA_OK(cudaEventRecord(sl.stageFree, ctx->stream));
+    if (forward()) return 1;
+    if (hostOutput) {
+        if (launch_merge_f32(ctx, out, sl.stageOut)) return 1;
+        SNNB_CUDA_OK(cudaMemcpyAsync(hostOutput, sl.stageOut, outFloats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    sl.classesHost = nullptr;
+    if (classes1 && isClassifier) {
+        if (launch_argmax(ctx, out, sl.argmax)) return 1;
+        SNNB_CUDA_OK(cudaMemcpyAsync(classes1, sl.argmax, sizeof(int) * options.batch, cudaMemcpyDeviceToHost, ctx->stream));
+        sl.classesHost = classes1;
+    }
+    SNNB_CUDA_OK(cudaEventRecord(sl.resultReady, ctx->stream));
+    sl.busy = sl.everUsed = true;
+    *ticket = nextTicket++;
+    return 0;
+}
+
+int MixedInferenceCore::wait(int ticket) {
+    SNNB_REQUIRE(ticket >= 0 && ticket < nextTicket && ticket >= nextTicket - 2, "wait: ticket %d is not in flight", ticket);
+    Slot& sl = slots[ticket & 1];
+    SNNB_REQUIRE(sl.busy, "wait: ticket %d was already waited for", ticket);
+    SNNB_CUDA_OK(cudaEventSynchronize(sl.resultReady));
+    if (sl.classesHost)
+        for (uint32_t i = 0; i < options.batch; ++i) sl.classesHost[i] += 1; // core.cpp:228-233: argmax + 1
+    sl.busy = false;
     return 0;
 }
 

@@ -306,6 +306,9 @@ public:
     int getOutput(int idx, float* host, size_t capacityFloats);
     // run(RunParameters) end to end (core.cpp:97-245): H2D, forward, D2H, class index
     int run(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1);
+    // streaming: double-buffered submit/wait (H2D of batch i+1 overlaps compute of batch i)
+    int submit(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
+    int wait(int ticket);
     int layerOutput(int layerId, float* host, size_t capacityFloats);
     int timeLayers(std::vector<float>& ms);
     int dumpOutputs(const std::string& dir);
@@ -332,6 +335,18 @@ private:
     size_t ioStageBytes = 0;
     int* argmaxDev   = nullptr;
     dp::YOLOLayer* yolo = nullptr;
+    // streaming state
+    struct Slot {
+        float* stageIn = nullptr;   // device fp32 staging for this slot's input batch
+        float* stageOut = nullptr;  // device fp32 staging for output 0
+        int* argmax = nullptr;
+        cudaEvent_t h2dDone = nullptr, stageFree = nullptr, resultReady = nullptr;
+        int* classesHost = nullptr;
+        bool busy = false, everUsed = false;
+    } slots[2];
+    cudaStream_t copyStream = nullptr;
+    int nextTicket = 0;
+    int ensureStreaming();
 };
 
 } // namespace snn

@@ -97,6 +97,15 @@ int snnb_model_run(snnb_model* m, const float* host_input, float* host_output, s
     SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->run(host_input, host_output, out_capacity, classes);
 }
+int snnb_model_submit(snnb_model* m, const float* host_input, float* host_output, size_t out_capacity, int* classes, int* ticket) {
+    SNNB_REQUIRE(m, "snnb_model_submit: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
+    return m->core->submit(host_input, host_output, out_capacity, classes, ticket);
+}
+int snnb_model_wait(snnb_model* m, int ticket) {
+    SNNB_REQUIRE(m, "snnb_model_wait: null model");
+    return m->core->wait(ticket);
+}
 int snnb_model_set_input(snnb_model* m, int idx, const float* host_input) {
     SNNB_REQUIRE(m, "snnb_model_set_input: null model");
     return m->core->setInput(idx, host_input);

@@ -377,8 +377,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // new layout: the whole weight panel [n_blk][kh x 64] (hi+lo) is TMA-loaded ONCE per persistent CTA and stays in
 // shared memory. A cannot come from a TMA box (the window of output pixel ox starts at input pixel ox*s - pad, an
 // overlapping strided view), so 8 producer warps build each A stage with plain 16-byte copies global -> swizzled smem
-// (no arithmetic: the operands are already split-bf16), zero vectors where the window leaves the image (constant
-// padding), then fence.proxy.async and hand the stage to the MMA warp through the same full/empty mbarrier ring.
+// (cp.async; no arithmetic: the operands are already split-bf16), zero-filled where the window leaves the image
+// (constant padding); cp.async.mbarrier.arrive hands the stage to the MMA warp through the same full/empty ring.
 // Tiles are 128 consecutive output pixels in (n, oy, ox) raster order: no overhang, every MMA row is live.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RG_STAGES        = 3;
@@ -423,7 +423,7 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
         tma_prefetch_desc(&tmB_hi);
         tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < RG_STAGES; ++s) {
-            mbar_init(full_bar(s), RG_PROD_WARPS); // one arrive per producer warp
+            mbar_init(full_bar(s), 32 * RG_PROD_WARPS); // every producer thread's cp.async completion arrives (noinc)
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -495,8 +495,8 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
         int stage = 0;
         uint32_t phase = 0;
         // One "step" = (tile, ky) = one smem stage. Copies are cp.async (LDGSTS, 16 bytes, zero-fill when the tap leaves
-        // the image), so no registers are staged and two steps' worth of loads are always in flight per thread; a step
-        // is published to the MMA warp (fence.proxy.async -> mbarrier arrive) once its cp.async group has landed.
+        // the image): no registers are staged, nothing is waited for, and each thread's completion is reported to the
+        // stage's full barrier by cp.async.mbarrier.arrive.noinc.
         const uint32_t sdst0 = sA0 + row_off;
         auto issue = [&](int tile, int ky, int stg) {
             const long long m = (long long) tile * UM_BLOCK_M + row;
@@ -519,29 +519,16 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
                 const void* src = ok ? (const void*) (grow + (size_t) ix * 8) : (const void*) src_plane;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            // completion of THIS thread's copies arrives on the stage's full barrier - no wait, no fence on the producer
+            // side (the pattern of cutlass' sm100 cp.async->UMMA collective): producers run ahead as far as `empty` allows
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stg)) : "memory");
         };
-        auto publish = [&](int stg) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(stg));
-        };
-        int prev_stage = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int ky = 0; ky < p.kh; ++ky) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 issue(tile, ky, stage);
-                if (prev_stage >= 0) {
-                    asm volatile("cp.async.wait_group 1;" ::: "memory"); // everything but the group just committed has landed
-                    publish(prev_stage);
-                }
-                prev_stage = stage;
                 if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
             }
-        }
-        if (prev_stage >= 0) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            publish(prev_stage);
         }
     } else {
         // ---- epilogue: 4 warps, one TMEM lane quarter each ----

@@ -169,3 +169,36 @@ def test_model_error_paths(ctx, tmp_path):
     trunc.write_text('{"numLayers": {"count": 2}')
     with pytest.raises(SnnbError):
         core.MixedInferenceCore(ctx, str(trunc))
+
+
+def test_streaming_submit_wait_matches_synchronous_run(ctx, model_dir):
+    # snnb_model_submit / snnb_model_wait: double-buffered pipeline, results identical to run(), tickets enforce depth 2
+    import ctypes as C
+
+    from shadernn_b200._lib import SnnbError
+    path, _ = modelzoo.build("resnet18", model_dir, input_hw=(64, 64))
+    m = core.MixedInferenceCore(ctx, path, batch=4, input_hw=(64, 64), fuse=True, use_cuda_graph=True)
+    xs = [modelzoo.synthetic_input("resnet18", 4, (64, 64), seed=s) for s in range(5)]
+    want = [m.run(x) for x in xs]
+    outs = [np.empty(m.output_shape(0), np.float32) for _ in xs]
+    clss = [(C.c_int * 4)() for _ in xs]
+    ins = [np.ascontiguousarray(x) for x in xs]
+    tickets = []
+    for i in range(5):
+        t = m.submit_raw(ins[i].ctypes.data_as(C.c_void_p), outs[i].ctypes.data_as(C.c_void_p), outs[i].size, clss[i])
+        tickets.append(t)
+        if i >= 1:
+            m.wait(tickets[i - 1])
+    with pytest.raises(SnnbError):
+        m.wait(tickets[0])  # already consumed
+    m.wait(tickets[-1])
+    for i in range(5):
+        assert np.array_equal(outs[i], want[i][0])
+        assert list(clss[i]) == list(want[i][1])
+    # a third submission without waiting is refused
+    t0 = m.submit_raw(ins[0].ctypes.data_as(C.c_void_p), outs[0].ctypes.data_as(C.c_void_p), outs[0].size, clss[0])
+    t1 = m.submit_raw(ins[1].ctypes.data_as(C.c_void_p), outs[1].ctypes.data_as(C.c_void_p), outs[1].size, clss[1])
+    with pytest.raises(SnnbError):
+        m.submit_raw(ins[2].ctypes.data_as(C.c_void_p), outs[2].ctypes.data_as(C.c_void_p), outs[2].size, clss[2])
+    m.wait(t0)
+    m.wait(t1)
