@@ -1,0 +1,82 @@
+// Microbenchmark: issue rate / dependent-chain latency of tcgen05.mma (kind::f16, bf16, cta_group::1, M=128) for
+// several N, with all MMAs accumulating into ONE TMEM tile vs alternating between two tiles. No loads: smem is
+// whatever it is (values irrelevant). One CTA per SM. Prints clocks per MMA.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_microbench tools/umma_microbench.cu && ./umma_microbench
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24); }
+
+__global__ void __launch_bounds__(64, 1) bench(int N, int iters, int two_acc, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero operands so nothing overflows
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4u * i), "r"(0));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = slot;
+    if (warp == 1 && lane == 0) {
+        const uint64_t a = make_desc(base), b = make_desc(base + 16384);
+        const uint32_t idesc = make_idesc(128, N);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tmem + ((two_acc && (i & 1)) ? 256u : 0u);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a + 2u * (i & 3)),
+                         "l"(b + 2u * (i & 3)), "r"(idesc), "r"(i > 1 ? 1u : 0u)
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+        }
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+int main() {
+    long long* d;
+    cudaMalloc(&d, 8);
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+    const int iters = 4096;
+    for (int grid : {1, 148})
+        for (int two : {0, 1})
+            for (int N : {16, 32, 64, 96, 128, 192, 256}) {
+                bench<<<grid, 64, 60 * 1024>>>(N, iters, two, d);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) {
+                    printf("error %s\n", cudaGetErrorString(e));
+                    return 1;
+                }
+                long long c;
+                cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+                printf("grid %3d  N %3d  %s  %7.1f clk/MMA  (%.0f MAC/clk/SM)\n", grid, N, two ? "two accumulators" : "one accumulator ", (double) c / iters,
+                       128.0 * N * 16 * iters / (double) c);
+            }
+    return 0;
+}
