@@ -125,10 +125,9 @@ void orc_same_padding(int k, int is_same, int* offs) {
 // 0/1 constant (out of range -> zero), 2 replicate (clamp), 3 reflect (-i ; 2n-2-i).
 static inline int orc_src_coord(int s, int n, int mode) {
     if (mode == 2) return std::min(std::max(s, 0), n - 1);
-    if (mode == 3) {
+    if (mode == 3) { // one reflection; a coordinate still outside reads zero like an out-of-range texelFetch
         s = (s < 0) ? -s : s;
         s = (s >= n) ? 2 * n - 2 - s : s;
-        return s;
     }
     return (s >= 0 && s < n) ? s : -1;
 }

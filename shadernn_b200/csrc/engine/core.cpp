@@ -171,7 +171,24 @@ bool MixedInferenceCore::init(std::string& err) {
             L->residual = outOf.at(resolve(L->prevLayers.back()));
         }
         for (size_t k = 0; k < nin; ++k) L->inputs.push_back(outOf.at(resolve(L->prevLayers[k])));
-        if (L->typeName == "Conv2D") static_cast<Conv2DLayer*>(L)->algo = options.convAlgo;
+        if (L->typeName == "Conv2D") {
+            auto* cl  = static_cast<Conv2DLayer*>(L);
+            cl->algo = options.convAlgo;
+            // weights are not packed yet: probe with a weights stub that says "tensor path available"
+            int ph = 0, pw = 0;
+            snnb_weights probe_w;
+            probe_w.w_hi = probe_w.w_lo = reinterpret_cast<__nv_bfloat16*>(1);
+            std::swap(cl->weights, probe_w);
+            const bool prepad = cl->wantsPrepad(L->inputs[0], L->output, options.convAlgo, ph, pw);
+            std::swap(cl->weights, probe_w);
+            if (prepad) {
+                if (tensor_alloc(ctx, N, ph, pw, L->inputs[0]->c, &cl->prepadded)) {
+                    err = get_error();
+                    return false;
+                }
+                ownedTensors.push_back(cl->prepadded);
+            }
+        }
         if (L->typeName == "Dense") {
             auto* dl = static_cast<DenseLayer*>(L);
             if (L->inputs[0]->h * L->inputs[0]->w != 1) {

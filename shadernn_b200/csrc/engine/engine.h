@@ -156,7 +156,10 @@ class Conv2DLayer : public GenericModelLayer {
 public:
     Conv2DDesc _desc;
     int algo = SNNB_ALGO_AUTO;
-    // pad folded in from a preceding Pad layer (fusion)
+    // Replicate / reflect padding on the tensor path: the TMA unit can only zero-fill, so the engine materialises the
+    // padded input once (pad kernel, vk_pad.comp semantics) and runs the tcgen05 kernel over it with zero padding.
+    snnb_tensor* prepadded = nullptr;
+    bool wantsPrepad(const snnb_tensor* in, const snnb_tensor* out, int convAlgo, int& ph, int& pw) const;
     Transform getOutputScaleDimAdjustment() const override; // conv2d.cpp:102-113
     void getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const override;
     void packWeights(snnb::PackedHost& p) override;

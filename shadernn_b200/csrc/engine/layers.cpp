@@ -71,9 +71,27 @@ static int padModeId(const std::string& m) { // conv2dVulkan.cpp:73-80
     if (m == "reflect") return SNNB_PAD_REFLECT;
     return SNNB_PAD_NONE;
 }
+bool Conv2DLayer::wantsPrepad(const snnb_tensor* in, const snnb_tensor* out, int convAlgo, int& ph, int& pw) const {
+    const int mode = padModeId(_desc.padding.mode);
+    if (!(mode == SNNB_PAD_REPLICATE || mode == SNNB_PAD_REFLECT) || _desc.kernelSize <= 1 || convAlgo == SNNB_ALGO_SIMT) return false;
+    ConvArgs probe {in, nullptr, const_cast<snnb_tensor*>(out), &weights, (int) _desc.kernelSize, (int) _desc.stride, 0, 0, SNNB_PAD_CONSTANT, 0, 0.0f};
+    if (!conv2d_umma_supported(probe)) return false;
+    // the window of the last output pixel ends at (O-1)*s + k - 1 in padded coordinates
+    ph = (out->h - 1) * (int) _desc.stride + (int) _desc.kernelSize;
+    pw = (out->w - 1) * (int) _desc.stride + (int) _desc.kernelSize;
+    return true;
+}
+
 int Conv2DLayer::run(snnb_context* ctx, const ExecOptions& opt) {
     uint32_t offs[4];
     _desc.padding.offsets((int) _desc.kernelSize, true, offs);
+    if (prepadded) {
+        // padded[y][x] = in[reflect/replicate(y - pad_y)][..(x - pad_x)] with the conv's own (pad_x, pad_y) = (T, L) mapping
+        if (launch_pad(ctx, inputs[0], prepadded, (int) offs[0], (int) offs[2], padModeId(_desc.padding.mode))) return 1;
+        ConvArgs a {prepadded, residual, output, &weights, (int) _desc.kernelSize, (int) _desc.stride, 0, 0, SNNB_PAD_CONSTANT,
+                    fusedAct >= 0 ? fusedAct : _desc.activation.id, fusedAct >= 0 ? fusedAlpha : _desc.activation.alpha};
+        return launch_conv2d_umma(ctx, a);
+    }
     ConvArgs a;
     a.in = inputs[0], a.residual = residual, a.out = output, a.w = &weights;
     a.k = (int) _desc.kernelSize, a.stride = (int) _desc.stride;

@@ -82,10 +82,9 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
 // Source coordinate under a padding mode (vk_conv2d.comp:168-218): returns -1 for "reads zero".
 __device__ __forceinline__ int src_coord(int s, int n, int mode) {
     if (mode == SNNB_PAD_REPLICATE) return min(max(s, 0), n - 1);
-    if (mode == SNNB_PAD_REFLECT) {
+    if (mode == SNNB_PAD_REFLECT) { // one reflection, as the shader does; still outside -> reads zero (never faults)
         s = (s < 0) ? -s : s;
         s = (s >= n) ? 2 * n - 2 - s : s;
-        return s;
     }
     return (s >= 0 && s < n) ? s : -1;
 }
