@@ -209,6 +209,7 @@ int snnb_weights_pack_conv2d(snnb_context* ctx, const snnb_conv_desc* d, const f
     SNNB_REQUIRE(d->in_channels > 0 && d->out_channels > 0 && d->kernel > 0, "snnb_weights_pack_conv2d: bad desc");
     PackedHost p;
     pack_conv2d_host(d->in_channels, d->out_channels, d->kernel, w_oihw, bias, g, b, m, v, p);
+    pack_rowwin_host(p, d->stride, d->pad_x);
     return make_weights(ctx, p, out);
 }
 int snnb_weights_pack_depthwise(snnb_context* ctx, const snnb_conv_desc* d, const float* w_chw, const float* bias, const float* g, const float* b,

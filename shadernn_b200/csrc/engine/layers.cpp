@@ -53,6 +53,12 @@ void Conv2DLayer::getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const { /
     GenericModelLayer::getOutputDims(w, h, d);
     d = numOutputPlanes;
 }
+static int padModeId(const std::string& m) { // conv2dVulkan.cpp:73-80
+    if (m == "constant") return SNNB_PAD_CONSTANT;
+    if (m == "replicate") return SNNB_PAD_REPLICATE;
+    if (m == "reflect") return SNNB_PAD_REFLECT;
+    return SNNB_PAD_NONE;
+}
 static const float* bnv(const std::map<std::string, std::vector<float>>& bn, const char* key) {
     auto it = bn.find(key);
     return (it == bn.end() || it->second.empty()) ? nullptr : it->second.data();
@@ -63,13 +69,13 @@ void Conv2DLayer::packWeights(PackedHost& p) {
     pack_conv2d_host((int) numInputPlanes, (int) numOutputPlanes, (int) _desc.kernelSize, _desc.weights.data(), _desc.biases.empty() ? nullptr : _desc.biases.data(),
                      use ? bnv(bn, "gamma") : nullptr, use ? bnv(bn, "beta") : nullptr, use ? bnv(bn, "movingMean") : nullptr,
                      use ? bnv(bn, "movingVariance") : nullptr, p);
+    {
+        uint32_t offs[4];
+        _desc.padding.offsets((int) _desc.kernelSize, true, offs);
+        const int mode = padModeId(_desc.padding.mode);
+        if (mode == SNNB_PAD_NONE || mode == SNNB_PAD_CONSTANT) pack_rowwin_host(p, (int) _desc.stride, _desc.kernelSize == 1 ? 0 : (int) offs[0]);
+    }
     std::vector<float>().swap(_desc.weights); // host copy no longer needed
-}
-static int padModeId(const std::string& m) { // conv2dVulkan.cpp:73-80
-    if (m == "constant") return SNNB_PAD_CONSTANT;
-    if (m == "replicate") return SNNB_PAD_REPLICATE;
-    if (m == "reflect") return SNNB_PAD_REFLECT;
-    return SNNB_PAD_NONE;
 }
 bool Conv2DLayer::wantsPrepad(const snnb_tensor* in, const snnb_tensor* out, int convAlgo, int& ph, int& pw) const {
     const int mode = padModeId(_desc.padding.mode);

@@ -369,66 +369,78 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small-input-channel convolution (IC <= 8: the 7x7/3x3 RGB stems, ESPCN's 1-channel 5x5) on the same tensor cores.
+// Small-input-channel convolution (IC <= 8: the 7x7 / 3x3 RGB stems, ESPCN's 1-channel 5x5) on the same tensor cores,
+// with a ZERO-COPY sliding-window A operand.
 //
-// With C padded to 8 bf16 (= one 16-byte vector per pixel and plane) the kw taps of one filter row are CONTIGUOUS in
-// NHWC memory: kw * 16 bytes. So K is ordered (ky | kx, c): one 64-element K block per filter row ky, of which
-// kw*8 <= 64 elements are live - exactly the column order the packed weights already have (pack.cpp), so B needs no
-// new layout: the whole weight panel [n_blk][kh x 64] (hi+lo) is TMA-loaded ONCE per persistent CTA and stays in
-// shared memory. A cannot come from a TMA box (the window of output pixel ox starts at input pixel ox*s - pad, an
-// overlapping strided view), so 8 producer warps build each A stage with plain 16-byte copies global -> swizzled smem
-// (cp.async; no arithmetic: the operands are already split-bf16), zero-filled where the window leaves the image
-// (constant padding); cp.async.mbarrier.arrive hands the stage to the MMA warp through the same full/empty ring.
-// Tiles are 128 consecutive output pixels in (n, oy, ox) raster order: no overhang, every MMA row is live.
+// With C padded to 8 bf16 one pixel is ONE 16-byte vector per plane = exactly one K "chunk" of a tcgen05 K-major
+// operand. In the un-swizzled (SWIZZLE_NONE) canonical layout row m / chunk c of A is read from
+//        start + (m/8)*SBO + (m%8)*16 B + c*LBO,
+// and nothing stops LBO from being 16 B: chunk c of row m is then simply pixel m + c of a dense pixel row in shared
+// memory - the convolution's sliding window, expressed in the descriptor (probed on B200: tools/umma_desc_probe.cu).
+// So for every filter row ky the producer TMA-loads ONE dense row segment per column parity (for stride 2 the even and
+// odd input columns are de-interleaved by the tensor map's 32-byte pixel stride; out-of-image pixels are zero-filled =
+// constant padding) and the MMA warp issues one K=16 step per pair of taps: no im2col, no producer warps, no copies.
+// L2 -> SM traffic per 128-pixel tile: kh * s * ~136 * 16 B * 2 planes (61 KB for the 7x7 stem) instead of 224 KB of
+// gathered 16-byte requests. The weight panel [kh][n_blk][64] (hi + lo, K columns in RowPlan order) is loaded once per
+// persistent CTA and stays resident. Tiles = up to 128 consecutive output pixels of one output row.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RG_STAGES        = 3;
-constexpr int RG_PROD_WARPS    = 8;
-constexpr int RG_EPI_WARPS     = 4;
-constexpr int RG_THREADS       = 64 + 32 * (RG_PROD_WARPS + RG_EPI_WARPS);
-constexpr int RG_MAX_KH        = 7;
-constexpr int RG_MAX_N         = 64;
-constexpr int RG_B_PLANE_BYTES = RG_MAX_KH * RG_MAX_N * 128; // [ky][n_blk rows x 128 B]
-constexpr int RG_A_STAGE_BYTES = 2 * UM_A_BYTES;             // A_hi + A_lo
-constexpr int RG_SMEM_BYTES    = 2 * RG_B_PLANE_BYTES + RG_STAGES * RG_A_STAGE_BYTES + 1024 + 256;
+constexpr int RW_STAGES        = 8;
+constexpr int RW_EPI_WARPS     = 4;
+constexpr int RW_THREADS       = 64 + 32 * RW_EPI_WARPS;
+constexpr int RW_MAX_KH        = 8;
+constexpr int RW_MAX_N         = 64;
+constexpr int RW_BOXW          = 144;                          // 128 tile pixels + up to 8 of window overhang, padded
+constexpr int RW_ARR_BYTES     = RW_BOXW * 16;                 // one (plane, parity) pixel row segment
+constexpr int RW_STAGE_BYTES   = 4 * RW_ARR_BYTES;             // hi/lo x parity 0/1 = 9216 B
+constexpr int RW_B_PLANE_BYTES = RW_MAX_KH * RW_MAX_N * 128;   // [ky][n_blk rows x 128 B]
+constexpr int RW_SMEM_BYTES    = 2 * RW_B_PLANE_BYTES + RW_STAGES * RW_STAGE_BYTES + 1024 + 256;
 
-struct RowGemmParams {
-    const __nv_bfloat16* in_hi;
-    const __nv_bfloat16* in_lo;
+struct RowWinParams {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     const float* bias;
-    int N, H, W, OH, OW, OC, OCp, n_blk;
-    int kh, kw, stride, pad_x, pad_y;
+    int N, OH, OW, OC, OCp, n_blk, ocr;
+    int kh, stride, pad_y;
+    int tiles_x;
+    int parities, dmin[2];
+    int ksteps, ks_parity[4], ks_erel[4];
     int act;
     float alpha;
-    long long M; // N*OH*OW
 };
 
-__global__ void __launch_bounds__(RG_THREADS, 1)
-conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const RowGemmParams p) {
+// SWIZZLE_NONE K-major descriptor with an overlapping K stride: LBO = 16 B (next chunk = next pixel), SBO = 128 B
+// (8 rows x 16 B), version 1, layout type 0.
+__device__ __forceinline__ uint64_t make_window_desc(uint32_t saddr) { return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (8ull << 32) | (1ull << 46); }
+
+__global__ void __launch_bounds__(RW_THREADS, 1)
+conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_constant__ CUtensorMap tmA_hi1, const __grid_constant__ CUtensorMap tmA_lo0,
+                   const __grid_constant__ CUtensorMap tmA_lo1, const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   const RowWinParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sB_hi = smem_base, sB_lo = smem_base + RG_B_PLANE_BYTES;
-    const uint32_t sA0      = smem_base + 2 * RG_B_PLANE_BYTES;
-    const uint32_t bar_base = sA0 + RG_STAGES * RG_A_STAGE_BYTES;
+    const uint32_t sB_hi = smem_base, sB_lo = smem_base + RW_B_PLANE_BYTES;
+    const uint32_t sA0      = smem_base + 2 * RW_B_PLANE_BYTES;
+    const uint32_t bar_base = sA0 + RW_STAGES * RW_STAGE_BYTES;
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar      = [&](int s) { return bar_base + 8u * (RG_STAGES + s); };
-    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * RG_STAGES + a); };
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * RG_STAGES + 2 + a); };
-    const uint32_t b_bar     = bar_base + 8u * (2 * RG_STAGES + 4);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * RG_STAGES + 5);
+    auto empty_bar      = [&](int s) { return bar_base + 8u * (RW_STAGES + s); };
+    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * RW_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * RW_STAGES + 2 + a); };
+    const uint32_t b_bar     = bar_base + 8u * (2 * RW_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * RW_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi0);
+        tma_prefetch_desc(&tmA_lo0);
         tma_prefetch_desc(&tmB_hi);
         tma_prefetch_desc(&tmB_lo);
-        for (int s = 0; s < RG_STAGES; ++s) {
-            mbar_init(full_bar(s), 32 * RG_PROD_WARPS); // every producer thread's cp.async completion arrives (noinc)
+        for (int s = 0; s < RW_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), RG_EPI_WARPS);
+            mbar_init(tmem_empty_bar(a), RW_EPI_WARPS);
         }
         mbar_init(b_bar, 1);
         fence_barrier_init();
@@ -440,19 +452,39 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int total_tiles = (int) ((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M);
+    const int total_tiles = p.N * p.OH * p.tiles_x;
 
     if (warp == 0) {
-        // ---- weight panel: loaded once, resident for the CTA's lifetime ----
         if (lane == 0) {
+            // weight panel: once per CTA
             mbar_expect_tx(b_bar, 2u * (uint32_t) p.kh * (uint32_t) p.n_blk * 128u);
             for (int ky = 0; ky < p.kh; ++ky) {
-                tma_load_2d(sB_hi + ky * p.n_blk * 128, &tmB_hi, b_bar, ky * p.kw * 8, 0);
-                tma_load_2d(sB_lo + ky * p.n_blk * 128, &tmB_lo, b_bar, ky * p.kw * 8, 0);
+                tma_load_2d(sB_hi + ky * p.n_blk * 128, &tmB_hi, b_bar, 0, ky * p.ocr);
+                tma_load_2d(sB_lo + ky * p.n_blk * 128, &tmB_lo, b_bar, 0, ky * p.ocr);
+            }
+            // activation row segments
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = 2u * (uint32_t) p.parities * RW_ARR_BYTES;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int xt = tile % p.tiles_x, oy = (tile / p.tiles_x) % p.OH, n = tile / (p.tiles_x * p.OH);
+                const int ox0 = xt * UM_BLOCK_M;
+                for (int ky = 0; ky < p.kh; ++ky) {
+                    const int iy = oy * p.stride - p.pad_y + ky; // out of range -> the whole row is zero-filled
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), tx_bytes);
+                    tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                    tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                    if (p.parities == 2) {
+                        tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                        tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                    }
+                    if (++stage == RW_STAGES) stage = 0, phase ^= 1u;
+                }
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer ----
         mbar_wait(b_bar, 0);
         int stage = 0;
         uint32_t phase = 0;
@@ -463,71 +495,25 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * RG_MAX_N);
+            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * RW_MAX_N);
             for (int ky = 0; ky < p.kh; ++ky) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sA = sA0 + stage * RG_A_STAGE_BYTES;
-                    const uint64_t a_hi = make_smem_desc(sA), a_lo = make_smem_desc(sA + UM_A_BYTES);
+                    const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
                     const uint64_t b_hi = make_smem_desc(sB_hi + ky * p.n_blk * 128), b_lo = make_smem_desc(sB_lo + ky * p.n_blk * 128);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_hi + 2u * j, idesc, (ky > 0 || j > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, a_lo + 2u * j, b_hi + 2u * j, idesc, 1u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_lo + 2u * j, idesc, 1u);
+                    for (int q = 0; q < p.ksteps; ++q) {
+                        const uint32_t off = (uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u;
+                        const uint64_t a_hi = make_window_desc(sA + off), a_lo = make_window_desc(sA + 2 * RW_ARR_BYTES + off);
+                        umma_bf16(d_tmem, a_hi, b_hi + 2u * q, idesc, (ky > 0 || q > 0) ? 1u : 0u);
+                        umma_bf16(d_tmem, a_lo, b_hi + 2u * q, idesc, 1u);
+                        umma_bf16(d_tmem, a_hi, b_lo + 2u * q, idesc, 1u);
+                    }
                     umma_commit(empty_bar(stage));
                     if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
                 }
                 __syncwarp();
-                if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
-            }
-        }
-    } else if (warp < 2 + RG_PROD_WARPS) {
-        // ---- A producers: 256 threads, thread -> (row, plane); per stage 8 x 16-byte chunks of one 128-byte row ----
-        const int t     = threadIdx.x - 64;
-        const int row   = t & 127;
-        const int plane = t >> 7;
-        const __nv_bfloat16* src_plane = plane ? p.in_lo : p.in_hi;
-        const uint32_t row_off  = (uint32_t) plane * UM_A_BYTES + (uint32_t) row * 128u;
-        const uint32_t sw       = (uint32_t) (row & 7);
-        int stage = 0;
-        uint32_t phase = 0;
-        // One "step" = (tile, ky) = one smem stage. Copies are cp.async (LDGSTS, 16 bytes, zero-fill when the tap leaves
-        // the image): no registers are staged, nothing is waited for, and each thread's completion is reported to the
-        // stage's full barrier by cp.async.mbarrier.arrive.noinc.
-        const uint32_t sdst0 = sA0 + row_off;
-        auto issue = [&](int tile, int ky, int stg) {
-            const long long m = (long long) tile * UM_BLOCK_M + row;
-            const bool live   = m < p.M;
-            int n = 0, oy = 0, ox = 0;
-            if (live) {
-                n             = (int) (m / ((long long) p.OH * p.OW));
-                const int rem = (int) (m - (long long) n * p.OH * p.OW);
-                oy            = rem / p.OW;
-                ox            = rem - oy * p.OW;
-            }
-            const int ix0 = ox * p.stride - p.pad_x, iy = oy * p.stride - p.pad_y + ky;
-            const bool row_ok = live && iy >= 0 && iy < p.H;
-            const __nv_bfloat16* grow = src_plane + (((size_t) n * p.H + (row_ok ? iy : 0)) * p.W) * 8;
-            const uint32_t dst = sdst0 + stg * RG_A_STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ix  = ix0 + j;
-                const bool ok = row_ok && j < p.kw && ix >= 0 && ix < p.W;
-                const void* src = ok ? (const void*) (grow + (size_t) ix * 8) : (const void*) src_plane;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + ((((uint32_t) j) ^ sw) << 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
-            }
-            // completion of THIS thread's copies arrives on the stage's full barrier - no wait, no fence on the producer
-            // side (the pattern of cutlass' sm100 cp.async->UMMA collective): producers run ahead as far as `empty` allows
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stg)) : "memory");
-        };
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int ky = 0; ky < p.kh; ++ky) {
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                issue(tile, ky, stage);
-                if (++stage == RG_STAGES) stage = 0, phase ^= 1u;
+                if (++stage == RW_STAGES) stage = 0, phase ^= 1u;
             }
         }
     } else {
@@ -541,13 +527,15 @@ conv_rowgemm_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_con
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
-            const long long m = (long long) tile * UM_BLOCK_M + row;
-            const bool valid  = m < p.M;
-            __nv_bfloat16* o_hi = p.out_hi + (size_t) m * p.OCp;
-            __nv_bfloat16* o_lo = p.out_lo + (size_t) m * p.OCp;
+            const int xt = tile % p.tiles_x, oy = (tile / p.tiles_x) % p.OH, n = tile / (p.tiles_x * p.OH);
+            const int ox      = xt * UM_BLOCK_M + row;
+            const bool valid  = ox < p.OW;
+            const size_t base = (((size_t) n * p.OH + oy) * p.OW + ox) * (size_t) p.OCp;
+            __nv_bfloat16* o_hi = p.out_hi + base;
+            __nv_bfloat16* o_lo = p.out_lo + base;
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * RG_MAX_N);
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * RW_MAX_N);
             for (int c = 0; c < p.n_blk; c += 16) {
                 uint32_t r[16];
                 tmem_ld16(taddr + (uint32_t) c, r);
@@ -659,15 +647,18 @@ static int plan_n_blk(int OC, int m_tiles, int rows_used, int sm_count, int& til
     return best_blk;
 }
 
-static bool rowgemm_supported(const ConvArgs& a) {
-    // small-C stems: IC <= 8 (one 16-byte vector per pixel), one 64-wide K block per filter row, weights resident in smem
-    return a.in->cp == 8 && a.k >= 1 && a.k <= RG_MAX_KH && a.k * 8 <= UM_BLOCK_K && a.out->c <= RG_MAX_N && a.residual == nullptr && a.stride >= 1;
+static bool rowwin_supported(const ConvArgs& a) {
+    // small-C stems: IC <= 8 (one 16-byte vector per pixel), stride 1 or 2, <= 4 K steps per filter row, weights packed
+    // for exactly this (stride, pad_x), whole panel resident in smem
+    RowPlan rp;
+    return a.in->cp == 8 && a.w && a.w->w_row_hi && a.w->w_row_lo && a.w->row_stride == a.stride && a.w->row_pad == a.pad_x && a.k <= RW_MAX_KH &&
+           a.out->c <= RW_MAX_N && a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW;
 }
 
 bool conv2d_umma_supported(const ConvArgs& a) {
     if (!a.w || !a.w->w_hi || !a.w->w_lo) return false;
     if (!(a.pad_mode == SNNB_PAD_NONE || a.pad_mode == SNNB_PAD_CONSTANT)) return false; // replicate / reflect: SIMT gather
-    if (rowgemm_supported(a)) return true;
+    if (rowwin_supported(a)) return true;
     if (!(a.stride == 1 || a.stride == 2)) return false; // stride 2 = TMA traversal stride (elementStrides) on W and H
     if (a.in->c < 16) return false; // wider small-C cases the row-GEMM variant cannot take: K would be >75% zero padding
     if (a.k < 1 || a.k > 11) return false;
@@ -677,37 +668,59 @@ bool conv2d_umma_supported(const ConvArgs& a) {
 
 static bool g_attr_set = false, g_attr_set_rg = false;
 
-static int launch_conv2d_rowgemm(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
+static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;
-    RowGemmParams p;
-    p.in_hi = in->hi, p.in_lo = in->lo, p.out_hi = out->hi, p.out_lo = out->lo, p.bias = a.w->bias;
-    p.N = out->n, p.H = in->h, p.W = in->w, p.OH = out->h, p.OW = out->w, p.OC = out->c, p.OCp = out->cp;
-    p.n_blk = round_up(out->c, 16);
-    p.kh = a.k, p.kw = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y, p.act = a.act, p.alpha = a.alpha;
-    p.M = (long long) out->n * out->h * out->w;
-    SNNB_REQUIRE(a.w->kp == a.k * a.k * 8, "launch_conv2d_rowgemm: packed weights do not match (kp %d)", a.w->kp);
-    CUtensorMap tmB[2];
-    const cuuint64_t dims[2]    = {(cuuint64_t) a.w->kp, (cuuint64_t) a.w->ocr};
-    const cuuint64_t strides[1] = {(cuuint64_t) a.w->kp * 2};
-    const cuuint32_t box[2]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) p.n_blk};
-    const cuuint32_t estr[2]    = {1, 1};
-    __nv_bfloat16* planes[2]    = {a.w->w_hi, a.w->w_lo};
-    for (int i = 0; i < 2; ++i) {
-        CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, rowgemm) failed: %d", (int) r);
+    RowPlan rp;
+    SNNB_REQUIRE(make_row_plan(a.k, a.stride, a.pad_x, rp), "launch_conv2d_rowwin: no row plan");
+    RowWinParams p;
+    p.out_hi = out->hi, p.out_lo = out->lo, p.bias = a.w->bias;
+    p.N = out->n, p.OH = out->h, p.OW = out->w, p.OC = out->c, p.OCp = out->cp;
+    p.n_blk = round_up(out->c, 16), p.ocr = a.w->ocr;
+    p.kh = a.k, p.stride = a.stride, p.pad_y = a.pad_y;
+    p.tiles_x  = (out->w + UM_BLOCK_M - 1) / UM_BLOCK_M;
+    p.parities = rp.parities, p.dmin[0] = rp.dmin[0], p.dmin[1] = rp.dmin[1];
+    p.ksteps   = rp.ksteps;
+    for (int q = 0; q < 4; ++q) p.ks_parity[q] = q < rp.ksteps ? rp.ks_parity[q] : 0, p.ks_erel[q] = q < rp.ksteps ? rp.ks_erel[q] : 0;
+    p.act = a.act, p.alpha = a.alpha;
+
+    // A: per plane and column parity a 4-D view (8 ch | de-interleaved pixel index | row | image) of the NHWC plane
+    CUtensorMap tmA[4], tmB[2];
+    for (int plane = 0; plane < 2; ++plane)
+        for (int par = 0; par < 2; ++par) {
+            const int pp = par < rp.parities ? par : 0; // unused maps alias parity 0 (kernel never issues them)
+            __nv_bfloat16* base = (plane ? in->lo : in->hi) + (size_t) pp * 8;
+            const int wp        = (in->w - pp + a.stride - 1) / a.stride; // pixels of this parity per row
+            const cuuint64_t dims[4]    = {8, (cuuint64_t) (wp > 0 ? wp : 1), (cuuint64_t) in->h, (cuuint64_t) in->n};
+            const cuuint64_t strides[3] = {(cuuint64_t) a.stride * 16, (cuuint64_t) in->w * 16, (cuuint64_t) in->h * in->w * 16};
+            const cuuint32_t box[4]     = {8, (cuuint32_t) RW_BOXW, 1, 1};
+            const cuuint32_t estr[4]    = {1, 1, 1, 1};
+            CUresult r = encode(&tmA[plane * 2 + par], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, rowwin) failed: %d", (int) r);
+        }
+    {
+        const cuuint64_t dims[2]    = {64, (cuuint64_t) a.k * a.w->ocr};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2]     = {64, (cuuint32_t) p.n_blk};
+        const cuuint32_t estr[2]    = {1, 1};
+        __nv_bfloat16* planes[2]    = {a.w->w_row_hi, a.w->w_row_lo};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, rowwin) failed: %d", (int) r);
+        }
     }
     if (!g_attr_set_rg) {
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
         g_attr_set_rg = true;
     }
-    const int total_tiles = (int) ((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M);
+    const int total_tiles = p.N * p.OH * p.tiles_x;
     const int grid        = std::min(total_tiles, ctx->sm_count);
-    conv_rowgemm_kernel<<<grid, RG_THREADS, RG_SMEM_BYTES, ctx->stream>>>(tmB[0], tmB[1], p);
+    conv_rowwin_kernel<<<grid, RW_THREADS, RW_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("conv_rowgemm_kernel launch failed: %s", cudaGetErrorString(e));
+        set_error("conv_rowwin_kernel launch failed: %s", cudaGetErrorString(e));
         return 1;
     }
     ctx->launches++;
@@ -717,7 +730,7 @@ static int launch_conv2d_rowgemm(snnb_context* ctx, const ConvArgs& a, EncodeTil
 int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     EncodeTiledFn encode = get_encode(ctx);
     SNNB_REQUIRE(encode, "launch_conv2d_umma: cuTensorMapEncodeTiled is unavailable in this driver");
-    if (rowgemm_supported(a)) return launch_conv2d_rowgemm(ctx, a, encode);
+    if (rowwin_supported(a)) return launch_conv2d_rowwin(ctx, a, encode);
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;
     UmmaParams p;

@@ -18,6 +18,8 @@ size_t PackedHost::device_bytes() const {
     b += align256(w_f32.size() * sizeof(float));
     b += align256(w_hi.size() * sizeof(__nv_bfloat16));
     b += align256(w_lo.size() * sizeof(__nv_bfloat16));
+    b += align256(w_row_hi.size() * sizeof(__nv_bfloat16));
+    b += align256(w_row_lo.size() * sizeof(__nv_bfloat16));
     b += align256(bias.size() * sizeof(float));
     b += align256(gamma.size() * sizeof(float));
     b += align256(beta.size() * sizeof(float));
@@ -77,6 +79,29 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
     }
 }
 
+void pack_rowwin_host(PackedHost& p, int stride, int pad_x) {
+    RowPlan rp;
+    if (p.kind != 1 || p.in_ch > 8 || p.out_ch > 64 || !make_row_plan(p.kernel, stride, pad_x, rp)) return;
+    const int k = p.kernel, IC = p.in_ch, OC = p.out_ch;
+    p.row_stride = stride, p.row_pad = pad_x;
+    p.w_row_hi.assign((size_t) k * p.ocr * 64, __float2bfloat16_rn(0.0f));
+    p.w_row_lo.assign((size_t) k * p.ocr * 64, __float2bfloat16_rn(0.0f));
+    for (int ky = 0; ky < k; ++ky)
+        for (int o = 0; o < OC; ++o)
+            for (int q = 0; q < rp.ksteps; ++q)
+                for (int h = 0; h < 2; ++h) {
+                    const int j = rp.ks_tap[q][h];
+                    if (j < 0) continue;
+                    for (int c = 0; c < IC; ++c) {
+                        const float wv        = p.w_f32[(size_t) ((ky * k + j) * IC + c) * p.ocw + o]; // BN already folded in
+                        const size_t idx      = ((size_t) ky * p.ocr + o) * 64 + q * 16 + h * 8 + c;
+                        const __nv_bfloat16 hh = __float2bfloat16_rn(wv);
+                        p.w_row_hi[idx]       = hh;
+                        p.w_row_lo[idx]       = __float2bfloat16_rn(wv - __bfloat162float(hh));
+                    }
+                }
+}
+
 void pack_depthwise_host(int C, int k, const float* w_chw, const float* bias, const float* g, const float* b, const float* m, const float* v,
                          PackedHost& out) {
     out.kind = 2, out.in_ch = C, out.out_ch = C, out.kernel = k;
@@ -121,9 +146,12 @@ int place_weights(snnb_context* ctx, const PackedHost& p, char* base, snnb_weigh
     char* cur = base;
     w->ctx = ctx, w->kind = p.kind, w->in_ch = p.in_ch, w->out_ch = p.out_ch, w->kernel = p.kernel;
     w->ocw = p.ocw, w->kp = p.kp, w->ocr = p.ocr;
+    w->row_stride = p.row_stride, w->row_pad = p.row_pad;
     if (put(ctx, p.w_f32, cur, &w->w_f32)) return 1;
     if (put(ctx, p.w_hi, cur, &w->w_hi)) return 1;
     if (put(ctx, p.w_lo, cur, &w->w_lo)) return 1;
+    if (put(ctx, p.w_row_hi, cur, &w->w_row_hi)) return 1;
+    if (put(ctx, p.w_row_lo, cur, &w->w_row_lo)) return 1;
     if (put(ctx, p.bias, cur, &w->bias)) return 1;
     if (put(ctx, p.gamma, cur, &w->gamma)) return 1;
     if (put(ctx, p.beta, cur, &w->beta)) return 1;

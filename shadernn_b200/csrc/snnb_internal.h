@@ -66,6 +66,10 @@ struct snnb_weights {
     __nv_bfloat16* w_hi = nullptr;
     __nv_bfloat16* w_lo = nullptr;
     int kp = 0, ocr = 0;
+    // small-input-channel "row window" variant (IC <= 8): bf16 hi/lo [kh][OCr][64], columns in RowPlan K order
+    __nv_bfloat16* w_row_hi = nullptr;
+    __nv_bfloat16* w_row_lo = nullptr;
+    int row_stride = 0, row_pad = 0;
     // depthwise: fp32 [k*k][Cp]
     // folded bias: fp32 [round_up(OC, 64)]
     float* bias = nullptr;
@@ -126,9 +130,47 @@ int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t); 
 int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc);       // hi/lo -> fp32 NHWC (pitch C)
 
 // ---- host-side weight folding/packing (pack.cpp) -----------------------------------------------------------
+// K ordering of the row-window convolution kernel (kernels_umma.cu): for stride s the taps of one filter row fall
+// into s column parities; within a parity consecutive taps read consecutive pixels of the de-interleaved row, so one
+// tcgen05.mma K step (16 bf16 = 2 pixels x 8 channels) covers two taps of the same parity.
+struct RowPlan {
+    int parities = 0;
+    int dmin[2]  = {0, 0}; // pixel offset (in de-interleaved index) of the first tap of each parity, relative to the output index
+    int ntaps[2] = {0, 0};
+    int ksteps   = 0;
+    int ks_parity[4], ks_erel[4], ks_tap[4][2];
+    int span = 0; // pixels needed beyond the 128 of the tile
+};
+static inline bool make_row_plan(int k, int stride, int pad_x, RowPlan& rp) {
+    if (k < 1 || k > 8 || !(stride == 1 || stride == 2)) return false;
+    rp = RowPlan();
+    rp.parities = stride;
+    for (int par = 0; par < stride; ++par) {
+        int js[8], t = 0;
+        for (int j = 0; j < k; ++j)
+            if ((((j - pad_x) % stride) + stride) % stride == par) js[t++] = j;
+        rp.ntaps[par] = t;
+        if (!t) continue;
+        const int a  = js[0] - pad_x;
+        rp.dmin[par] = a >= 0 ? a / stride : -((-a + stride - 1) / stride);
+        for (int q = 0; q < (t + 1) / 2; ++q) {
+            if (rp.ksteps >= 4) return false;
+            rp.ks_parity[rp.ksteps] = par;
+            rp.ks_erel[rp.ksteps]   = 2 * q;
+            rp.ks_tap[rp.ksteps][0] = js[2 * q];
+            rp.ks_tap[rp.ksteps][1] = (2 * q + 1 < t) ? js[2 * q + 1] : -1;
+            rp.ksteps++;
+        }
+        rp.span = rp.span > 2 * ((t + 1) / 2) ? rp.span : 2 * ((t + 1) / 2);
+    }
+    return rp.ksteps > 0;
+}
+
 struct PackedHost {
     std::vector<float> w_f32;           // [K][OCw]
     std::vector<__nv_bfloat16> w_hi, w_lo; // [OCr][Kp]
+    std::vector<__nv_bfloat16> w_row_hi, w_row_lo; // [kh][OCr][64] (row-window kernel), empty unless IC <= 8
+    int row_stride = 0, row_pad = 0;
     std::vector<float> bias;            // [round_up(OC,64)]
     std::vector<float> gamma, beta, mean, var;
     int kind = 0, in_ch = 0, out_ch = 0, kernel = 1, ocw = 0, kp = 0, ocr = 0;
@@ -136,6 +178,8 @@ struct PackedHost {
 };
 void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* bias, const float* g, const float* b, const float* m, const float* v,
                       PackedHost& out);
+// Adds the row-window operand (w_row_hi/lo) for small-IC convolutions; needs the layer's stride and x padding.
+void pack_rowwin_host(PackedHost& p, int stride, int pad_x);
 void pack_depthwise_host(int C, int k, const float* w_chw, const float* bias, const float* g, const float* b, const float* m, const float* v,
                          PackedHost& out);
 void pack_channels_host(int C, const float* g, const float* b, const float* m, const float* v, PackedHost& out);

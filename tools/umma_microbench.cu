@@ -63,8 +63,17 @@ int main() {
     long long* d;
     cudaMalloc(&d, 8);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+    // fixed latency of a short burst: issue `iters` MMAs, commit, wait (what one K block of the conv kernels does)
+    for (int N : {64, 128})
+        for (int it : {1, 4, 12, 24, 48}) {
+            bench<<<148, 64, 60 * 1024>>>(N, it, 0, d);
+            cudaDeviceSynchronize();
+            long long c;
+            cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+            printf("burst N %3d  %2d MMAs + commit + wait: %lld clk\n", N, it, c);
+        }
     const int iters = 4096;
-    for (int grid : {1, 148})
+    for (int grid : {148})
         for (int two : {0, 1})
             for (int N : {16, 32, 64, 96, 128, 192, 256}) {
                 bench<<<grid, 64, 60 * 1024>>>(N, iters, two, d);
