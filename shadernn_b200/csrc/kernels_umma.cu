@@ -40,7 +40,8 @@ constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES; // A_hi, A_lo, B
 constexpr int UM_EPI_WARPS   = 8;                       // two warps per TMEM lane quarter, interleaved over 16-column chunks
 constexpr int UM_THREADS     = 64 + 32 * UM_EPI_WARPS; // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int UM_TMEM_COLS   = 256; // two accumulator buffers of up to 128 fp32 columns
-constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int UM_STG_BYTES   = 2 * UM_BLOCK_M * 128; // epilogue staging: one 64-channel slab, hi + lo planes (32 KB)
+constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct UmmaParams {
     __nv_bfloat16* out_hi;
@@ -135,6 +136,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused for swizzled K-major) | [32,46) SBO >> 4 (= 1024 B: 8 rows x 128 B)
 //   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
@@ -169,24 +179,144 @@ __device__ __forceinline__ void um_split2(float a, float b, uint32_t& h, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Epilogue of one output tile, shared by both tensor-core kernels: TMEM -> registers -> +bias (+residual) -> activation
+// -> split-bf16 -> SHARED MEMORY (128B-swizzled, bank-conflict-free) -> ONE TMA bulk store per plane and 64-channel slab.
+//
+// Why through smem + TMA: each thread owns one output pixel (TMEM lane), so direct global stores are 32 scattered
+// 16-byte pieces per warp instruction = 32 L1 wavefronts each; at 128 rows x n_blk channels that is 8-16 k wavefronts
+// per tile, MORE than the tile's MMA time - the first version of both kernels was bound by exactly that (their run time
+// did not move across five different producer designs). The TMA store writes full 128-byte lines, clips rows/channels
+// that fall outside the tensor by itself, and costs one instruction. The fused residual (Conv2D -> Add) comes in the same
+// way: a TMA box load of the residual tile into the staging buffer, read back with swizzled LDS.
+// ---------------------------------------------------------------------------------------------------------------
+struct EpiArgs {
+    const CUtensorMap *o_hi64, *o_lo64, *o_hiT, *o_loT; // output maps: 64-channel slab (SWIZZLE_128B) and tail slab (dense)
+    const CUtensorMap *r_hi64, *r_lo64, *r_hiT, *r_loT; // residual maps, same geometry
+    const float* bias;
+    int n_blk, OC, act, has_res, rows_box;
+    float alpha;
+    uint32_t stg;       // staging smem (hi plane; lo plane at + UM_BLOCK_M * 128)
+    uint32_t res_bar;   // mbarrier for the residual TMA load
+    uint32_t tmem_empty;
+};
+
+template <int NWARPS>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, int oc0, int c1, int c2, int c3, int row, int half, bool leader, int lane,
+                                              uint32_t& res_phase) {
+    const bool fast_act = e.act == SNNB_ACT_NONE || e.act == SNNB_ACT_RELU || e.act == SNNB_ACT_RELU6 || e.act == SNNB_ACT_LEAKY_RELU;
+    const float slope   = (e.act == SNNB_ACT_RELU || e.act == SNNB_ACT_RELU6) ? 0.0f : (e.act == SNNB_ACT_LEAKY_RELU ? e.alpha : 1.0f);
+    const float hi_clip = e.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+    const int nslabs    = (e.n_blk + 63) >> 6;
+    for (int sl = 0; sl < nslabs; ++sl) {
+        const int w        = min(64, e.n_blk - sl * 64); // slab width in channels (multiple of 16)
+        const bool sw      = w == 64;                    // full slab: 128-byte rows, SWIZZLE_128B
+        const uint32_t pitch = sw ? 128u : (uint32_t) w * 2u;
+        const uint32_t srow  = e.stg + (uint32_t) row * pitch;
+        const uint32_t xr    = sw ? (uint32_t) (row & 7) : 0u;
+        const int slab_oc    = oc0 + sl * 64;
+        if (e.has_res && leader) {
+            mbar_expect_tx(e.res_bar, 2u * (uint32_t) e.rows_box * pitch); // the box has rows_box rows (<= 128)
+            tma_load_4d(e.stg, sw ? e.r_hi64 : e.r_hiT, e.res_bar, slab_oc, c1, c2, c3);
+            tma_load_4d(e.stg + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, slab_oc, c1, c2, c3);
+        }
+        bool res_ready = false;
+        for (int ci = (NWARPS == 8 ? half : 0); ci < (w >> 4); ci += (NWARPS == 8 ? 2 : 1)) {
+            const int c = sl * 64 + ci * 16;
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t) c, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + oc0 + c) + j4);
+                v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+                v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+                v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+                v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+            }
+            if (e.has_res) {
+                if (!res_ready) {
+                    mbar_wait(e.res_bar, res_phase);
+                    res_ready = true;
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
+                    uint32_t hh[4], ll[4];
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]) : "r"(a));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(a + UM_BLOCK_M * 128));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[g * 8 + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+                        v[g * 8 + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+                    }
+                }
+            }
+            if (fast_act) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (oc0 + c + j < e.OC) ? umma_act(v[j], e.act, e.alpha) : 0.0f; // out-of-line call
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint32_t oh[4], ol[4];
+                um_split2(v[g * 8 + 0], v[g * 8 + 1], oh[0], ol[0]);
+                um_split2(v[g * 8 + 2], v[g * 8 + 3], oh[1], ol[1]);
+                um_split2(v[g * 8 + 4], v[g * 8 + 5], oh[2], ol[2]);
+                um_split2(v[g * 8 + 6], v[g * 8 + 7], oh[3], ol[3]);
+                const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[0]), "r"(oh[1]), "r"(oh[2]), "r"(oh[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[0]), "r"(ol[1]), "r"(ol[2]), "r"(ol[3]) : "memory");
+            }
+        }
+        if (e.has_res && !res_ready) mbar_wait(e.res_bar, res_phase); // warps without a chunk in this slab still consume the phase
+        if (e.has_res) res_phase ^= 1u;
+        if (sl == nslabs - 1) { // this warp has issued its last tcgen05.ld of the tile: the accumulator buffer may be reused
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e.tmem_empty);
+        }
+        fence_async_smem();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, NWARPS * 32);
+        if (leader) {
+            tma_store_4d(sw ? e.o_hi64 : e.o_hiT, e.stg, slab_oc, c1, c2, c3);
+            tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
+            bulk_commit();
+            bulk_wait_read0();              // staging may be overwritten once the bulk stores have read it
+        }
+        named_bar_sync(1, NWARPS * 32);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
-                 const __grid_constant__ CUtensorMap tmB_lo, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO_hi64, const __grid_constant__ CUtensorMap tmO_lo64,
+                 const __grid_constant__ CUtensorMap tmO_hiT, const __grid_constant__ CUtensorMap tmO_loT, const __grid_constant__ CUtensorMap tmR_hi64,
+                 const __grid_constant__ CUtensorMap tmR_lo64, const __grid_constant__ CUtensorMap tmR_hiT, const __grid_constant__ CUtensorMap tmR_loT,
+                 const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bar_base  = smem_base + UM_STAGES * UM_STAGE_BYTES;
-    // barrier slots (8 bytes each): full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), then the TMEM base slot
+    const uint32_t stg       = smem_base + UM_STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned)
+    const uint32_t bar_base  = stg + UM_STG_BYTES;
+    // barrier slots (8 bytes each): full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), TMEM base slot, residual barrier
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar      = [&](int s) { return bar_base + 8u * (UM_STAGES + s); };
     auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * UM_STAGES + a); };
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * UM_STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * UM_STAGES + 4);
+    const uint32_t res_bar   = bar_base + 8u * (2 * UM_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
+        mbar_init(res_bar, 1);
+        tma_prefetch_desc(&tmO_hi64);
+        tma_prefetch_desc(&tmO_lo64);
         tma_prefetch_desc(&tmA_hi);
         tma_prefetch_desc(&tmA_lo);
         tma_prefetch_desc(&tmB_hi);
@@ -272,91 +402,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> bias/residual/activation -> split-bf16 -> HBM =====================
-        // Lean by construction (the first version spent ~2000 SASS instructions per 16 values on per-element activation
-        // switches, scalar bias loads and channel predicates and throttled the whole pipeline): activations of the
-        // relu family are one branch-free max/min pair, bias is fetched as float4 from a zero-padded vector, and padded
-        // output channels need no mask because their weights, bias and residual are all zero.
-        const int q    = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;          // which interleaved set of 16-column chunks this warp owns
+        // ===================== epilogue (8 warps): see epilogue_tile =====================
+        const int q    = warp & 3;        // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2; // which interleaved set of 16-column chunks this warp owns
         const int row  = q * 32 + lane;
-        const bool fast_act = p.act == SNNB_ACT_NONE || p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6 || p.act == SNNB_ACT_LEAKY_RELU;
-        const float slope   = (p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6) ? 0.0f : (p.act == SNNB_ACT_LEAKY_RELU ? p.alpha : 1.0f);
-        const float hi_clip = p.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
-        const int tx_i = row % p.tw, ty_i = (row / p.tw) % p.th, tn_i = row / (p.tw * p.th);
+        EpiArgs e;
+        e.o_hi64 = &tmO_hi64, e.o_lo64 = &tmO_lo64, e.o_hiT = &tmO_hiT, e.o_loT = &tmO_loT;
+        e.r_hi64 = &tmR_hi64, e.r_lo64 = &tmR_lo64, e.r_hiT = &tmR_hiT, e.r_loT = &tmR_loT;
+        e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = p.has_res, e.rows_box = p.rows_used, e.alpha = p.alpha;
+        e.stg = stg, e.res_bar = res_bar;
+        uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
             const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
-            const int ox = bx * p.tw + tx_i, oy = by * p.th + ty_i, n = bn * p.tn + tn_i;
-            const bool valid = row < p.rows_used && ox < p.OW && oy < p.OH && n < p.N;
-            const int oc0    = oc_idx * p.n_blk;
-            const size_t base = (((size_t) n * p.OH + oy) * p.OW + ox) * (size_t) p.OCp + oc0;
-            __nv_bfloat16* o_hi       = p.out_hi + base;
-            __nv_bfloat16* o_lo       = p.out_lo + base;
-            const __nv_bfloat16* r_hi = p.res_hi + base;
-            const __nv_bfloat16* r_lo = p.res_lo + base;
-            const float* bias         = p.bias + oc0;
-
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
+            e.tmem_empty = tmem_empty_bar(acc);
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * UM_MAX_N);
-            for (int c = half * 16; c < p.n_blk; c += 32) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t) c, r);
-                tmem_ld_wait();
-                if (valid) {
-                    float v[16];
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c) + j4);
-                        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-                        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-                        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-                        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
-                    }
-                    const bool g0 = oc0 + c < p.OCp, g1 = oc0 + c + 8 < p.OCp; // 8-channel groups inside the tensor's pitch
-                    if (p.has_res) {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            if (g == 0 ? g0 : g1) {
-                                const uint4 h = __ldg(reinterpret_cast<const uint4*>(r_hi + c + g * 8));
-                                const uint4 l = __ldg(reinterpret_cast<const uint4*>(r_lo + c + g * 8));
-                                const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    v[g * 8 + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-                                    v[g * 8 + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
-                                }
-                            }
-                        }
-                    }
-                    if (fast_act) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = (oc0 + c + j < p.OC) ? umma_act(v[j], p.act, p.alpha) : 0.0f; // out-of-line call
-                    }
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        if (g == 0 ? g0 : g1) {
-                            uint4 oh, ol;
-                            um_split2(v[g * 8 + 0], v[g * 8 + 1], oh.x, ol.x);
-                            um_split2(v[g * 8 + 2], v[g * 8 + 3], oh.y, ol.y);
-                            um_split2(v[g * 8 + 4], v[g * 8 + 5], oh.z, ol.z);
-                            um_split2(v[g * 8 + 6], v[g * 8 + 7], oh.w, ol.w);
-                            *reinterpret_cast<uint4*>(o_hi + c + g * 8) = oh;
-                            *reinterpret_cast<uint4*>(o_lo + c + g * 8) = ol;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, warp == 2 && lane == 0, lane, res_phase);
         }
     }
 
@@ -384,7 +450,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // gathered 16-byte requests. The weight panel [kh][n_blk][64] (hi + lo, K columns in RowPlan order) is loaded once per
 // persistent CTA and stays resident. Tiles = up to 128 consecutive output pixels of one output row.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RW_STAGES        = 8;
+constexpr int RW_STAGES        = 6;
 constexpr int RW_EPI_WARPS     = 4;
 constexpr int RW_THREADS       = 64 + 32 * RW_EPI_WARPS;
 constexpr int RW_MAX_KH        = 8;
@@ -393,7 +459,7 @@ constexpr int RW_BOXW          = 144;                          // 128 tile pixel
 constexpr int RW_ARR_BYTES     = RW_BOXW * 16;                 // one (plane, parity) pixel row segment
 constexpr int RW_STAGE_BYTES   = 4 * RW_ARR_BYTES;             // hi/lo x parity 0/1 = 9216 B
 constexpr int RW_B_PLANE_BYTES = RW_MAX_KH * RW_MAX_N * 128;   // [ky][n_blk rows x 128 B]
-constexpr int RW_SMEM_BYTES    = 2 * RW_B_PLANE_BYTES + RW_STAGES * RW_STAGE_BYTES + 1024 + 256;
+constexpr int RW_SMEM_BYTES    = 2 * RW_B_PLANE_BYTES + RW_STAGES * RW_STAGE_BYTES + UM_STG_BYTES + 1024 + 256;
 
 struct RowWinParams {
     __nv_bfloat16* out_hi;
@@ -415,11 +481,12 @@ __device__ __forceinline__ uint64_t make_window_desc(uint32_t saddr) { return (u
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_constant__ CUtensorMap tmA_hi1, const __grid_constant__ CUtensorMap tmA_lo0,
                    const __grid_constant__ CUtensorMap tmA_lo1, const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   const RowWinParams p) {
+                   const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo, const RowWinParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB_hi = smem_base, sB_lo = smem_base + RW_B_PLANE_BYTES;
-    const uint32_t sA0      = smem_base + 2 * RW_B_PLANE_BYTES;
+    const uint32_t stg      = smem_base + 2 * RW_B_PLANE_BYTES; // epilogue staging (1024-aligned)
+    const uint32_t sA0      = stg + UM_STG_BYTES;
     const uint32_t bar_base = sA0 + RW_STAGES * RW_STAGE_BYTES;
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar      = [&](int s) { return bar_base + 8u * (RW_STAGES + s); };
@@ -517,63 +584,26 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             }
         }
     } else {
-        // ---- epilogue: 4 warps, one TMEM lane quarter each ----
+        // ---- epilogue: 4 warps, one TMEM lane quarter each (see epilogue_tile) ----
         const int q   = warp & 3;
         const int row = q * 32 + lane;
-        const bool fast_act = p.act == SNNB_ACT_NONE || p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6 || p.act == SNNB_ACT_LEAKY_RELU;
-        const float slope   = (p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6) ? 0.0f : (p.act == SNNB_ACT_LEAKY_RELU ? p.alpha : 1.0f);
-        const float hi_clip = p.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        EpiArgs e;
+        // a 64-channel slab uses the swizzled map, a narrower one the dense map: the host encodes the right one into both slots
+        e.o_hi64 = &tmO_hi, e.o_lo64 = &tmO_lo, e.o_hiT = &tmO_hi, e.o_loT = &tmO_lo;
+        e.r_hi64 = e.r_lo64 = e.r_hiT = e.r_loT = &tmO_hi;
+        e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = 0, e.rows_box = UM_BLOCK_M, e.alpha = p.alpha;
+        e.stg = stg, e.res_bar = 0;
+        uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             const int xt = tile % p.tiles_x, oy = (tile / p.tiles_x) % p.OH, n = tile / (p.tiles_x * p.OH);
-            const int ox      = xt * UM_BLOCK_M + row;
-            const bool valid  = ox < p.OW;
-            const size_t base = (((size_t) n * p.OH + oy) * p.OW + ox) * (size_t) p.OCp;
-            __nv_bfloat16* o_hi = p.out_hi + base;
-            __nv_bfloat16* o_lo = p.out_lo + base;
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
+            e.tmem_empty = tmem_empty_bar(acc);
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * RW_MAX_N);
-            for (int c = 0; c < p.n_blk; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t) c, r);
-                tmem_ld_wait();
-                if (valid) {
-                    float v[16];
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c) + j4);
-                        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-                        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-                        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-                        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
-                    }
-                    if (fast_act) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = (c + j < p.OC) ? umma_act(v[j], p.act, p.alpha) : 0.0f;
-                    }
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        if (c + g * 8 < p.OCp) {
-                            uint4 oh, ol;
-                            um_split2(v[g * 8 + 0], v[g * 8 + 1], oh.x, ol.x);
-                            um_split2(v[g * 8 + 2], v[g * 8 + 3], oh.y, ol.y);
-                            um_split2(v[g * 8 + 4], v[g * 8 + 5], oh.z, ol.z);
-                            um_split2(v[g * 8 + 6], v[g * 8 + 7], oh.w, ol.w);
-                            *reinterpret_cast<uint4*>(o_hi + c + g * 8) = oh;
-                            *reinterpret_cast<uint4*>(o_lo + c + g * 8) = ol;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, 0, warp == 2 && lane == 0, lane, res_phase);
         }
     }
 
@@ -599,6 +629,23 @@ static EncodeTiledFn get_encode(snnb_context* ctx) {
         ctx->tmap_encode_fn = fn;
     }
     return reinterpret_cast<EncodeTiledFn>(ctx->tmap_encode_fn);
+}
+
+// Tensor maps of an NHWC split-bf16 tensor for the epilogue's TMA stores / residual loads: box = (width channels, tw, th, tn).
+static int encode_nhwc_box_maps(EncodeTiledFn encode, const snnb_tensor* t, int width, int tw, int th, int tn, bool swizzle128, CUtensorMap (&maps)[2]) {
+    const cuuint64_t dims[4]    = {(cuuint64_t) t->cp, (cuuint64_t) t->w, (cuuint64_t) t->h, (cuuint64_t) t->n};
+    const cuuint64_t strides[3] = {(cuuint64_t) t->cp * 2, (cuuint64_t) t->w * t->cp * 2, (cuuint64_t) t->h * t->w * t->cp * 2};
+    const cuuint32_t box[4]     = {(cuuint32_t) width, (cuuint32_t) tw, (cuuint32_t) th, (cuuint32_t) tn};
+    const cuuint32_t estr[4]    = {1, 1, 1, 1};
+    __nv_bfloat16* planes[2]    = {t->hi, t->lo};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out/residual) failed: %d (cp %d w %d h %d n %d box %d %d %d %d)", (int) r, t->cp, t->w, t->h, t->n,
+                     width, tw, th, tn);
+    }
+    return 0;
 }
 
 struct TilePlan {
@@ -711,13 +758,15 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, rowwin) failed: %d", (int) r);
         }
     }
+    CUtensorMap tmO[2];
+    if (encode_nhwc_box_maps(encode, out, p.n_blk, UM_BLOCK_M, 1, 1, p.n_blk == 64, tmO)) return 2;
     if (!g_attr_set_rg) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
         g_attr_set_rg = true;
     }
     const int total_tiles = p.N * p.OH * p.tiles_x;
     const int grid        = std::min(total_tiles, ctx->sm_count);
-    conv_rowwin_kernel<<<grid, RW_THREADS, RW_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], p);
+    conv_rowwin_kernel<<<grid, RW_THREADS, RW_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], tmO[0], tmO[1], p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_rowwin_kernel launch failed: %s", cudaGetErrorString(e));
@@ -776,13 +825,24 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (kp %d ocr %d n_blk %d)", (int) r, a.w->kp, a.w->ocr, p.n_blk);
         }
     }
+    // epilogue maps: full 64-channel slabs (swizzled) and the tail slab (n_blk % 64 channels, dense)
+    CUtensorMap tmO64[2], tmOT[2], tmR64[2], tmRT[2];
+    {
+        const int wT = p.n_blk % 64;
+        const snnb_tensor* res = a.residual ? a.residual : out;
+        if (encode_nhwc_box_maps(encode, out, p.n_blk >= 64 ? 64 : wT, p.tw, p.th, p.tn, p.n_blk >= 64, tmO64)) return 2;
+        if (encode_nhwc_box_maps(encode, out, wT ? wT : 64, p.tw, p.th, p.tn, wT == 0, tmOT)) return 2;
+        if (encode_nhwc_box_maps(encode, res, p.n_blk >= 64 ? 64 : wT, p.tw, p.th, p.tn, p.n_blk >= 64, tmR64)) return 2;
+        if (encode_nhwc_box_maps(encode, res, wT ? wT : 64, p.tw, p.th, p.tn, wT == 0, tmRT)) return 2;
+    }
     if (!g_attr_set) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
         g_attr_set = true;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles, ctx->sm_count);
-    conv_umma_kernel<<<grid, UM_THREADS, UM_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], p);
+    conv_umma_kernel<<<grid, UM_THREADS, UM_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0],
+                                                                      tmRT[1], p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_umma_kernel launch failed: %s", cudaGetErrorString(e));
