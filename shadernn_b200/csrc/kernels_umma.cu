@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <vector>
 #include <cstdlib>
 
 #include "snnb_internal.h"
@@ -39,7 +40,8 @@ constexpr int UM_B_BYTES     = UM_MAX_N * 128;
 constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES; // A_hi, A_lo, B_hi, B_lo = 64 KB
 constexpr int UM_EPI_WARPS   = 8;                       // two warps per TMEM lane quarter, interleaved over 16-column chunks
 constexpr int UM_THREADS     = 64 + 32 * UM_EPI_WARPS; // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr int UM_TMEM_COLS   = 256; // two accumulator buffers of up to 128 fp32 columns
+constexpr int UM_ACC_COLS    = 2 * UM_MAX_N; // one accumulator buffer: [A_hi.B_hi + A_lo.B_hi | A_hi.B_lo], up to 2 x 128 fp32 columns
+constexpr int UM_TMEM_COLS   = 2 * UM_ACC_COLS; // double-buffered: all 512 columns
 constexpr int UM_STG_BYTES   = 2 * UM_BLOCK_M * 128; // epilogue staging: one 64-channel slab, hi + lo planes (32 KB)
 constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -57,6 +59,8 @@ struct UmmaParams {
     int act;
     float alpha;
     int has_res;
+    long long* trace; // profiling aid (env SNNB_UMMA_TRACE): CTA 0 writes clock64 stamps per role, [6][256]
+    int ablate; // profiling aid (env SNNB_UMMA_ABLATE, results are WRONG when set): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -80,6 +84,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) { // never suspends
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a broken descriptor or protocol bug must surface as a trapped kernel, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -90,6 +105,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             __trap();
         }
     }
+}
+// One lane of a CONVERGED warp. Unlike `lane == 0` the compiler knows a single thread is active in the guarded region, so
+// descriptors stay in uniform registers and each tcgen05.mma / TMA issue is one predicated instruction rather than an
+// ELECT + BRA.U.ANY waterfall loop (ncu r01: the issuing warp spent 77% of its time in that scalar code, not waiting).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -193,84 +216,115 @@ struct EpiArgs {
     const CUtensorMap *o_hi64, *o_lo64, *o_hiT, *o_loT; // output maps: 64-channel slab (SWIZZLE_128B) and tail slab (dense)
     const CUtensorMap *r_hi64, *r_lo64, *r_hiT, *r_loT; // residual maps, same geometry
     const float* bias;
-    int n_blk, OC, act, has_res, rows_box;
+    int n_blk, OC, act, has_res, rows_box; // the A_hi.B_lo partial sums sit n_blk columns after the main block
     float alpha;
     uint32_t stg;       // staging smem (hi plane; lo plane at + UM_BLOCK_M * 128)
     uint32_t res_bar;   // mbarrier for the residual TMA load
     uint32_t tmem_empty;
+    long long* trace; // profiling aid: leader warp stamps the phases of its first slabs into [4][64 + 8 * slab_seq ...]
+    int trace_seq;
 };
+
+// Fused residual (Conv2D -> Add): TMA box load of the residual tile's slab into the staging buffer. The previous bulk store
+// must have finished READING the buffer. Called for slab 0 BEFORE the wait for the accumulator, so the load's latency
+// hides behind the tile's MMAs. `leader` is warp-uniform: the whole leader warp calls, one lane issues.
+__device__ __forceinline__ void epilogue_residual_load(const EpiArgs& e, int sl, int oc0, int c1, int c2, int c3, bool leader) {
+    if (!leader) return;
+    const int w          = min(64, e.n_blk - sl * 64);
+    const bool sw        = w == 64;
+    const uint32_t pitch = sw ? 128u : (uint32_t) w * 2u;
+    if (elect_one()) {
+        bulk_wait_read0();
+        mbar_expect_tx(e.res_bar, 2u * (uint32_t) e.rows_box * pitch); // the box has rows_box rows (<= 128)
+        tma_load_4d(e.stg, sw ? e.r_hi64 : e.r_hiT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
+        tma_load_4d(e.stg + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
+    }
+    __syncwarp();
+}
 
 template <int NWARPS>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, int oc0, int c1, int c2, int c3, int row, int half, bool leader, int lane,
                                               uint32_t& res_phase) {
+    constexpr int MAXC  = NWARPS == 8 ? 2 : 4; // 16-column chunks of one 64-column slab owned by this warp
     const bool fast_act = e.act == SNNB_ACT_NONE || e.act == SNNB_ACT_RELU || e.act == SNNB_ACT_RELU6 || e.act == SNNB_ACT_LEAKY_RELU;
     const float slope   = (e.act == SNNB_ACT_RELU || e.act == SNNB_ACT_RELU6) ? 0.0f : (e.act == SNNB_ACT_LEAKY_RELU ? e.alpha : 1.0f);
     const float hi_clip = e.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
     const int nslabs    = (e.n_blk + 63) >> 6;
+#define EPI_STAMP(k)                                                                                      \
+    do {                                                                                                  \
+        if (e.trace && leader && lane == 0 && blockIdx.x == 0 && tseq < 16) e.trace[4 * 256 + 64 + 8 * tseq + (k)] = clock64(); \
+    } while (0)
     for (int sl = 0; sl < nslabs; ++sl) {
+        const int tseq     = e.trace_seq * nslabs + sl;
+        EPI_STAMP(0);
         const int w        = min(64, e.n_blk - sl * 64); // slab width in channels (multiple of 16)
         const bool sw      = w == 64;                    // full slab: 128-byte rows, SWIZZLE_128B
         const uint32_t pitch = sw ? 128u : (uint32_t) w * 2u;
         const uint32_t srow  = e.stg + (uint32_t) row * pitch;
         const uint32_t xr    = sw ? (uint32_t) (row & 7) : 0u;
         const int slab_oc    = oc0 + sl * 64;
-        if (e.has_res && leader) {
-            mbar_expect_tx(e.res_bar, 2u * (uint32_t) e.rows_box * pitch); // the box has rows_box rows (<= 128)
-            tma_load_4d(e.stg, sw ? e.r_hi64 : e.r_hiT, e.res_bar, slab_oc, c1, c2, c3);
-            tma_load_4d(e.stg + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, slab_oc, c1, c2, c3);
-        }
+        if (e.has_res && sl > 0) epilogue_residual_load(e, sl, oc0, c1, c2, c3, leader); // slab 0's was issued before the accumulator wait
+        // ---- phase 1: TMEM -> registers -> bias (+ residual) -> activation -> packed split-bf16, nothing written yet ----
+        uint32_t oh[MAXC][8], ol[MAXC][8];
         bool res_ready = false;
-        for (int ci = (NWARPS == 8 ? half : 0); ci < (w >> 4); ci += (NWARPS == 8 ? 2 : 1)) {
-            const int c = sl * 64 + ci * 16;
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t) c, r);
+#pragma unroll
+        for (int k0 = 0; k0 < MAXC; k0 += 2) { // two chunks at a time: their four TMEM loads and bias loads are in flight together
+            uint32_t r[2][16], r2[2][16];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int ci = NWARPS == 8 ? half + 2 * (k0 + kk) : k0 + kk;
+                if (ci < (w >> 4)) {
+                    const int c = sl * 64 + ci * 16;
+                    tmem_ld16(taddr + (uint32_t) c, r[kk]);
+                    tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2[kk]);
+                }
+            }
             tmem_ld_wait();
-            float v[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + oc0 + c) + j4);
-                v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-                v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-                v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-                v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
-            }
-            if (e.has_res) {
-                if (!res_ready) {
-                    mbar_wait(e.res_bar, res_phase);
-                    res_ready = true;
-                }
+            for (int kk = 0; kk < 2; ++kk) {
+                const int k = k0 + kk, ci = NWARPS == 8 ? half + 2 * k : k;
+                if (ci < (w >> 4)) {
+                    const int c = sl * 64 + ci * 16;
+                    float v[16];
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
-                    uint32_t hh[4], ll[4];
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]) : "r"(a));
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(a + UM_BLOCK_M * 128));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[g * 8 + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-                        v[g * 8 + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+                    for (int j4 = 0; j4 < 4; ++j4) { // the bias slice of a tile stays L1-resident across the CTA's tiles
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + oc0 + c) + j4);
+                        v[4 * j4 + 0] = (__uint_as_float(r[kk][4 * j4 + 0]) + __uint_as_float(r2[kk][4 * j4 + 0])) + b.x;
+                        v[4 * j4 + 1] = (__uint_as_float(r[kk][4 * j4 + 1]) + __uint_as_float(r2[kk][4 * j4 + 1])) + b.y;
+                        v[4 * j4 + 2] = (__uint_as_float(r[kk][4 * j4 + 2]) + __uint_as_float(r2[kk][4 * j4 + 2])) + b.z;
+                        v[4 * j4 + 3] = (__uint_as_float(r[kk][4 * j4 + 3]) + __uint_as_float(r2[kk][4 * j4 + 3])) + b.w;
                     }
+                    if (e.has_res) {
+                        if (!res_ready) {
+                            mbar_wait(e.res_bar, res_phase);
+                            res_ready = true;
+                        }
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) { // this thread later overwrites exactly the 16-byte pieces it reads here
+                            const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
+                            uint32_t hh[4], ll[4];
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]) : "r"(a));
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(a + UM_BLOCK_M * 128));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[g * 8 + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+                                v[g * 8 + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (fast_act) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = (oc0 + c + j < e.OC) ? umma_act(v[j], e.act, e.alpha) : 0.0f; // out-of-line call
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) um_split2(v[2 * j], v[2 * j + 1], oh[k][j], ol[k][j]);
                 }
-            }
-            if (fast_act) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = (oc0 + c + j < e.OC) ? umma_act(v[j], e.act, e.alpha) : 0.0f; // out-of-line call
-            }
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                uint32_t oh[4], ol[4];
-                um_split2(v[g * 8 + 0], v[g * 8 + 1], oh[0], ol[0]);
-                um_split2(v[g * 8 + 2], v[g * 8 + 3], oh[1], ol[1]);
-                um_split2(v[g * 8 + 4], v[g * 8 + 5], oh[2], ol[2]);
-                um_split2(v[g * 8 + 6], v[g * 8 + 7], oh[3], ol[3]);
-                const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[0]), "r"(oh[1]), "r"(oh[2]), "r"(oh[3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[0]), "r"(ol[1]), "r"(ol[2]), "r"(ol[3]) : "memory");
             }
         }
+        EPI_STAMP(1); // phase 1 done
         if (e.has_res && !res_ready) mbar_wait(e.res_bar, res_phase); // warps without a chunk in this slab still consume the phase
         if (e.has_res) res_phase ^= 1u;
         if (sl == nslabs - 1) { // this warp has issued its last tcgen05.ld of the tile: the accumulator buffer may be reused
@@ -278,21 +332,63 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
             __syncwarp();
             if (lane == 0) mbar_arrive(e.tmem_empty);
         }
-        fence_async_smem();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, NWARPS * 32);
-        if (leader) {
-            tma_store_4d(sw ? e.o_hi64 : e.o_hiT, e.stg, slab_oc, c1, c2, c3);
-            tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
-            bulk_commit();
-            bulk_wait_read0();              // staging may be overwritten once the bulk stores have read it
+        // ---- phase 2: staging buffer. The previous slab's / tile's bulk store has had all of phase 1 (and usually the whole
+        // wait for the next accumulator) to finish READING the buffer; only now does anyone wait for it. ----
+        if (!e.has_res) {
+            if (leader) {
+                if (elect_one()) bulk_wait_read0();
+                __syncwarp();
+            }
+            EPI_STAMP(2); // leader's wait for the previous store's reads
+            named_bar_sync(1, NWARPS * 32);
         }
+        EPI_STAMP(3); // bar A
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const int ci = NWARPS == 8 ? half + 2 * k : k;
+            if (ci < (w >> 4)) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[k][4 * g]), "r"(oh[k][4 * g + 1]), "r"(oh[k][4 * g + 2]), "r"(oh[k][4 * g + 3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[k][4 * g]), "r"(ol[k][4 * g + 1]), "r"(ol[k][4 * g + 2]), "r"(ol[k][4 * g + 3])
+                                 : "memory");
+                }
+            }
+        }
+        EPI_STAMP(4); // STS issued
+        fence_async_smem();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
+        EPI_STAMP(5); // fence
         named_bar_sync(1, NWARPS * 32);
+        EPI_STAMP(6); // bar B
+        if (leader) {
+            if (elect_one()) {
+                tma_store_4d(sw ? e.o_hi64 : e.o_hiT, e.stg, slab_oc, c1, c2, c3);
+                tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
+                bulk_commit();
+            }
+            __syncwarp();
+        }
+        EPI_STAMP(7); // store issued
+    }
+#undef EPI_STAMP
+}
+// After the last tile: the leader's bulk stores must have completed before the CTA (and its shared memory) goes away.
+__device__ __forceinline__ void epilogue_drain(bool leader) {
+    if (leader) {
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
+#define UM_TRACE(role, idx)                                                                          \
+    do {                                                                                             \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && (idx) < 256) p.trace[(role) * 256 + (idx)] = clock64(); \
+    } while (0)
+
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO_hi64, const __grid_constant__ CUtensorMap tmO_lo64,
@@ -312,6 +408,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t res_bar   = bar_base + 8u * (2 * UM_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) UM_TRACE(5, 0); // kernel entry
+    if (p.trace && threadIdx.x == 0) { // wall-clock (ns) envelope over ALL CTAs: [5][8] = earliest entry, [5][9] = latest exit, [5][10..11] CTA 0's own
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMin(reinterpret_cast<unsigned long long*>(p.trace) + 5 * 256 + 8, g);
+        if (blockIdx.x == 0) p.trace[5 * 256 + 10] = (long long) g;
+    }
 
     if (warp == 0 && lane == 0) {
         mbar_init(res_bar, 1);
@@ -337,6 +440,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp == 0) UM_TRACE(5, 1); // setup done
 
     const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
     const int total_tiles = m_tiles * p.tiles_oc;
@@ -344,26 +448,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = 2u * (uint32_t) p.rows_used * 128u + 2u * (uint32_t) p.n_blk * 128u;
+            const int ks = p.ksize, cbs = p.cblocks, icp = p.ICp;
+            const bool skip_tma = (p.ablate & 2) != 0;
+            const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u; // B_lo rows follow B_hi's: one [2 n_blk x 64] operand
+            int tr = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
                 const int ix0 = bx * p.tw * p.stride - p.pad_x, iy0 = by * p.th * p.stride - p.pad_y, n0 = bn * p.tn;
                 const int oc0 = oc_idx * p.n_blk;
-                for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
-                    const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-                    for (int cb = 0; cb < p.cblocks; ++cb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sA = smem_base + stage * UM_STAGE_BYTES;
-                        mbar_expect_tx(full_bar(stage), tx_bytes);
-                        tma_load_4d(sA, &tmA_hi, full_bar(stage), cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
-                        tma_load_4d(sA + UM_A_BYTES, &tmA_lo, full_bar(stage), cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
-                        tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, full_bar(stage), tap * p.ICp + cb * UM_BLOCK_K, oc0);
-                        tma_load_2d(sA + 2 * UM_A_BYTES + UM_B_BYTES, &tmB_lo, full_bar(stage), tap * p.ICp + cb * UM_BLOCK_K, oc0);
-                        if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+                // Keep this loop lean: it runs once per K block and every stall here delays the whole pipeline (no divisions,
+                // no parameter loads: ncu r01 showed ~60 dependent scalar instructions/iteration bounding the kernel).
+                int wk = 0; // K coordinate into the packed weights = tap * ICp + cb * 64
+                for (int ky = 0; ky < ks; ++ky) {
+                    for (int kx = 0; kx < ks; ++kx, wk += icp) {
+                        for (int cb = 0; cb < cbs; ++cb) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            UM_TRACE(0, tr);
+                            ++tr;
+                            if (elect_one()) {
+                                const uint32_t sA = smem_base + stage * UM_STAGE_BYTES, fb = full_bar(stage);
+                                if (skip_tma) {
+                                    mbar_arrive(fb);
+                                } else {
+                                    mbar_expect_tx(fb, tx_bytes);
+                                    tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                                    tma_load_4d(sA + UM_A_BYTES, &tmA_lo, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                                    tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, fb, wk + cb * UM_BLOCK_K, oc0);
+                                    tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
+                                }
+                            }
+                            if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+                        }
                     }
                 }
             }
@@ -372,35 +492,57 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // ===================== MMA issuer =====================
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t idesc = make_idesc(UM_BLOCK_M, p.n_blk);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
-            mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_MAX_N);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(full_bar(stage), phase); // TMA bytes have landed
+        // 3-term split product with TWO MMAs per K step: A_hi x [B_hi ; B_lo] (N = 2 n_blk, two column blocks) and
+        // A_lo x B_hi (N = n_blk, onto the first block); the epilogue adds the blocks. Same math as three N = n_blk MMAs, but
+        // A_hi is fetched from shared memory once instead of twice and there are 8 instead of 12 issues per K block.
+        const uint32_t idesc_cat = make_idesc(UM_BLOCK_M, 2 * p.n_blk), idesc = make_idesc(UM_BLOCK_M, p.n_blk);
+        // Descriptor of stage 0's A_hi tile; every other operand is this plus a constant in the 16-byte address field (all of
+        // shared memory is < 256 KB, so the 14-bit field never carries). Keeps the per-K-block preamble to a couple of adds:
+        // the issue of tcgen05.mma does not run ahead of the tensor pipe, so every scalar clock here is a lost MMA clock.
+        const uint64_t desc0 = make_smem_desc(smem_base);
+        // ONE thread runs the whole issue loop. Issuing tcgen05.mma stalls the thread while the tensor pipe's short queue is
+        // full, so scalar work placed BETWEEN the MMAs of a K block overlaps with them, while work between K blocks is lost
+        // tensor time: the look-ahead test of the next stage's barrier and the bookkeeping sit before the last two MMAs.
+        if (elect_one()) {
+            int it = 0, tr = 0;
+            bool ready = false; // full_bar(stage) already observed complete by the look-ahead
+            const bool no_mma = (p.ablate & 4) != 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sA = smem_base + stage * UM_STAGE_BYTES;
-                    const uint64_t a_hi = make_smem_desc(sA), a_lo = make_smem_desc(sA + UM_A_BYTES);
-                    const uint64_t b_hi = make_smem_desc(sA + 2 * UM_A_BYTES), b_lo = make_smem_desc(sA + 2 * UM_A_BYTES + UM_B_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_ACC_COLS);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!ready) mbar_wait(full_bar(stage), phase); // TMA bytes have landed
+                    tc_fence_after();
+                    UM_TRACE(1, tr);
+                    const uint64_t a_hi = desc0 + (uint64_t) (uint32_t) (stage * (UM_STAGE_BYTES >> 4)), a_lo = a_hi + (UM_A_BYTES >> 4);
+                    const uint64_t b_cat = a_hi + (2 * UM_A_BYTES >> 4); // rows [0, n_blk) = B_hi, [n_blk, 2 n_blk) = B_lo
+                    // UMMA_K = 16 bf16 = 32 bytes: K step j advances the start address by 2 (x16 B)
+                    if (!no_mma) {
 #pragma unroll
-                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) // UMMA_K = 16 bf16 = 32 bytes: advance the start address by 2 (x16 B)
-                        umma_bf16(d_tmem, a_hi + 2u * j, b_hi + 2u * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_lo + 2u * j, b_hi + 2u * j, idesc, 1u);
-#pragma unroll
-                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_lo + 2u * j, idesc, 1u);
-                    umma_commit(empty_bar(stage));                     // smem slot free once these MMAs retire
+                        for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_bf16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
+                        umma_bf16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
+                    }
+                    const int cur         = stage;
+                    const uint32_t nphase = phase ^ (stage == UM_STAGES - 1 ? 1u : 0u);
+                    stage                 = stage == UM_STAGES - 1 ? 0 : stage + 1;
+                    phase                 = nphase;
+                    ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking
+                    if (!no_mma) {
+                        umma_bf16(d_tmem, a_lo + 4u, b_cat + 4u, idesc, 1u);
+                        umma_bf16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(cur));                           // smem slot free once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
+                    UM_TRACE(2, tr);
+                    ++tr;
                 }
-                __syncwarp();
-                if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
             }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue (8 warps): see epilogue_tile =====================
         const int q    = warp & 3;        // TMEM lane quarter this warp may access
@@ -418,16 +560,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
             const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
+            if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, warp == 2);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
+            if (warp == 2) UM_TRACE(3, it);
             e.tmem_empty = tmem_empty_bar(acc);
-            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * UM_MAX_N);
-            epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, warp == 2 && lane == 0, lane, res_phase);
+            e.trace = p.trace, e.trace_seq = it;
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * UM_ACC_COLS);
+            if (p.ablate & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e.tmem_empty);
+                continue;
+            }
+            epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, warp == 2, lane, res_phase);
+            if (warp == 2) UM_TRACE(4, it);
         }
+        epilogue_drain(warp == 2);
     }
 
+    if (warp == 0) UM_TRACE(5, 2); // producer done
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) UM_TRACE(5, 3); // all roles done
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMax(reinterpret_cast<unsigned long long*>(p.trace) + 5 * 256 + 9, g);
+        if (blockIdx.x == 0) p.trace[5 * 256 + 11] = (long long) g;
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, UM_TMEM_COLS);
@@ -484,7 +645,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                    const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo, const RowWinParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sB_hi = smem_base, sB_lo = smem_base + RW_B_PLANE_BYTES;
+    const uint32_t sB = smem_base; // weight panel: per kernel row ky, [n_blk rows of B_hi ; n_blk rows of B_lo] x 128 B
     const uint32_t stg      = smem_base + 2 * RW_B_PLANE_BYTES; // epilogue staging (1024-aligned)
     const uint32_t sA0      = stg + UM_STG_BYTES;
     const uint32_t bar_base = sA0 + RW_STAGES * RW_STAGE_BYTES;
@@ -512,7 +673,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         mbar_init(b_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128); // two accumulator buffers of <= 64 columns
+    if (warp == 1) tmem_alloc(tmem_slot, 4 * RW_MAX_N); // two accumulator buffers of 2 x (<= 64) columns
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -522,13 +683,16 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
     const int total_tiles = p.N * p.OH * p.tiles_x;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             // weight panel: once per CTA
-            mbar_expect_tx(b_bar, 2u * (uint32_t) p.kh * (uint32_t) p.n_blk * 128u);
-            for (int ky = 0; ky < p.kh; ++ky) {
-                tma_load_2d(sB_hi + ky * p.n_blk * 128, &tmB_hi, b_bar, 0, ky * p.ocr);
-                tma_load_2d(sB_lo + ky * p.n_blk * 128, &tmB_lo, b_bar, 0, ky * p.ocr);
+            if (elect_one()) {
+                mbar_expect_tx(b_bar, 2u * (uint32_t) p.kh * (uint32_t) p.n_blk * 128u);
+                for (int ky = 0; ky < p.kh; ++ky) {
+                    tma_load_2d(sB + (2 * ky) * p.n_blk * 128, &tmB_hi, b_bar, 0, ky * p.ocr);
+                    tma_load_2d(sB + (2 * ky + 1) * p.n_blk * 128, &tmB_lo, b_bar, 0, ky * p.ocr);
+                }
             }
+            __syncwarp();
             // activation row segments
             int stage = 0;
             uint32_t phase = 0;
@@ -539,14 +703,17 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                 for (int ky = 0; ky < p.kh; ++ky) {
                     const int iy = oy * p.stride - p.pad_y + ky; // out of range -> the whole row is zero-filled
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), tx_bytes);
-                    tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
-                    tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
-                    if (p.parities == 2) {
-                        tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
-                        tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                    if (elect_one()) {
+                        const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
+                        mbar_expect_tx(full_bar(stage), tx_bytes);
+                        tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                        tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                        if (p.parities == 2) {
+                            tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                            tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == RW_STAGES) stage = 0, phase ^= 1u;
                 }
             }
@@ -555,26 +722,25 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         mbar_wait(b_bar, 0);
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t idesc = make_idesc(UM_BLOCK_M, p.n_blk);
+        const uint32_t idesc_cat = make_idesc(UM_BLOCK_M, 2 * p.n_blk), idesc = make_idesc(UM_BLOCK_M, p.n_blk); // see conv_umma_kernel
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * RW_MAX_N);
+            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * 2 * RW_MAX_N);
             for (int ky = 0; ky < p.kh; ++ky) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
-                    const uint64_t b_hi = make_smem_desc(sB_hi + ky * p.n_blk * 128), b_lo = make_smem_desc(sB_lo + ky * p.n_blk * 128);
+                    const uint64_t b_cat = make_smem_desc(sB + (2 * ky) * p.n_blk * 128); // [B_hi ; B_lo] rows of this kernel row
                     for (int q = 0; q < p.ksteps; ++q) {
                         const uint32_t off = (uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u;
                         const uint64_t a_hi = make_window_desc(sA + off), a_lo = make_window_desc(sA + 2 * RW_ARR_BYTES + off);
-                        umma_bf16(d_tmem, a_hi, b_hi + 2u * q, idesc, (ky > 0 || q > 0) ? 1u : 0u);
-                        umma_bf16(d_tmem, a_lo, b_hi + 2u * q, idesc, 1u);
-                        umma_bf16(d_tmem, a_hi, b_lo + 2u * q, idesc, 1u);
+                        umma_bf16(d_tmem, a_hi, b_cat + 2u * q, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u); // -> [hi.hi | hi.lo]
+                        umma_bf16(d_tmem, a_lo, b_cat + 2u * q, idesc, 1u);                              // lo.hi onto the first block
                     }
                     umma_commit(empty_bar(stage));
                     if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
@@ -593,6 +759,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         e.r_hi64 = e.r_lo64 = e.r_hiT = e.r_loT = &tmO_hi;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = 0, e.rows_box = UM_BLOCK_M, e.alpha = p.alpha;
         e.stg = stg, e.res_bar = 0;
+        e.trace = nullptr, e.trace_seq = 0;
         uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -602,16 +769,17 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             e.tmem_empty = tmem_empty_bar(acc);
-            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * RW_MAX_N);
-            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, 0, warp == 2 && lane == 0, lane, res_phase);
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * 2 * RW_MAX_N);
+            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, 0, warp == 2, lane, res_phase);
         }
+        epilogue_drain(warp == 2);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 4 * RW_MAX_N);
     }
 }
 
@@ -797,6 +965,8 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     p.cblocks = (in->c + UM_BLOCK_K - 1) / UM_BLOCK_K;
     p.ICp     = round_up(in->c, 8);
     p.act = a.act, p.alpha = a.alpha;
+    static const int ablate = getenv("SNNB_UMMA_ABLATE") ? atoi(getenv("SNNB_UMMA_ABLATE")) : 0;
+    p.ablate                = ablate;
     SNNB_REQUIRE(a.w->kp == a.k * a.k * p.ICp, "launch_conv2d_umma: packed weights do not match (kp %d vs %d)", a.w->kp, a.k * a.k * p.ICp);
 
     CUtensorMap tmA[2], tmB[2];
@@ -841,8 +1011,44 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles, ctx->sm_count);
+    static const bool trace_on = getenv("SNNB_UMMA_TRACE") != nullptr;
+    static long long* d_trace  = nullptr;
+    p.trace                    = nullptr;
+    if (trace_on) { // eager mode only (synchronises): dumps CTA 0's per-role timeline of every launch to stderr
+        if (!d_trace) SNNB_CUDA_OK(cudaMalloc(&d_trace, 6 * 256 * sizeof(long long)));
+        SNNB_CUDA_OK(cudaMemsetAsync(d_trace, 0, 6 * 256 * sizeof(long long), ctx->stream));
+        const long long big = 0x7fffffffffffffffLL;
+        SNNB_CUDA_OK(cudaMemcpyAsync(d_trace + 5 * 256 + 8, &big, sizeof(big), cudaMemcpyHostToDevice, ctx->stream));
+        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        p.trace = d_trace;
+    }
     conv_umma_kernel<<<grid, UM_THREADS, UM_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0],
                                                                       tmRT[1], p);
+    if (trace_on) {
+        std::vector<long long> h(6 * 256);
+        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        SNNB_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const long long t0 = h[5 * 256];
+        fprintf(stderr, "TRACE conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d\n", a.k, a.stride, in->c, out->c, out->n, out->h, out->w, p.n_blk, total_tiles,
+                grid, p.ksize * p.ksize * p.cblocks);
+        fprintf(stderr, "  wallclock_ns   all-CTA span %lld | CTA0 entry +%lld exit +%lld\n", h[5 * 256 + 9] - h[5 * 256 + 8], h[5 * 256 + 10] - h[5 * 256 + 8],
+                h[5 * 256 + 11] - h[5 * 256 + 8]);
+        fprintf(stderr, "  epi_phases (start, +phase1, +wait_read, +barA, +STS, +fence, +barB, +store) per slab:");
+        for (int sq = 0; sq < 16 && h[4 * 256 + 64 + 8 * sq]; ++sq) {
+            fprintf(stderr, " [");
+            for (int k = 1; k < 8; ++k) fprintf(stderr, "%lld ", h[4 * 256 + 64 + 8 * sq + k] ? h[4 * 256 + 64 + 8 * sq + k] - h[4 * 256 + 64 + 8 * sq] : -1);
+            fprintf(stderr, "]");
+        }
+        fprintf(stderr, "\n");
+        h[4 * 256 + 64] = 0;
+        h[5 * 256 + 4] = 0; // terminate the clock64 row before the wall-clock slots
+        const char* names[6] = {"prod_got_empty", "mma_got_full", "mma_issued", "epi_got_full", "epi_done", "entry_setup_proddone_alldone"};
+        for (int r = 0; r < 6; ++r) {
+            fprintf(stderr, "  %-14s", names[r]);
+            for (int i = 0; i < 256 && (h[r * 256 + i] || (r == 5 && i == 0)); ++i) fprintf(stderr, " %lld", h[r * 256 + i] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_umma_kernel launch failed: %s", cudaGetErrorString(e));
