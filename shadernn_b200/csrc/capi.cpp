@@ -2,6 +2,7 @@
 // (The whole-model engine entry points live in engine/model_capi.cpp.) See include/snnb.h for the reference
 // interface each entry point replaces.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -17,6 +18,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+    static const bool on = getenv("SNNB_NO_PDL") == nullptr;
+    return on;
+}
 
 int ensure_stage(snnb_context* ctx, size_t bytes) {
     if (ctx->stage_dev_bytes < bytes) {

@@ -8,6 +8,8 @@
 //
 // Semantics follow the reference's Vulkan compute shaders (cited per kernel; paths relative to the reference repo
 // core/data/assets/shaders/).
+#include <cstdlib>
+
 #include "snnb_internal.h"
 
 namespace snnb {
@@ -19,6 +21,16 @@ __device__ __forceinline__ float bf16lo_to_f32(uint32_t u) { return __uint_as_fl
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // 8 channels: v[i] = hi[i] + lo[i]
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float v[8]) {
+    v[0] = bf16lo_to_f32(h.x) + bf16lo_to_f32(l.x);
+    v[1] = bf16hi_to_f32(h.x) + bf16hi_to_f32(l.x);
+    v[2] = bf16lo_to_f32(h.y) + bf16lo_to_f32(l.y);
+    v[3] = bf16hi_to_f32(h.y) + bf16hi_to_f32(l.y);
+    v[4] = bf16lo_to_f32(h.z) + bf16lo_to_f32(l.z);
+    v[5] = bf16hi_to_f32(h.z) + bf16hi_to_f32(l.z);
+    v[6] = bf16lo_to_f32(h.w) + bf16lo_to_f32(l.w);
+    v[7] = bf16hi_to_f32(h.w) + bf16hi_to_f32(l.w);
+}
 __device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t off, float v[8]) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
     const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
@@ -127,6 +139,7 @@ struct ConvKParams {
 constexpr int CV_BM = 64, CV_BN = 64, CV_BK = 16;
 
 __global__ void __launch_bounds__(128) conv2d_simt_kernel(const ConvKParams p) {
+    pdl_wait();
     __shared__ __align__(16) float As[CV_BK][CV_BM + 4];
     __shared__ __align__(16) float Bs[CV_BK][CV_BN];
 
@@ -255,7 +268,7 @@ int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a) {
     p.K  = a.k * a.k * a.in->c;
     const long long M = (long long) a.out->n * a.out->h * a.out->w;
     dim3 grid((unsigned) ((M + CV_BM - 1) / CV_BM), (unsigned) ((a.out->cp + CV_BN - 1) / CV_BN));
-    conv2d_simt_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    launch_k(conv2d_simt_kernel, dim3(grid), dim3(128), 0, ctx->stream, p);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -276,6 +289,7 @@ struct DwParams {
 
 template <int K, int S, int TX>
 __global__ void __launch_bounds__(128) depthwise_kernel(const DwParams p) {
+    pdl_wait();
     const int CG            = p.out.Cp >> 3;
     const int strips        = (p.out.W + TX - 1) / TX;
     const long long total   = (long long) p.out.N * p.out.H * strips * CG;
@@ -344,6 +358,7 @@ __global__ void __launch_bounds__(128) depthwise_kernel(const DwParams p) {
 
 // generic (any k / stride): one thread = 8 channels x 1 output pixel
 __global__ void __launch_bounds__(128) depthwise_generic_kernel(const DwParams p) {
+    pdl_wait();
     const int CG          = p.out.Cp >> 3;
     const long long total = (long long) p.out.N * p.out.H * p.out.W * CG;
     const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,6 +394,8 @@ __global__ void __launch_bounds__(128) depthwise_generic_kernel(const DwParams p
 }
 
 int launch_depthwise(snnb_context* ctx, const ConvArgs& a) {
+    static const bool no_tma = getenv("SNNB_DW_SIMT") != nullptr; // A/B switch: the CUDA-core kernels below
+    if (!no_tma && depthwise_tma_supported(a)) return launch_depthwise_tma(ctx, a);
     DwParams p;
     p.in = view(a.in), p.out = view(a.out);
     p.w = a.w->w_f32, p.bias = a.w->bias;
@@ -390,12 +407,12 @@ int launch_depthwise(snnb_context* ctx, const ConvArgs& a) {
         const long long total = (long long) a.out->n * a.out->h * strips * CG;
         const unsigned blocks = (unsigned) ((total + 127) / 128);
         if (a.stride == 1)
-            depthwise_kernel<3, 1, TX><<<blocks, 128, 0, ctx->stream>>>(p);
+            launch_k(depthwise_kernel<3, 1, TX>, dim3(blocks), dim3(128), 0, ctx->stream, p);
         else
-            depthwise_kernel<3, 2, TX><<<blocks, 128, 0, ctx->stream>>>(p);
+            launch_k(depthwise_kernel<3, 2, TX>, dim3(blocks), dim3(128), 0, ctx->stream, p);
     } else {
         const long long total = (long long) a.out->n * a.out->h * a.out->w * CG;
-        depthwise_generic_kernel<<<(unsigned) ((total + 127) / 128), 128, 0, ctx->stream>>>(p);
+        launch_k(depthwise_generic_kernel, dim3((unsigned) ((total + 127) / 128)), dim3(128), 0, ctx->stream, p);
     }
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
@@ -406,7 +423,12 @@ int launch_depthwise(snnb_context* ctx, const ConvArgs& a) {
 // top/left, maxpool2dVulkan.cpp:57-60), taps clipped to the input, max starts at -100000, avg divides by the
 // number of valid taps. One thread = 8 channels x 1 output pixel.
 // ------------------------------------------------------------------------------------------------------------
+// K > 0: window size known at compile time, all K*K taps' loads are issued before any is consumed (the generic loop keeps
+// only one tap in flight per thread and ran at 40% of the HBM roofline on ResNet's 3x3/2 max pool).
+template <int K>
 __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int stride, int avg) {
+    pdl_wait();
+    if (K > 0) k = K;
     const int CG          = out.Cp >> 3;
     const long long total = (long long) out.N * out.H * out.W * CG;
     const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,19 +446,50 @@ __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int str
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = avg ? 0.0f : -100000.0f;
     float num = 0.0f;
-    for (int fy = 0; fy < efy; ++fy)
-        for (int fx = 0; fx < efx; ++fx) {
-            float v[8];
-            load8(in.hi, in.lo, (((size_t) n * in.H + sy + fy) * in.W + sx + fx) * in.Cp + c, v);
-            if (avg) {
+    if (K > 0) {
+        constexpr int KK = K > 0 ? K * K : 1;
+        uint4 th[KK], tl[KK]; // raw hi / lo planes of every tap; clipped taps re-read the window origin (always valid)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += v[j];
-                num += 1.0f;
-            } else {
+        for (int fy = 0; fy < K; ++fy)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], v[j]);
+            for (int fx = 0; fx < K; ++fx) {
+                const bool ok  = fy < efy && fx < efx;
+                const size_t o = (((size_t) n * in.H + sy + (ok ? fy : 0)) * in.W + sx + (ok ? fx : 0)) * in.Cp + c;
+                th[fy * K + fx] = __ldg(reinterpret_cast<const uint4*>(in.hi + o));
+                tl[fy * K + fx] = __ldg(reinterpret_cast<const uint4*>(in.lo + o));
             }
-        }
+#pragma unroll
+        for (int fy = 0; fy < K; ++fy)
+#pragma unroll
+            for (int fx = 0; fx < K; ++fx) {
+                if (fy < efy && fx < efx) {
+                    float v[8];
+                    unpack8(th[fy * K + fx], tl[fy * K + fx], v);
+                    if (avg) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                        num += 1.0f;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], v[j]);
+                    }
+                }
+            }
+    } else {
+        for (int fy = 0; fy < efy; ++fy)
+            for (int fx = 0; fx < efx; ++fx) {
+                float v[8];
+                load8(in.hi, in.lo, (((size_t) n * in.H + sy + fy) * in.W + sx + fx) * in.Cp + c, v);
+                if (avg) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                    num += 1.0f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], v[j]);
+                }
+            }
+    }
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (c + j < out.C) ? (avg ? acc[j] / num : acc[j]) : 0.0f;
@@ -446,6 +499,7 @@ __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int str
 // Global average pool (AveragePooling2D with pool == H == W, stride 1, valid — how the converter emits GAP,
 // tools/convertTool/layers/supportedLayers/averagepooling2d.py:40-55): one warp per (n, 8-channel group).
 __global__ void __launch_bounds__(256) global_avgpool_kernel(TV in, TV out) {
+    pdl_wait();
     const int CG   = out.Cp >> 3;
     const int warp = (int) (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -478,10 +532,13 @@ int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int 
     TV vi = view(in), vo = view(out);
     if (avg && out->h == 1 && out->w == 1 && k >= in->h && k >= in->w && in->h * in->w >= 16) {
         const long long warps = (long long) in->n * (out->cp >> 3);
-        global_avgpool_kernel<<<(unsigned) ((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(vi, vo);
+        launch_k(global_avgpool_kernel, dim3((unsigned) ((warps * 32 + 255) / 256)), dim3(256), 0, ctx->stream, vi, vo);
     } else {
         const long long total = (long long) out->n * out->h * out->w * (out->cp >> 3);
-        pool_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(vi, vo, k, stride, avg ? 1 : 0);
+        const dim3 grid((unsigned) ((total + 255) / 256));
+        if (k == 2) launch_k(pool_kernel<2>, grid, dim3(256), 0, ctx->stream, vi, vo, k, stride, avg ? 1 : 0);
+        else if (k == 3) launch_k(pool_kernel<3>, grid, dim3(256), 0, ctx->stream, vi, vo, k, stride, avg ? 1 : 0);
+        else launch_k(pool_kernel<0>, grid, dim3(256), 0, ctx->stream, vi, vo, k, stride, avg ? 1 : 0);
     }
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
@@ -493,6 +550,7 @@ int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int 
 //   (vk_activation.comp:41-85).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) add_kernel(TV a, TV b, TV out, int act, float alpha) {
+    pdl_wait();
     const size_t total = (size_t) out.N * out.H * out.W * (out.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -510,6 +568,7 @@ __global__ void __launch_bounds__(256) add_kernel(TV a, TV b, TV out, int act, f
 // mode 0: BN (scale = gamma/s precomputed on host as `gamma`), mode 1: activation only.
 __global__ void __launch_bounds__(256) chanwise_kernel(TV in, TV out, const float* __restrict__ scale, const float* __restrict__ mean,
                                                          const float* __restrict__ beta, int mode, int act, float alpha) {
+    pdl_wait();
     const size_t total = (size_t) out.N * out.H * out.W * (out.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -532,17 +591,17 @@ static unsigned vec_blocks(const snnb_tensor* t, int threads) {
 }
 
 int launch_add(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out, int act, float alpha) {
-    add_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(a), view(b), view(out), act, alpha);
+    launch_k(add_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(a), view(b), view(out), act, alpha);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha) {
-    chanwise_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), w->var /* = BN scale, see pack.cpp */, w->mean, w->beta, 0, act, alpha);
+    launch_k(chanwise_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), w->var /* = BN scale, see pack.cpp */, w->mean, w->beta, 0, act, alpha);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int act, float alpha) {
-    chanwise_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), nullptr, nullptr, nullptr, 1, act, alpha);
+    launch_k(chanwise_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), nullptr, nullptr, nullptr, 1, act, alpha);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -552,6 +611,7 @@ int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out
 // Argmax over channels per image -> 0-based index of the FIRST maximum (core.cpp:228-233 adds 1 at the API).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) softmax_kernel(TV in, TV out) {
+    pdl_wait();
     const long long px = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane     = threadIdx.x & 31;
     if (px >= (long long) in.N * in.H * in.W) return;
@@ -569,12 +629,13 @@ __global__ void __launch_bounds__(128) softmax_kernel(TV in, TV out) {
 }
 int launch_softmax(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out) {
     const long long px = (long long) in->pixels();
-    softmax_kernel<<<(unsigned) ((px * 32 + 127) / 128), 128, 0, ctx->stream>>>(view(in), view(out));
+    launch_k(softmax_kernel, dim3((unsigned) ((px * 32 + 127) / 128)), dim3(128), 0, ctx->stream, view(in), view(out));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 __global__ void __launch_bounds__(128) argmax_kernel(TV in, int* __restrict__ idx) {
+    pdl_wait();
     const int n    = (int) (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= in.N) return;
@@ -593,7 +654,7 @@ __global__ void __launch_bounds__(128) argmax_kernel(TV in, int* __restrict__ id
     if (lane == 0) idx[n] = bi;
 }
 int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx) {
-    argmax_kernel<<<(unsigned) (((long long) in->n * 32 + 127) / 128), 128, 0, ctx->stream>>>(view(in), dev_idx);
+    launch_k(argmax_kernel, dim3((unsigned) (((long long) in->n * 32 + 127) / 128)), dim3(128), 0, ctx->stream, view(in), dev_idx);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -603,6 +664,7 @@ int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx) {
 // ------------------------------------------------------------------------------------------------------------
 // Flatten, HWC order (cpulayer.h:94-115): out[n, (y*W + x)*C + c] = in[n,y,x,c]
 __global__ void flatten_kernel(TV in, TV out) {
+    pdl_wait();
     const size_t total = (size_t) out.N * out.Cp;
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -616,13 +678,14 @@ __global__ void flatten_kernel(TV in, TV out) {
 }
 int launch_flatten(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out) {
     const size_t total = (size_t) out->n * out->cp;
-    flatten_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(view(in), view(out));
+    launch_k(flatten_kernel, dim3((unsigned) ((total + 255) / 256)), dim3(256), 0, ctx->stream, view(in), view(out));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 // Concatenate along channels (vk_concat.comp:39-52).
 __global__ void concat_kernel(TV a, TV b, TV out) {
+    pdl_wait();
     const size_t total = (size_t) out.N * out.H * out.W * out.Cp;
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -637,13 +700,14 @@ __global__ void concat_kernel(TV a, TV b, TV out) {
 }
 int launch_concat(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out) {
     const size_t total = out->pixels() * out->cp;
-    concat_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(view(a), view(b), view(out));
+    launch_k(concat_kernel, dim3((unsigned) ((total + 255) / 256)), dim3(256), 0, ctx->stream, view(a), view(b), view(out));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 // UpSampling2D (vk_upsampling2d_nearest.comp:43-64; vk_upsampling2d_bilinear.comp:43-86), 8-channel vectors.
 __global__ void upsample_kernel(TV in, TV out, float inv, int bilinear) {
+    pdl_wait();
     const int CG          = out.Cp >> 3;
     const long long total = (long long) out.N * out.H * out.W * CG;
     const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -683,13 +747,14 @@ __global__ void upsample_kernel(TV in, TV out, float inv, int bilinear) {
     store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
 }
 int launch_upsample(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, float scale, bool bilinear) {
-    upsample_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), 1.0f / scale, bilinear ? 1 : 0);
+    launch_k(upsample_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), 1.0f / scale, bilinear ? 1 : 0);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 // Pad (vk_pad.comp:42-70): constant(0) / replicate / reflect.
 __global__ void pad_kernel(TV in, TV out, int pad_x, int pad_y, int mode) {
+    pdl_wait();
     const int CG          = out.Cp >> 3;
     const long long total = (long long) out.N * out.H * out.W * CG;
     const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -708,7 +773,7 @@ __global__ void pad_kernel(TV in, TV out, int pad_x, int pad_y, int mode) {
     store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
 }
 int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int pad_x, int pad_y, int mode) {
-    pad_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), pad_x, pad_y, mode);
+    launch_k(pad_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), pad_x, pad_y, mode);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -717,6 +782,7 @@ int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int p
 // Pass 1: one CTA per (n, 8-channel group): two-pass mean / variance in fp32 with a fixed reduction tree
 // (deterministic), stats -> global. Pass 2: elementwise normalise + act.
 __global__ void __launch_bounds__(256) instnorm_stats_kernel(TV in, float* __restrict__ stats) {
+    pdl_wait();
     __shared__ float red[8][8]; // [warp][channel]
     __shared__ float meanv[8];
     const int CG = in.Cp >> 3;
@@ -770,6 +836,7 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(TV in, float* __res
 }
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(TV in, TV out, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, int act, float alpha) {
+    pdl_wait();
     const int CG          = out.Cp >> 3;
     const long long total = (long long) out.N * out.H * out.W * CG;
     const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -794,15 +861,16 @@ int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* o
         if (ensure_stage(ctx, stat_bytes)) return 1;
         stats = ctx->stage_dev;
     }
-    instnorm_stats_kernel<<<(unsigned) (in->n * (in->cp >> 3)), 256, 0, ctx->stream>>>(view(in), stats);
+    launch_k(instnorm_stats_kernel, dim3((unsigned) (in->n * (in->cp >> 3))), dim3(256), 0, ctx->stream, view(in), stats);
     SNNB_LAUNCH_CHECK(ctx);
-    instnorm_apply_kernel<<<vec_blocks(out, 256), 256, 0, ctx->stream>>>(view(in), view(out), stats, w->gamma, w->beta, act, alpha);
+    launch_k(instnorm_apply_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), stats, w->gamma, w->beta, act, alpha);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 // Subpixel: depth_to_space(r) + tanh (vk_subpixel.comp:43-70; component = x%r + r*(y%r), fs_subpixel.glsl:41).
 __global__ void subpixel_kernel(TV in, TV out, int r) {
+    pdl_wait();
     const long long total = (long long) out.N * out.H * out.W;
     const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -820,7 +888,7 @@ __global__ void subpixel_kernel(TV in, TV out, int r) {
 }
 int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int r) {
     const long long total = (long long) out->pixels();
-    subpixel_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(view(in), view(out), r);
+    launch_k(subpixel_kernel, dim3((unsigned) ((total + 255) / 256)), dim3(256), 0, ctx->stream, view(in), view(out), r);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -829,6 +897,7 @@ int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, 
 // API edge: fp32 NHWC (dense pitch C) <-> split-bf16 (pitch Cp).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void split_kernel(const float* __restrict__ src, TV t) {
+    pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -841,6 +910,7 @@ __global__ void split_kernel(const float* __restrict__ src, TV t) {
     store8(t.hi, t.lo, gid * 8, v);
 }
 __global__ void merge_kernel(TV t, float* __restrict__ dst) {
+    pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -854,12 +924,12 @@ __global__ void merge_kernel(TV t, float* __restrict__ dst) {
         if (c + j < t.C) dst[px * t.C + c + j] = v[j];
 }
 int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t) {
-    split_kernel<<<vec_blocks(t, 256), 256, 0, ctx->stream>>>(dev_nhwc, view(t));
+    launch_k(split_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc, view(t));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc) {
-    merge_kernel<<<vec_blocks(t, 256), 256, 0, ctx->stream>>>(view(t), dev_nhwc);
+    launch_k(merge_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, view(t), dev_nhwc);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -408,14 +408,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t res_bar   = bar_base + 8u * (2 * UM_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0) UM_TRACE(5, 0); // kernel entry
-    if (p.trace && threadIdx.x == 0) { // wall-clock (ns) envelope over ALL CTAs: [5][8] = earliest entry, [5][9] = latest exit, [5][10..11] CTA 0's own
-        unsigned long long g;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-        atomicMin(reinterpret_cast<unsigned long long*>(p.trace) + 5 * 256 + 8, g);
-        if (blockIdx.x == 0) p.trace[5 * 256 + 10] = (long long) g;
-    }
-
+    pdl_trigger(); // the next kernel may start launching; it waits for this grid's completion before touching memory
     if (warp == 0 && lane == 0) {
         mbar_init(res_bar, 1);
         tma_prefetch_desc(&tmO_hi64);
@@ -440,6 +433,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait(); // everything above (barriers, TMEM, tensor-map prefetch) overlapped with the previous kernel's tail
+    if (warp == 0) UM_TRACE(5, 0); // kernel entry (after the dependency wait)
+    if (p.trace && threadIdx.x == 0) { // wall-clock (ns) envelope over ALL CTAs: [5][8] = earliest entry, [5][9] = latest exit, [5][10..11] CTA 0's own
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMin(reinterpret_cast<unsigned long long*>(p.trace) + 5 * 256 + 8, g);
+        if (blockIdx.x == 0) p.trace[5 * 256 + 10] = (long long) g;
+    }
+
     if (warp == 0) UM_TRACE(5, 1); // setup done
 
     const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -612,7 +614,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // persistent CTA and stays resident. Tiles = up to 128 consecutive output pixels of one output row.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RW_STAGES        = 6;
-constexpr int RW_EPI_WARPS     = 4;
+constexpr int RW_EPI_WARPS     = 8;
 constexpr int RW_THREADS       = 64 + 32 * RW_EPI_WARPS;
 constexpr int RW_MAX_KH        = 8;
 constexpr int RW_MAX_N         = 64;
@@ -633,6 +635,7 @@ struct RowWinParams {
     int ksteps, ks_parity[4], ks_erel[4];
     int act;
     float alpha;
+    long long* trace; // profiling aid, see UmmaParams
 };
 
 // SWIZZLE_NONE K-major descriptor with an overlapping K stride: LBO = 16 B (next chunk = next pixel), SBO = 128 B
@@ -657,6 +660,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
     const uint32_t tmem_slot = bar_base + 8u * (2 * RW_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi0);
         tma_prefetch_desc(&tmA_lo0);
@@ -679,6 +683,14 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    if (warp == 0) UM_TRACE(5, 0);
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMin(reinterpret_cast<unsigned long long*>(p.trace) + 5 * 256 + 8, g);
+        if (blockIdx.x == 0) p.trace[5 * 256 + 10] = (long long) g;
+    }
 
     const int total_tiles = p.N * p.OH * p.tiles_x;
 
@@ -720,46 +732,63 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         }
     } else if (warp == 1) {
         mbar_wait(b_bar, 0);
-        int stage = 0;
-        uint32_t phase = 0;
         const uint32_t idesc_cat = make_idesc(UM_BLOCK_M, 2 * p.n_blk), idesc = make_idesc(UM_BLOCK_M, p.n_blk); // see conv_umma_kernel
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
-            mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t) (acc * 2 * RW_MAX_N);
-            for (int ky = 0; ky < p.kh; ++ky) {
-                mbar_wait(full_bar(stage), phase);
+        if (elect_one()) { // one thread owns the issue loop (see conv_umma_kernel)
+            // window descriptor (16-byte address field) offsets of the K steps, relative to the stage's hi plane
+            uint32_t koff[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) koff[q] = q < p.ksteps ? (((uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u) >> 4) : 0u;
+            const uint64_t wdesc0 = make_window_desc(sA0), bdesc0 = make_smem_desc(sB);
+            const uint32_t b_ky   = (uint32_t) (2 * p.n_blk * 128) >> 4; // one kernel row of [B_hi ; B_lo]
+            const int last_q      = p.ksteps - 1;
+            const uint32_t koff_last = ((uint32_t) p.ks_parity[last_q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[last_q] * 16u) >> 4;
+            int stage = 0, it = 0, tr = 0;
+            uint32_t phase = 0;
+            bool ready     = false;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
-                    const uint64_t b_cat = make_smem_desc(sB + (2 * ky) * p.n_blk * 128); // [B_hi ; B_lo] rows of this kernel row
-                    for (int q = 0; q < p.ksteps; ++q) {
-                        const uint32_t off = (uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u;
-                        const uint64_t a_hi = make_window_desc(sA + off), a_lo = make_window_desc(sA + 2 * RW_ARR_BYTES + off);
-                        umma_bf16(d_tmem, a_hi, b_cat + 2u * q, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u); // -> [hi.hi | hi.lo]
-                        umma_bf16(d_tmem, a_lo, b_cat + 2u * q, idesc, 1u);                              // lo.hi onto the first block
+                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * 2 * RW_MAX_N);
+                uint64_t b_cat = bdesc0;
+                for (int ky = 0; ky < p.kh; ++ky, b_cat += b_ky) {
+                    if (!ready) mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    UM_TRACE(1, tr);
+                    const uint64_t a0 = wdesc0 + (uint64_t) (uint32_t) (stage * (RW_STAGE_BYTES >> 4));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < last_q) {
+                            umma_bf16(d_tmem, a0 + koff[q], b_cat + 2u * q, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u);   // -> [hi.hi | hi.lo]
+                            umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff[q], b_cat + 2u * q, idesc, 1u);     // lo.hi onto the first block
+                        }
                     }
-                    umma_commit(empty_bar(stage));
+                    const int cur = stage;
+                    phase ^= (stage == RW_STAGES - 1) ? 1u : 0u;
+                    stage = stage == RW_STAGES - 1 ? 0 : stage + 1;
+                    ready = mbar_test_wait(full_bar(stage), phase); // look-ahead, overlaps with the MMAs already queued
+                    umma_bf16(d_tmem, a0 + koff_last, b_cat + 2u * last_q, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
+                    umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff_last, b_cat + 2u * last_q, idesc, 1u);
+                    umma_commit(empty_bar(cur));
                     if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
+                    UM_TRACE(2, tr);
+                    ++tr;
                 }
-                __syncwarp();
-                if (++stage == RW_STAGES) stage = 0, phase ^= 1u;
             }
         }
+        __syncwarp();
     } else {
-        // ---- epilogue: 4 warps, one TMEM lane quarter each (see epilogue_tile) ----
-        const int q   = warp & 3;
-        const int row = q * 32 + lane;
+        // ---- epilogue: 8 warps, TMEM lane quarter = warp % 4, two interleaved sets of 16-column chunks (see epilogue_tile) ----
+        const int q    = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row  = q * 32 + lane;
         EpiArgs e;
         // a 64-channel slab uses the swizzled map, a narrower one the dense map: the host encodes the right one into both slots
         e.o_hi64 = &tmO_hi, e.o_lo64 = &tmO_lo, e.o_hiT = &tmO_hi, e.o_loT = &tmO_lo;
         e.r_hi64 = e.r_lo64 = e.r_hiT = e.r_loT = &tmO_hi;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = 0, e.rows_box = UM_BLOCK_M, e.alpha = p.alpha;
         e.stg = stg, e.res_bar = 0;
-        e.trace = nullptr, e.trace_seq = 0;
         uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -768,15 +797,25 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             const int xt = tile % p.tiles_x, oy = (tile / p.tiles_x) % p.OH, n = tile / (p.tiles_x * p.OH);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
+            if (warp == 2) UM_TRACE(3, it);
             e.tmem_empty = tmem_empty_bar(acc);
+            e.trace = p.trace, e.trace_seq = it;
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * 2 * RW_MAX_N);
-            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, 0, warp == 2, lane, res_phase);
+            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, half, warp == 2, lane, res_phase);
+            if (warp == 2) UM_TRACE(4, it);
         }
         epilogue_drain(warp == 2);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) UM_TRACE(5, 3);
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMax(reinterpret_cast<unsigned long long*>(p.trace) + 5 * 256 + 9, g);
+        if (blockIdx.x == 0) p.trace[5 * 256 + 11] = (long long) g;
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 4 * RW_MAX_N);
@@ -786,6 +825,47 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: tile-shape selection, tensor maps, launch
 // ---------------------------------------------------------------------------------------------------------------
+// ---- SNNB_UMMA_TRACE: per-launch timeline of CTA 0 (eager mode only: synchronises around every launch) ----
+static bool trace_enabled() {
+    static const bool on = getenv("SNNB_UMMA_TRACE") != nullptr;
+    return on;
+}
+static int trace_begin(snnb_context* ctx, long long** out) {
+    static long long* d_trace = nullptr;
+    if (!d_trace) SNNB_CUDA_OK(cudaMalloc(&d_trace, 6 * 256 * sizeof(long long)));
+    SNNB_CUDA_OK(cudaMemsetAsync(d_trace, 0, 6 * 256 * sizeof(long long), ctx->stream));
+    const long long big = 0x7fffffffffffffffLL;
+    SNNB_CUDA_OK(cudaMemcpyAsync(d_trace + 5 * 256 + 8, &big, sizeof(big), cudaMemcpyHostToDevice, ctx->stream));
+    SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *out = d_trace;
+    return 0;
+}
+static int trace_end(snnb_context* ctx, const long long* d_trace, const char* header) {
+    std::vector<long long> h(6 * 256);
+    SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    SNNB_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const long long t0 = h[5 * 256];
+    fprintf(stderr, "TRACE %s\n", header);
+    fprintf(stderr, "  wallclock_ns   all-CTA span %lld | CTA0 entry +%lld exit +%lld\n", h[5 * 256 + 9] - h[5 * 256 + 8], h[5 * 256 + 10] - h[5 * 256 + 8],
+            h[5 * 256 + 11] - h[5 * 256 + 8]);
+    fprintf(stderr, "  epi_phases (start, +phase1, +wait_read, +barA, +STS, +fence, +barB, +store) per slab:");
+    for (int sq = 0; sq < 16 && h[4 * 256 + 64 + 8 * sq]; ++sq) {
+        fprintf(stderr, " [");
+        for (int k = 1; k < 8; ++k) fprintf(stderr, "%lld ", h[4 * 256 + 64 + 8 * sq + k] ? h[4 * 256 + 64 + 8 * sq + k] - h[4 * 256 + 64 + 8 * sq] : -1);
+        fprintf(stderr, "]");
+    }
+    fprintf(stderr, "\n");
+    h[4 * 256 + 64] = 0;
+    h[5 * 256 + 4]  = 0; // terminate the clock64 row before the wall-clock slots
+    const char* names[6] = {"prod_got_empty", "mma_got_full", "mma_issued", "epi_got_full", "epi_done", "entry_setup_proddone_alldone"};
+    for (int r = 0; r < 6; ++r) {
+        fprintf(stderr, "  %-14s", names[r]);
+        for (int i = 0; i < 256 && (h[r * 256 + i] || (r == 5 && i == 0)); ++i) fprintf(stderr, " %lld", h[r * 256 + i] - t0);
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -934,8 +1014,16 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     }
     const int total_tiles = p.N * p.OH * p.tiles_x;
     const int grid        = std::min(total_tiles, ctx->sm_count);
-    conv_rowwin_kernel<<<grid, RW_THREADS, RW_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], tmO[0], tmO[1], p);
-    cudaError_t e = cudaGetLastError();
+    p.trace = nullptr;
+    if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
+    const cudaError_t le = launch_k_pdl(conv_rowwin_kernel, dim3(grid), dim3(RW_THREADS), RW_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], tmO[0], tmO[1], p);
+    if (p.trace) {
+        char hdr[256];
+        snprintf(hdr, sizeof hdr, "rowwin k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d kh %d ksteps %d", a.k, a.stride, a.in->c, a.out->c, a.out->n, a.out->h, a.out->w,
+                 p.n_blk, total_tiles, grid, p.kh, p.ksteps);
+        if (trace_end(ctx, p.trace, hdr)) return 1;
+    }
+    cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_rowwin_kernel launch failed: %s", cudaGetErrorString(e));
         return 1;
@@ -1011,51 +1099,251 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles, ctx->sm_count);
-    static const bool trace_on = getenv("SNNB_UMMA_TRACE") != nullptr;
-    static long long* d_trace  = nullptr;
-    p.trace                    = nullptr;
-    if (trace_on) { // eager mode only (synchronises): dumps CTA 0's per-role timeline of every launch to stderr
-        if (!d_trace) SNNB_CUDA_OK(cudaMalloc(&d_trace, 6 * 256 * sizeof(long long)));
-        SNNB_CUDA_OK(cudaMemsetAsync(d_trace, 0, 6 * 256 * sizeof(long long), ctx->stream));
-        const long long big = 0x7fffffffffffffffLL;
-        SNNB_CUDA_OK(cudaMemcpyAsync(d_trace + 5 * 256 + 8, &big, sizeof(big), cudaMemcpyHostToDevice, ctx->stream));
-        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-        p.trace = d_trace;
+    p.trace = nullptr;
+    if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
+    const cudaError_t le = launch_k_pdl(conv_umma_kernel, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1],
+                                    tmR64[0], tmR64[1], tmRT[0], tmRT[1], p);
+    if (p.trace) {
+        char hdr[256];
+        snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d", a.k, a.stride, in->c, out->c, out->n, out->h, out->w, p.n_blk,
+                 total_tiles, grid, p.ksize * p.ksize * p.cblocks);
+        if (trace_end(ctx, p.trace, hdr)) return 1;
     }
-    conv_umma_kernel<<<grid, UM_THREADS, UM_SMEM_BYTES, ctx->stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0],
-                                                                      tmRT[1], p);
-    if (trace_on) {
-        std::vector<long long> h(6 * 256);
-        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-        SNNB_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        const long long t0 = h[5 * 256];
-        fprintf(stderr, "TRACE conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d\n", a.k, a.stride, in->c, out->c, out->n, out->h, out->w, p.n_blk, total_tiles,
-                grid, p.ksize * p.ksize * p.cblocks);
-        fprintf(stderr, "  wallclock_ns   all-CTA span %lld | CTA0 entry +%lld exit +%lld\n", h[5 * 256 + 9] - h[5 * 256 + 8], h[5 * 256 + 10] - h[5 * 256 + 8],
-                h[5 * 256 + 11] - h[5 * 256 + 8]);
-        fprintf(stderr, "  epi_phases (start, +phase1, +wait_read, +barA, +STS, +fence, +barB, +store) per slab:");
-        for (int sq = 0; sq < 16 && h[4 * 256 + 64 + 8 * sq]; ++sq) {
-            fprintf(stderr, " [");
-            for (int k = 1; k < 8; ++k) fprintf(stderr, "%lld ", h[4 * 256 + 64 + 8 * sq + k] ? h[4 * 256 + 64 + 8 * sq + k] - h[4 * 256 + 64 + 8 * sq] : -1);
-            fprintf(stderr, "]");
-        }
-        fprintf(stderr, "\n");
-        h[4 * 256 + 64] = 0;
-        h[5 * 256 + 4] = 0; // terminate the clock64 row before the wall-clock slots
-        const char* names[6] = {"prod_got_empty", "mma_got_full", "mma_issued", "epi_got_full", "epi_done", "entry_setup_proddone_alldone"};
-        for (int r = 0; r < 6; ++r) {
-            fprintf(stderr, "  %-14s", names[r]);
-            for (int i = 0; i < 256 && (h[r * 256 + i] || (r == 5 && i == 0)); ++i) fprintf(stderr, " %lld", h[r * 256 + i] - t0);
-            fprintf(stderr, "\n");
-        }
-    }
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_umma_kernel launch failed: %s", cudaGetErrorString(e));
         return 1;
     }
     ctx->launches++;
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Depthwise 3x3 (stride 1 / 2), TMA-staged + register-tiled (shadertemplate_vk_depthwise.comp:64-139).
+//
+// HBM-bound work: every input byte should cross the memory system once. A persistent CTA walks tiles of
+// TH x TW output pixels x 64 channels; for each tile ONE TMA box load per plane brings the (TH-1)*S+3 x (TW-1)*S+3
+// input patch (128-byte pixel rows, no swizzle; out-of-image pixels and channels >= C are zero-filled = the zero padding)
+// into a 3-deep shared-memory ring, so loads of the next tiles are in flight while this one is computed. A thread owns
+// 8 channels (one 16-byte piece of the pixel row) and TXT consecutive output columns and streams the patch rows through
+// registers (stride 1: 18 pixel loads for 4 outputs). A warp reads 4 pixel rows x 128 B per instruction: conflict-free.
+// Outputs go straight to global memory: a warp writes 4 full 128-byte lines per plane.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DW_THREADS = 256;
+constexpr int DW_STAGES  = 3;
+template <int S> struct DwTile {
+    static constexpr int TW = S == 1 ? 16 : 8, TH = S == 1 ? 8 : 4; // output pixels per tile: 128 / 32
+    static constexpr int TXT = S == 1 ? 4 : 1;                      // output columns per thread
+    static constexpr int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
+    static constexpr int PLANE_BYTES = IW * IH * 128;
+    static constexpr int STAGE_BYTES = 2 * PLANE_BYTES;
+    static constexpr int SMEM_BYTES  = DW_STAGES * STAGE_BYTES + 128 /*alignment*/ + 64 /*barriers*/;
+};
+struct DwTmaParams {
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    const float* w;    // [9][Cp]
+    const float* bias; // [Cp + padding]
+    int N, OH, OW, C, Cp;
+    int pad_x, pad_y;
+    int tiles_x, tiles_y, chunks;
+    int act;
+    float alpha;
+};
+
+template <int S>
+__global__ void __launch_bounds__(DW_THREADS, 1) depthwise_tma_kernel(const __grid_constant__ CUtensorMap tmI_hi, const __grid_constant__ CUtensorMap tmI_lo, const DwTmaParams p) {
+    using T = DwTile<S>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t bar_base  = smem_base + DW_STAGES * T::STAGE_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    pdl_trigger();
+    if (tid == 0) {
+        tma_prefetch_desc(&tmI_hi);
+        tma_prefetch_desc(&tmI_lo);
+        for (int s = 0; s < DW_STAGES; ++s) mbar_init(bar_base + 8u * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    pdl_wait();
+
+    const int sp_tiles = p.N * p.tiles_y * p.tiles_x;
+    const int total    = sp_tiles * p.chunks; // chunk is the slowest index: a CTA's consecutive tiles share its weights
+    auto issue = [&](int tile, int stage) {   // one thread
+        const int chunk = tile / sp_tiles, sp = tile - chunk * sp_tiles;
+        const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, n = sp / (p.tiles_x * p.tiles_y);
+        const uint32_t dst = smem_base + stage * T::STAGE_BYTES, bar = bar_base + 8u * stage;
+        mbar_expect_tx(bar, T::STAGE_BYTES);
+        tma_load_4d(dst, &tmI_hi, bar, chunk * 64, tx * T::TW * S - p.pad_x, ty * T::TH * S - p.pad_y, n);
+        tma_load_4d(dst + T::PLANE_BYTES, &tmI_lo, bar, chunk * 64, tx * T::TW * S - p.pad_x, ty * T::TH * S - p.pad_y, n);
+    };
+    if (tid == 0)
+        for (int j = 0; j < DW_STAGES; ++j) {
+            const int tile = blockIdx.x + j * gridDim.x;
+            if (tile < total) issue(tile, j);
+        }
+
+    const int cg  = tid & 7, pt = tid >> 3;                                            // 16-byte channel piece, pixel-thread 0..31
+    const int tyl = S == 1 ? (pt >> 2) : (pt >> 3), txl = S == 1 ? (pt & 3) * 4 : (pt & 7); // first output (row, col) in the tile
+    const float slope   = (p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6) ? 0.0f : (p.act == SNNB_ACT_LEAKY_RELU ? p.alpha : 1.0f);
+    const float hi_clip = p.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+    const bool fast_act = p.act == SNNB_ACT_NONE || p.act == SNNB_ACT_RELU || p.act == SNNB_ACT_RELU6 || p.act == SNNB_ACT_LEAKY_RELU;
+
+    float wreg[9][8], breg[8];
+    int cur_chunk = -1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int stage = it % DW_STAGES;
+        const int chunk = tile / sp_tiles, sp = tile - chunk * sp_tiles;
+        const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, n = sp / (p.tiles_x * p.tiles_y);
+        const int c = chunk * 64 + cg * 8;
+        if (chunk != cur_chunk) { // this thread's 8 channels of the folded weights and bias
+            cur_chunk = chunk;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+                if (c < p.Cp) {
+                    w0 = __ldg(reinterpret_cast<const float4*>(p.w + (size_t) t * p.Cp + c));
+                    w1 = __ldg(reinterpret_cast<const float4*>(p.w + (size_t) t * p.Cp + c) + 1);
+                }
+                wreg[t][0] = w0.x, wreg[t][1] = w0.y, wreg[t][2] = w0.z, wreg[t][3] = w0.w;
+                wreg[t][4] = w1.x, wreg[t][5] = w1.y, wreg[t][6] = w1.z, wreg[t][7] = w1.w;
+            }
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (c < p.Cp) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + 1);
+            }
+            breg[0] = b0.x, breg[1] = b0.y, breg[2] = b0.z, breg[3] = b0.w, breg[4] = b1.x, breg[5] = b1.y, breg[6] = b1.z, breg[7] = b1.w;
+        }
+        mbar_wait(bar_base + 8u * stage, (uint32_t) (it / DW_STAGES) & 1u);
+        const uint32_t src = smem_base + stage * T::STAGE_BYTES + (uint32_t) cg * 16u;
+
+        float acc[T::TXT][8];
+#pragma unroll
+        for (int t = 0; t < T::TXT; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = breg[j];
+        constexpr int COLS = S * (T::TXT - 1) + 3;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int cx = 0; cx < COLS; ++cx) {
+                const uint32_t a = src + (uint32_t) (((tyl * S + ky) * T::IW + txl * S + cx) * 128);
+                uint32_t h[4], l[4];
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(a));
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(a + T::PLANE_BYTES));
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[2 * j]     = __uint_as_float(h[j] << 16) + __uint_as_float(l[j] << 16);
+                    v[2 * j + 1] = __uint_as_float(h[j] & 0xffff0000u) + __uint_as_float(l[j] & 0xffff0000u);
+                }
+#pragma unroll
+                for (int t = 0; t < T::TXT; ++t) {
+                    const int kx = cx - t * S; // compile-time after unrolling
+                    if (kx >= 0 && kx < 3) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(wreg[ky * 3 + kx][j], v[j], acc[t][j]);
+                    }
+                }
+            }
+        }
+        const int oy = ty * T::TH + tyl;
+        if (oy < p.OH && c < p.Cp) {
+#pragma unroll
+            for (int t = 0; t < T::TXT; ++t) {
+                const int ox = tx * T::TW + txl + t;
+                if (ox < p.OW) {
+                    float v[8];
+                    if (fast_act) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(acc[t][j], acc[t][j] * slope), hi_clip);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = umma_act(acc[t][j], p.act, p.alpha);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = (c + j < p.C) ? v[j] : 0.0f; // channel padding stays zero
+                    uint4 oh, ol;
+                    um_split2(v[0], v[1], oh.x, ol.x);
+                    um_split2(v[2], v[3], oh.y, ol.y);
+                    um_split2(v[4], v[5], oh.z, ol.z);
+                    um_split2(v[6], v[7], oh.w, ol.w);
+                    const size_t o = (((size_t) n * p.OH + oy) * p.OW + ox) * p.Cp + c;
+                    *reinterpret_cast<uint4*>(p.out_hi + o) = oh;
+                    *reinterpret_cast<uint4*>(p.out_lo + o) = ol;
+                }
+            }
+        }
+        __syncthreads(); // everyone is done reading this stage
+        if (tid == 0) {
+            const int next = tile + DW_STAGES * gridDim.x;
+            if (next < total) {
+                fence_async_smem(); // generic-proxy reads above, async-proxy (TMA) writes below
+                issue(next, stage);
+            }
+        }
+    }
+    (void) warp;
+}
+
+bool depthwise_tma_supported(const ConvArgs& a) {
+    // tiles are 8x16 (stride 1) / 4x8 (stride 2) output pixels: tiny feature maps (7x7) would leave most of a tile empty
+    const int tw = a.stride == 1 ? 16 : 8, th = a.stride == 1 ? 8 : 4;
+    const int tx = (a.out->w + tw - 1) / tw, ty = (a.out->h + th - 1) / th;
+    if ((double) a.out->w * a.out->h < 0.5 * (double) tx * tw * ty * th) return false;
+    return a.k == 3 && (a.stride == 1 || a.stride == 2) && a.residual == nullptr && a.in->c == a.out->c && a.w->w_f32 != nullptr &&
+           a.pad_mode <= SNNB_PAD_CONSTANT; // zero padding = the TMA out-of-bounds fill
+}
+
+template <int S> static int launch_depthwise_tma_s(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
+    using T = DwTile<S>;
+    const snnb_tensor* in = a.in;
+    snnb_tensor* out      = a.out;
+    DwTmaParams p;
+    p.out_hi = out->hi, p.out_lo = out->lo;
+    p.w = a.w->w_f32, p.bias = a.w->bias;
+    p.N = out->n, p.OH = out->h, p.OW = out->w, p.C = out->c, p.Cp = out->cp;
+    p.pad_x = a.pad_x, p.pad_y = a.pad_y;
+    p.tiles_x = (out->w + T::TW - 1) / T::TW, p.tiles_y = (out->h + T::TH - 1) / T::TH, p.chunks = (out->cp + 63) / 64;
+    p.act = a.act, p.alpha = a.alpha;
+    CUtensorMap tmI[2];
+    {
+        const cuuint64_t dims[4]    = {(cuuint64_t) in->c, (cuuint64_t) in->w, (cuuint64_t) in->h, (cuuint64_t) in->n}; // channels >= C read as zero
+        const cuuint64_t strides[3] = {(cuuint64_t) in->cp * 2, (cuuint64_t) in->w * in->cp * 2, (cuuint64_t) in->h * in->w * in->cp * 2};
+        const cuuint32_t box[4]     = {64, (cuuint32_t) T::IW, (cuuint32_t) T::IH, 1};
+        const cuuint32_t estr[4]    = {1, 1, 1, 1};
+        __nv_bfloat16* planes[2]    = {in->hi, in->lo};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = encode(&tmI[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(depthwise input) failed: %d", (int) r);
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SNNB_CUDA_OK(cudaFuncSetAttribute(depthwise_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long total = (long long) p.N * p.tiles_y * p.tiles_x * p.chunks;
+    const int grid        = (int) std::min<long long>(total, ctx->sm_count);
+    const cudaError_t le  = launch_k_pdl(depthwise_tma_kernel<S>, dim3(grid), dim3(DW_THREADS), T::SMEM_BYTES, ctx->stream, tmI[0], tmI[1], p);
+    cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("depthwise_tma_kernel launch failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    ctx->launches++;
+    return 0;
+}
+
+int launch_depthwise_tma(snnb_context* ctx, const ConvArgs& a) {
+    EncodeTiledFn encode = get_encode(ctx);
+    SNNB_REQUIRE(encode, "launch_depthwise_tma: cuTensorMapEncodeTiled is unavailable in this driver");
+    return a.stride == 1 ? launch_depthwise_tma_s<1>(ctx, a, encode) : launch_depthwise_tma_s<2>(ctx, a, encode);
 }
 
 } // namespace snnb

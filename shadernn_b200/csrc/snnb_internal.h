@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "snnb.h"
@@ -35,6 +36,45 @@ const char* get_error();
     } while (0)
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The persistent TMA / tcgen05 kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may
+// be scheduled (and run their prologue: barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel is
+// still draining. pdl_wait() blocks until the previous grid has completed and its writes are visible; NOTHING before it
+// may touch global memory that another kernel writes. pdl_trigger() lets the next grid start launching. ONLY the persistent
+// kernels (grid <= SM count, every CTA resident from the start) call it, first thing: in a multi-wave kernel the early
+// dependents would sit resident in griddepcontrol.wait and take SM slots from this grid's later waves (measured: the
+// style-transfer graph ran 2.2x slower with triggers in the CUDA-core kernels). Set SNNB_NO_PDL=1 to launch plainly.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_impl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = grid;
+    cfg.blockDim           = block;
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// plain stream-ordered launch (the CUDA-core kernels: no prologue worth overlapping)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_k_impl(false, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+// programmatic dependent launch (the persistent TMA / tcgen05 kernels, which call pdl_trigger() and pdl_wait())
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_k_impl(true, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+#endif
 
 } // namespace snnb
 
@@ -114,6 +154,8 @@ int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a);
 int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a); // kernels_umma.cu (tcgen05 + TMA)
 bool conv2d_umma_supported(const ConvArgs& a);
 int launch_depthwise(snnb_context* ctx, const ConvArgs& a);
+bool depthwise_tma_supported(const ConvArgs& a);          // 3x3 stride 1/2: TMA-staged, register-tiled (kernels_umma.cu)
+int launch_depthwise_tma(snnb_context* ctx, const ConvArgs& a);
 int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int k, int stride, bool avg);
 int launch_add(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out, int act, float alpha);
 int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha);
