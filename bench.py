@@ -306,6 +306,24 @@ def main():
         roof = {"bound": "hbm", "achieved": dby / (dms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
+    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this command (profiles/README.md),
+    # scaled to the launches of one step like `algorithmic_per_step`: far BELOW the algorithmic bytes here because a layer's
+    # input is still L2-resident from its producer (126 MB L2) - the re-reads that matter are L2->SM, see l2_to_sm_read_MB.
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_%s_kernels.csv" % args.workload)
+    if dom == "Conv2D" and os.path.exists(prof):
+        import csv
+        rows = list(csv.reader(open(prof)))
+        col = {n.split("[")[0]: i for i, n in enumerate(rows[0])}
+        sel = [r for r in rows[1:] if r[col["kernel"]].startswith("conv_umma") and not r[col["grid"]].startswith("(1,")]
+        if sel:
+            mb = [float(r[col["dram_read_MB"]]) + float(r[col["dram_write_MB"]]) * (1e-3 if "Kbyte" in rows[0][col["dram_write_MB"]] else 1.0) for r in sel]
+            l2 = [float(r[col["l2_to_sm_read_MB"]]) for r in sel]
+            roof["traffic"] = sum(mb) / len(mb) * 1e6 * dn
+            roof["traffic_note"] = "mean DRAM read+write of %d profiled conv_umma launches x %d launches/step (%s); L2->SM reads %.0f MB/launch" % (
+                len(sel), dn, os.path.basename(prof), sum(l2) / len(l2))
+    if dfl:  # each fp32-equivalent product is executed as 3 bf16 MMAs (split-bf16): the tensor pipe's own view of the same layers
+        roof["tensor_executed"] = {"flops_per_step": 3.0 * dfl, "achieved_tflops": 3.0 * dfl / (dms * 1e-3) / 1e12,
+                                   "frac_of_bf16_peak": 3.0 * dfl / (dms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
     roof["kernel"] = "%s layers (%d launches/step, %.3f ms/step of %.3f ms eager total)" % (dom, dn, dms, float(lt.sum()))
     roof["peak_source"] = pk["source"] + ("; sustained bf16 dense (kernel timed inside a long step)" if roof["bound"] == "tensor" else "")
     roof["algorithmic_per_step"] = {"flops": dfl, "bytes": dby}
