@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <thread>
+
 #include "engine.h"
 
 using namespace snnb;
@@ -296,7 +298,9 @@ int YOLOLayer::decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perIm
         }
     }
     perImage.assign(N, SNNModelOutputBoxes());
-    for (int n = 0; n < N; ++n) {
+    // decode + NMS are per image and quadratic in the candidate count: one host thread per image (the reference is
+    // single-image; the arithmetic and the order of every image's list are unchanged)
+    auto decodeImage = [&](int n) {
         std::vector<Box> list;
         for (int yi = 0; yi < 2; ++yi) {
             const snnb_tensor* t = inputs[yi];
@@ -335,6 +339,17 @@ int YOLOLayer::decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perIm
             }
             perImage[n].rows.push_back({(float) list[i].cls, list[i].score, list[i].x, list[i].y, list[i].w, list[i].h});
         }
+    };
+    const int nthreads = std::max(1, std::min(N, (int) std::min(32u, std::max(1u, std::thread::hardware_concurrency()))));
+    if (nthreads == 1) {
+        for (int n = 0; n < N; ++n) decodeImage(n);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t)
+            pool.emplace_back([&, t]() {
+                for (int n = t; n < N; n += nthreads) decodeImage(n);
+            });
+        for (auto& th : pool) th.join();
     }
     return 0;
 }
