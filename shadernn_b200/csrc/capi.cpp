@@ -98,6 +98,7 @@ int snnb_context_destroy(snnb_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+    for (void* b : ctx->scratch_blocks) cudaFree(b);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

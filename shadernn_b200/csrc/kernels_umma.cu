@@ -59,6 +59,12 @@ struct UmmaParams {
     int act;
     float alpha;
     int has_res;
+    // split-K (layers with too few output tiles to fill the GPU, e.g. 7x7x512): work item = (tile, K range). Every item
+    // dumps its fp32 partial tile to `partials`, bumps the tile's arrival counter, and the LAST arriver sums all partials
+    // in split order (deterministic) and runs the normal epilogue.
+    int ksplit, kb_per_split;
+    float* partials; // [tile][split][128 rows][n_blk]
+    int* counters;   // [tile], zero between launches (the last arriver resets it)
     long long* trace; // profiling aid (env SNNB_UMMA_TRACE): CTA 0 writes clock64 stamps per role, [6][256]
     int ablate; // profiling aid (env SNNB_UMMA_ABLATE, results are WRONG when set): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs
 };
@@ -221,6 +227,10 @@ struct EpiArgs {
     uint32_t stg;       // staging smem (hi plane; lo plane at + UM_BLOCK_M * 128)
     uint32_t res_bar;   // mbarrier for the residual TMA load
     uint32_t tmem_empty;
+    // split-K finalisation: accumulator values come from `part_splits` fp32 partial tiles [128][n_blk] in global memory
+    // (summed in split order) instead of TMEM
+    const float* part_src;
+    int part_splits;
     long long* trace; // profiling aid: leader warp stamps the phases of its first slabs into [4][64 + 8 * slab_seq ...]
     int trace_seq;
 };
@@ -275,11 +285,35 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                 const int ci = NWARPS == 8 ? half + 2 * (k0 + kk) : k0 + kk;
                 if (ci < (w >> 4)) {
                     const int c = sl * 64 + ci * 16;
-                    tmem_ld16(taddr + (uint32_t) c, r[kk]);
-                    tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2[kk]);
+                    if (e.part_src) {
+                        // all loads of the chunk are issued before the first add (L2 latency once, not once per split);
+                        // summed in split order: the result does not depend on which CTA arrived last
+                        float4 t[4][4];
+#pragma unroll
+                        for (int sp = 0; sp < 4; ++sp) {
+                            // partial tile layout [chunk][j4][row][4 floats]: a warp's 32 rows are 512 contiguous bytes per access
+                            const float4* src = reinterpret_cast<const float4*>(e.part_src + (size_t) sp * UM_BLOCK_M * e.n_blk) + (size_t) (c >> 4) * 4 * UM_BLOCK_M + row;
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                t[sp][j4] = sp < e.part_splits ? __ldcg(src + j4 * UM_BLOCK_M) : make_float4(0.f, 0.f, 0.f, 0.f); // L2: written by other SMs
+                        }
+                        float a16[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            a16[4 * j4] = t[0][j4].x, a16[4 * j4 + 1] = t[0][j4].y, a16[4 * j4 + 2] = t[0][j4].z, a16[4 * j4 + 3] = t[0][j4].w;
+#pragma unroll
+                            for (int sp = 1; sp < 4; ++sp)
+                                if (sp < e.part_splits) a16[4 * j4] += t[sp][j4].x, a16[4 * j4 + 1] += t[sp][j4].y, a16[4 * j4 + 2] += t[sp][j4].z, a16[4 * j4 + 3] += t[sp][j4].w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[kk][j] = __float_as_uint(a16[j]), r2[kk][j] = 0u;
+                    } else {
+                        tmem_ld16(taddr + (uint32_t) c, r[kk]);
+                        tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2[kk]);
+                    }
                 }
             }
-            tmem_ld_wait();
+            if (!e.part_src) tmem_ld_wait();
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const int k = k0 + kk, ci = NWARPS == 8 ? half + 2 * k : k;
@@ -327,7 +361,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
         EPI_STAMP(1); // phase 1 done
         if (e.has_res && !res_ready) mbar_wait(e.res_bar, res_phase); // warps without a chunk in this slab still consume the phase
         if (e.has_res) res_phase ^= 1u;
-        if (sl == nslabs - 1) { // this warp has issued its last tcgen05.ld of the tile: the accumulator buffer may be reused
+        if (sl == nslabs - 1 && !e.part_src) { // this warp has issued its last tcgen05.ld of the tile: the accumulator buffer may be reused
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(e.tmem_empty);
@@ -373,6 +407,26 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
     }
 #undef EPI_STAMP
 }
+// Split-K: write this work item's raw fp32 accumulator tile (both column blocks added) to global memory, laid out
+// [16-column chunk][float4 index][row][4 floats] so that every warp access is 512 contiguous bytes.
+template <int NWARPS>
+__device__ __forceinline__ void epilogue_dump_partial(const EpiArgs& e, uint32_t taddr, float* dst, int row, int half, int lane) {
+    for (int c = (NWARPS == 8 ? half : 0) * 16; c < e.n_blk; c += (NWARPS == 8 ? 32 : 16)) {
+        uint32_t r[16], r2[16];
+        tmem_ld16(taddr + (uint32_t) c, r);
+        tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2);
+        tmem_ld_wait();
+        float4* d = reinterpret_cast<float4*>(dst) + (size_t) (c >> 4) * 4 * UM_BLOCK_M + row; // [chunk][j4][row][4 floats]
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+            d[j4 * UM_BLOCK_M] = make_float4(__uint_as_float(r[4 * j4]) + __uint_as_float(r2[4 * j4]), __uint_as_float(r[4 * j4 + 1]) + __uint_as_float(r2[4 * j4 + 1]),
+                                __uint_as_float(r[4 * j4 + 2]) + __uint_as_float(r2[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]) + __uint_as_float(r2[4 * j4 + 3]));
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(e.tmem_empty);
+}
+
 // After the last tile: the leader's bulk stores must have completed before the CTA (and its shared memory) goes away.
 __device__ __forceinline__ void epilogue_drain(bool leader) {
     if (leader) {
@@ -447,6 +501,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
     const int total_tiles = m_tiles * p.tiles_oc;
     const int num_kb      = p.ksize * p.ksize * p.cblocks;
+    const int total_work  = total_tiles * p.ksplit; // work item = (tile, K range); ksplit == 1: one item per tile
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -458,34 +513,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const bool skip_tma = (p.ablate & 2) != 0;
             const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u; // B_lo rows follow B_hi's: one [2 n_blk x 64] operand
             int tr = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+                const int tile = work % total_tiles, split = work / total_tiles;
                 const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
                 const int ix0 = bx * p.tw * p.stride - p.pad_x, iy0 = by * p.th * p.stride - p.pad_y, n0 = bn * p.tn;
                 const int oc0 = oc_idx * p.n_blk;
+                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 // Keep this loop lean: it runs once per K block and every stall here delays the whole pipeline (no divisions,
                 // no parameter loads: ncu r01 showed ~60 dependent scalar instructions/iteration bounding the kernel).
-                int wk = 0; // K coordinate into the packed weights = tap * ICp + cb * 64
-                for (int ky = 0; ky < ks; ++ky) {
-                    for (int kx = 0; kx < ks; ++kx, wk += icp) {
-                        for (int cb = 0; cb < cbs; ++cb) {
-                            mbar_wait(empty_bar(stage), phase ^ 1u);
-                            UM_TRACE(0, tr);
-                            ++tr;
-                            if (elect_one()) {
-                                const uint32_t sA = smem_base + stage * UM_STAGE_BYTES, fb = full_bar(stage);
-                                if (skip_tma) {
-                                    mbar_arrive(fb);
-                                } else {
-                                    mbar_expect_tx(fb, tx_bytes);
-                                    tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
-                                    tma_load_4d(sA + UM_A_BYTES, &tmA_lo, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
-                                    tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, fb, wk + cb * UM_BLOCK_K, oc0);
-                                    tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
-                                }
-                            }
-                            if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+                // K block kb = (ky * ks + kx) * cbs + cb; the counters are decoded once per work item and then stepped.
+                int cb = kb0 % cbs, tap0 = kb0 / cbs;
+                int kx = tap0 % ks, ky = tap0 / ks;
+                int wk = tap0 * icp; // K coordinate into the packed weights = tap * ICp + cb * 64
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    UM_TRACE(0, tr);
+                    ++tr;
+                    if (elect_one()) {
+                        const uint32_t sA = smem_base + stage * UM_STAGE_BYTES, fb = full_bar(stage);
+                        if (skip_tma) {
+                            mbar_arrive(fb);
+                        } else {
+                            mbar_expect_tx(fb, tx_bytes);
+                            tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                            tma_load_4d(sA + UM_A_BYTES, &tmA_lo, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                            tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, fb, wk + cb * UM_BLOCK_K, oc0);
+                            tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
                         }
+                    }
+                    if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+                    if (++cb == cbs) {
+                        cb = 0, wk += icp;
+                        if (++kx == ks) kx = 0, ++ky;
                     }
                 }
             }
@@ -509,13 +569,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             int it = 0, tr = 0;
             bool ready = false; // full_bar(stage) already observed complete by the look-ahead
             const bool no_mma = (p.ablate & 4) != 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_ACC_COLS);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = (work / total_tiles) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (!ready) mbar_wait(full_bar(stage), phase); // TMA bytes have landed
                     tc_fence_after();
                     UM_TRACE(1, tr);
@@ -524,7 +585,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     // UMMA_K = 16 bf16 = 32 bytes: K step j advances the start address by 2 (x16 B)
                     if (!no_mma) {
 #pragma unroll
-                        for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (kb > 0 || j > 0) ? 1u : 0u);
+                        for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (kb > kb0 || j > 0) ? 1u : 0u);
                         umma_bf16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
                         umma_bf16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
                     }
@@ -538,7 +599,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         umma_bf16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
                     }
                     umma_commit(empty_bar(cur));                           // smem slot free once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
+                    if (kb == kb1 - 1) umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
                     UM_TRACE(2, tr);
                     ++tr;
                 }
@@ -555,14 +616,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         e.r_hi64 = &tmR_hi64, e.r_lo64 = &tmR_lo64, e.r_hiT = &tmR_hiT, e.r_loT = &tmR_loT;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = p.has_res, e.rows_box = p.rows_used, e.alpha = p.alpha;
         e.stg = stg, e.res_bar = res_bar;
+        e.part_src = nullptr, e.part_splits = 0;
+        const uint32_t last_flag = bar_base + 8u * (2 * UM_STAGES + 6); // split-K: "this CTA arrived last" broadcast slot
         uint32_t res_phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+            const int tile = work % total_tiles, split = work / total_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
             const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
-            if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, warp == 2);
+            if (p.has_res && p.ksplit == 1) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, warp == 2);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             if (warp == 2) UM_TRACE(3, it);
@@ -575,7 +639,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (lane == 0) mbar_arrive(e.tmem_empty);
                 continue;
             }
+            if (p.ksplit > 1) {
+                float* tile_parts = p.partials + (size_t) tile * p.ksplit * (UM_BLOCK_M * p.n_blk);
+                epilogue_dump_partial<UM_EPI_WARPS>(e, taddr, tile_parts + (size_t) split * (UM_BLOCK_M * p.n_blk), row, half, lane);
+                __threadfence(); // partial tile visible device-wide before the arrival is counted
+                named_bar_sync(1, UM_EPI_WARPS * 32);
+                if (warp == 2 && lane == 0) {
+                    const int old  = atomicAdd(p.counters + tile, 1);
+                    const int last = old == p.ksplit - 1;
+                    if (last) p.counters[tile] = 0; // every split has arrived: leave the counter ready for the next launch
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(last_flag), "r"(last) : "memory");
+                }
+                named_bar_sync(1, UM_EPI_WARPS * 32);
+                int last;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(last) : "r"(last_flag) : "memory");
+                if (!last) continue;
+                __threadfence();
+                e.part_src = tile_parts, e.part_splits = p.ksplit;
+                if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, warp == 2);
+            }
             epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, warp == 2, lane, res_phase);
+            e.part_src = nullptr;
             if (warp == 2) UM_TRACE(4, it);
         }
         epilogue_drain(warp == 2);
@@ -789,6 +873,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         e.r_hi64 = e.r_lo64 = e.r_hiT = e.r_loT = &tmO_hi;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = 0, e.rows_box = UM_BLOCK_M, e.alpha = p.alpha;
         e.stg = stg, e.res_bar = 0;
+        e.part_src = nullptr, e.part_splits = 0;
         uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -922,24 +1007,57 @@ static TilePlan plan_tiles(int N, int OH, int OW, int stride) {
     return best;
 }
 
-// Output-channel tile width. The kernel is fed from L2, so the cost of one tile is ~ its K blocks x (A bytes + B bytes);
-// the layer takes waves x that. A narrower n_blk re-reads A for more oc tiles but fills more SMs when a layer has few
-// pixel tiles (7x7 and 14x14 maps): pick the width (multiple of 16, <= 128) that minimises waves x bytes per tile.
-static int plan_n_blk(int OC, int m_tiles, int rows_used, int sm_count, int& tiles_oc) {
-    int best_blk = 0, best_tiles = 0;
+// Output-channel tile width and K split. Measured (profiles/r01_umma_timeline_trace.txt): a K block costs
+// max(bytes loaded / ~72 B per clk of L2->SM ingest, MMA issue ~310 clk at n_blk <= 64 / ~420 clk above) and a work item
+// another ~7 k clk of ramp-up + last epilogue. A layer takes rounds x that, rounds = ceil(work items / SMs). A narrower
+// n_blk re-reads A for more oc tiles but fills more SMs; splitting K (work item = tile x K range, fp32 partials reduced by
+// the last arriver, +~9 k clk) fills the GPU when a layer has few tiles and a long K (7x7x512: 128 tiles x 72 K blocks).
+struct OcPlan {
+    int n_blk = 0, tiles_oc = 0, ksplit = 1, kb_per_split = 0;
+};
+static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int num_kb, int sm_count) {
+    OcPlan best;
     double best_cost = 1e300;
+    static const int no_split = getenv("SNNB_NO_SPLITK") != nullptr;
     const int t_min = (OC + UM_MAX_N - 1) / UM_MAX_N, t_max = (OC + 15) / 16;
     for (int t = t_min; t <= t_max; ++t) {
         const int blk = std::min(UM_MAX_N, round_up((OC + t - 1) / t, 16));
         if (blk * t < OC) continue;
-        const long long tiles = (long long) m_tiles * t;
-        const long long waves = (tiles + sm_count - 1) / sm_count;
-        const double cost     = (double) waves * (2.0 * rows_used * 128 + 2.0 * blk * 128 + 4096.0 /* fixed per-K-block overhead */);
-        if (cost < best_cost - 1e-9) best_cost = cost, best_blk = blk, best_tiles = t;
+        // boxes narrower than 8 pixels (7x7 maps) move ~20 % fewer bytes per clock through the TMA unit (measured 59 vs 74-77 B/clk)
+        const double ingest  = tile_w < 8 ? 58.0 : 72.0;
+        const double kb_cost = std::max((2.0 * rows_used * 128 + 2.0 * blk * 128) / ingest, blk <= 64 ? 310.0 : 420.0) + 60.0;
+        for (int sp = 1; sp <= (no_split ? 1 : 4); ++sp) {
+            if (sp > 1 && (num_kb < 8 * sp)) break; // not worth a reduction for short K
+            const int kbps          = (num_kb + sp - 1) / sp;
+            if ((sp - 1) * kbps >= num_kb) continue; // an empty split
+            const long long items = (long long) m_tiles * t * sp;
+            const long long rounds = (items + sm_count - 1) / sm_count;
+            const double cost      = (double) rounds * (kbps * kb_cost + 7000.0 + (sp > 1 ? 9000.0 : 0.0));
+            if (cost < best_cost * (sp > 1 ? 0.93 : 1.0) - 1e-9) // split only for a clear win
+                best_cost = cost, best.n_blk = blk, best.tiles_oc = t, best.ksplit = sp, best.kb_per_split = kbps;
+        }
         if (blk <= 16) break;
     }
-    tiles_oc = best_tiles;
-    return best_blk;
+    return best;
+}
+
+// fp32 partial tiles + arrival counters of split-K launches. Grow-only, old blocks stay alive until the context dies:
+// captured CUDA graphs keep the pointers they were recorded with.
+static int ensure_splitk_scratch(snnb_context* ctx, size_t partial_bytes, size_t n_counters) {
+    if (partial_bytes > ctx->splitk_bytes) {
+        void* pnew = nullptr;
+        SNNB_CUDA_OK(cudaMalloc(&pnew, partial_bytes));
+        ctx->scratch_blocks.push_back(pnew);
+        ctx->splitk_partials = static_cast<float*>(pnew), ctx->splitk_bytes = partial_bytes;
+    }
+    if (n_counters > ctx->splitk_counter_n) {
+        void* pnew = nullptr;
+        SNNB_CUDA_OK(cudaMalloc(&pnew, n_counters * sizeof(int)));
+        SNNB_CUDA_OK(cudaMemset(pnew, 0, n_counters * sizeof(int)));
+        ctx->scratch_blocks.push_back(pnew);
+        ctx->splitk_counters = static_cast<int*>(pnew), ctx->splitk_counter_n = n_counters;
+    }
+    return 0;
 }
 
 static bool rowwin_supported(const ConvArgs& a) {
@@ -1048,9 +1166,22 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     SNNB_REQUIRE(tp.tw > 0, "launch_conv2d_umma: no tile plan");
     p.tw = tp.tw, p.th = tp.th, p.tn = tp.tn, p.rows_used = tp.tw * tp.th * tp.tn;
     p.tiles_x = tp.tiles_x, p.tiles_y = tp.tiles_y, p.tiles_n = tp.tiles_n;
-    p.n_blk   = plan_n_blk(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, ctx->sm_count, p.tiles_oc);
     p.ksize = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y;
     p.cblocks = (in->c + UM_BLOCK_K - 1) / UM_BLOCK_K;
+    const OcPlan op = plan_oc_ksplit(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, tp.tw, a.k * a.k * p.cblocks, ctx->sm_count);
+    SNNB_REQUIRE(op.n_blk > 0, "launch_conv2d_umma: no output-channel plan");
+    p.n_blk = op.n_blk, p.tiles_oc = op.tiles_oc, p.ksplit = op.ksplit, p.kb_per_split = op.kb_per_split;
+    p.partials = nullptr, p.counters = nullptr;
+    if (p.ksplit > 1) {
+        const size_t tiles = (size_t) tp.tiles_x * tp.tiles_y * tp.tiles_n * p.tiles_oc;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        SNNB_CUDA_OK(cudaStreamIsCapturing(ctx->stream, &cap));
+        const size_t need = tiles * p.ksplit * UM_BLOCK_M * p.n_blk * sizeof(float);
+        SNNB_REQUIRE(cap == cudaStreamCaptureStatusNone || (need <= ctx->splitk_bytes && tiles <= ctx->splitk_counter_n),
+                     "launch_conv2d_umma: split-K scratch must be allocated by an eager pass before graph capture");
+        if (ensure_splitk_scratch(ctx, need, tiles)) return 1;
+        p.partials = ctx->splitk_partials, p.counters = ctx->splitk_counters;
+    }
     p.ICp     = round_up(in->c, 8);
     p.act = a.act, p.alpha = a.alpha;
     static const int ablate = getenv("SNNB_UMMA_ABLATE") ? atoi(getenv("SNNB_UMMA_ABLATE")) : 0;
@@ -1098,15 +1229,15 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         g_attr_set = true;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
-    const int grid        = std::min(total_tiles, ctx->sm_count);
+    const int grid        = std::min(total_tiles * p.ksplit, ctx->sm_count);
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
     const cudaError_t le = launch_k_pdl(conv_umma_kernel, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1],
                                     tmR64[0], tmR64[1], tmRT[0], tmRT[1], p);
     if (p.trace) {
         char hdr[256];
-        snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d", a.k, a.stride, in->c, out->c, out->n, out->h, out->w, p.n_blk,
-                 total_tiles, grid, p.ksize * p.ksize * p.cblocks);
+        snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d ksplit %d", a.k, a.stride, in->c, out->c, out->n, out->h, out->w,
+                 p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, p.ksplit);
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

@@ -130,6 +130,12 @@ struct snnb_context {
     float* stage_host   = nullptr; // pinned
     size_t stage_host_bytes = 0;
     void* tmap_encode_fn = nullptr; // cuTensorMapEncodeTiled, resolved lazily
+    // split-K scratch of the tensor-core convolution (kernels_umma.cu); blocks are freed with the context
+    float* splitk_partials = nullptr;
+    size_t splitk_bytes    = 0;
+    int* splitk_counters   = nullptr;
+    size_t splitk_counter_n = 0;
+    std::vector<void*> scratch_blocks;
 };
 
 struct snnb_timer {

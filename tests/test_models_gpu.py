@@ -144,7 +144,9 @@ def test_fused_graph_equals_unfused_and_graph_replay(ctx, model_dir, name, hw, k
 
 def test_batch_consistency_at_baseline_size(ctx, model_dir):
     # size-independent property at BASELINE.json's full ResNet-18 config (224x224x3, batch 32): every image's logits
-    # equal what the same image yields in a batch of 1 — bit-exact, because no kernel reduces across images.
+    # equal what the same image yields in a batch of 1. No kernel reduces across images; the only difference allowed is
+    # fp32 association in layers whose K loop is split differently at the two batch sizes (split-K on the 7x7 maps),
+    # orders of magnitude below the 1e-3 parity bar. The class index must be identical.
     path, _ = modelzoo.build("resnet18", model_dir, input_hw=(224, 224))
     x = modelzoo.synthetic_input("resnet18", 32, (224, 224))
     big = core.MixedInferenceCore(ctx, path, batch=32, fuse=True, use_cuda_graph=True)
@@ -152,7 +154,8 @@ def test_batch_consistency_at_baseline_size(ctx, model_dir):
     one = core.MixedInferenceCore(ctx, path, batch=1, fuse=True)
     for i in (0, 13, 31):
         o1, c1 = one.run(x[i:i + 1])
-        assert np.array_equal(o1[0], out[i]) and c1[0] == cls[i]
+        assert c1[0] == cls[i]
+        assert float(np.abs(o1[0] - out[i]).max()) <= 2e-5 * max(1.0, float(np.abs(out[i]).max()))
     assert np.all((cls >= 1) & (cls <= 10))
 
 

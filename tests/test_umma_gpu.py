@@ -95,3 +95,17 @@ def test_many_tiles_persistent_loop(ctx):
 @pytest.mark.parametrize("k,ic,oc,h", [(3, 64, 128, 56), (1, 64, 128, 56), (3, 128, 256, 29), (3, 256, 512, 14), (1, 256, 512, 14), (5, 32, 32, 21)])
 def test_stride2_tma_traversal_stride(ctx, k, ic, oc, h):
     run_case(ctx, 2, h, h, ic, oc, k, s=2, padding="same" if k > 1 else "valid", act="relu")
+
+
+@pytest.mark.parametrize("n,h,w,ic,oc,k,residual,act", [
+    (32, 7, 7, 512, 512, 3, False, "relu"),   # ResNet-18 layer4 at bench size: 128 tiles x 72 K blocks -> split-K
+    (32, 7, 7, 512, 512, 3, True, "relu"),    # ... with the fused residual (Conv2D -> Add -> relu)
+    (8, 7, 7, 320, 96, 3, False, ""),         # uneven K ranges (45 K blocks), one oc tile
+    (2, 14, 14, 448, 64, 3, True, "relu6"),   # 63 K blocks, few tiles
+    (1, 13, 13, 1024, 512, 1, False, "leakyRelu"),  # long-K 1x1 (YOLO head): 16 K blocks
+])
+def test_split_k(ctx, n, h, w, ic, oc, k, residual, act):
+    # layers with too few output tiles for 148 SMs: K is split over several CTAs, fp32 partials are reduced by the last
+    # arriver in split order. Run twice: the second launch checks that the arrival counters were left at zero.
+    run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=ic + h)
+    run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=ic + h + 1)
