@@ -171,6 +171,12 @@ int snnb_model_run(snnb_model* m, const float* host_input_nhwc, float* host_outp
  * pinned for the copies to be asynchronous and must stay untouched until wait() returns. (The reference's run() is
  * strictly synchronous, core.cpp:97-245; this is additive.) */
 int snnb_model_submit(snnb_model* m, const float* host_input_nhwc, float* host_output, size_t out_capacity, int* classes_1based, int* ticket);
+/* submit() for 8-bit images: host_input is N*H*W*C bytes (NHWC, dense); the device computes (x - mean4[c & 3]) * norm4[c & 3]
+ * while converting, i.e. ImageTexture::convertToRGBA32FAndNormalize(means, norms) (core/inc/snn/imageTexture.h:114; per-model
+ * constants in demo/common/modelInference.cpp:135-224, e.g. ResNet-18 mean 127.5 norm 1/127.5) without a host pass, and a
+ * quarter of the fp32 bytes cross PCIe. */
+int snnb_model_submit_u8(snnb_model* m, const uint8_t* host_input_nhwc_u8, const float* mean4, const float* norm4, float* host_output, size_t out_capacity,
+                         int* classes_1based, int* ticket);
 int snnb_model_wait(snnb_model* m, int ticket);
 /* Device-resident variant: inputs already uploaded with snnb_model_set_input(); forward only, asynchronous. */
 int snnb_model_set_input(snnb_model* m, int idx, const float* host_input_nhwc);

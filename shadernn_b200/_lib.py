@@ -95,6 +95,7 @@ SIGNATURES = {
     "snnb_model_output_dims": (C.c_int, [vp, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]),
     "snnb_model_run": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "snnb_model_submit": (C.c_int, [vp, vp, vp, C.c_size_t, vp, c_int_p]),
+    "snnb_model_submit_u8": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, vp, c_int_p]),
     "snnb_model_wait": (C.c_int, [vp, C.c_int]),
     "snnb_model_set_input": (C.c_int, [vp, C.c_int, vp]),
     "snnb_model_forward": (C.c_int, [vp]),

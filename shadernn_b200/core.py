@@ -364,6 +364,24 @@ class MixedInferenceCore:
         check(lib().snnb_model_submit(self.h, in_ptr, out_ptr, out_floats, classes_ptr, C.byref(t)), "snnb_model_submit")
         return t.value
 
+    def submit_u8_raw(self, in_ptr, mean4, norm4, out_ptr, out_floats, classes_ptr=None):
+        """snnb_model_submit_u8: 8-bit NHWC images, normalised on the device as (x - mean[c & 3]) * norm[c & 3]."""
+        t = C.c_int()
+        m = (C.c_float * 4)(*[float(v) for v in mean4])
+        n = (C.c_float * 4)(*[float(v) for v in norm4])
+        check(lib().snnb_model_submit_u8(self.h, in_ptr, m, n, out_ptr, out_floats, classes_ptr, C.byref(t)), "snnb_model_submit_u8")
+        return t.value
+
+    def run_u8(self, images_u8, mean4, norm4, want_classes=True):
+        """Convenience wrapper: one batch of uint8 NHWC images through submit_u8 / wait (numpy in, numpy out)."""
+        images_u8 = np.ascontiguousarray(images_u8, dtype=np.uint8)
+        assert images_u8.shape == self.input_shape(0), (images_u8.shape, self.input_shape(0))
+        out = np.empty(self.output_shape(0), np.float32)
+        classes = (C.c_int * self.batch)() if want_classes else None
+        t = self.submit_u8_raw(images_u8.ctypes.data, mean4, norm4, out.ctypes.data, out.size, classes)
+        self.wait(t)
+        return out, (np.array(list(classes), dtype=np.int32) if want_classes else None)
+
     def wait(self, ticket):
         check(lib().snnb_model_wait(self.h, int(ticket)), "snnb_model_wait")
 

@@ -396,6 +396,14 @@ int MixedInferenceCore::ensureStreaming() {
 }
 
 int MixedInferenceCore::submit(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket) {
+    return submitImpl(hostInput, false, nullptr, nullptr, hostOutput, capacityFloats, classes1, ticket);
+}
+int MixedInferenceCore::submitU8(const uint8_t* hostInput, const float mean[4], const float norm[4], float* hostOutput, size_t capacityFloats, int* classes1, int* ticket) {
+    SNNB_REQUIRE(mean && norm, "submitU8: null mean / norm");
+    return submitImpl(hostInput, true, mean, norm, hostOutput, capacityFloats, classes1, ticket);
+}
+int MixedInferenceCore::submitImpl(const void* hostInput, bool u8, const float* mean, const float* norm, float* hostOutput, size_t capacityFloats, int* classes1,
+                                   int* ticket) {
     SNNB_REQUIRE(hostInput && ticket, "submit: null argument");
     SNNB_REQUIRE(!yolo, "submit: detection models decode on the host; use run()");
     if (ensureStreaming()) return 1;
@@ -404,7 +412,7 @@ int MixedInferenceCore::submit(const float* hostInput, float* hostOutput, size_t
     int outIdx = 0;
     snnb_tensor* in  = inputLayers[0]->output;
     snnb_tensor* out = outputLayers[outIdx]->output;
-    const size_t inBytes = in->pixels() * in->c * sizeof(float), outFloats = out->pixels() * out->c;
+    const size_t inBytes = in->pixels() * in->c * (u8 ? sizeof(uint8_t) : sizeof(float)), outFloats = out->pixels() * out->c;
     SNNB_REQUIRE(!hostOutput || capacityFloats >= outFloats, "submit: output buffer too small (%zu < %zu floats)", capacityFloats, outFloats);
     // copy stream: wait until the split kernel of the submission that last used this slot has consumed the staging
     if (sl.everUsed) SNNB_CUDA_OK(cudaStreamWaitEvent(copyStream, sl.stageFree, 0));
@@ -412,7 +420,7 @@ int MixedInferenceCore::submit(const float* hostInput, float* hostOutput, size_t
     SNNB_CUDA_OK(cudaEventRecord(sl.h2dDone, copyStream));
     // compute stream
     SNNB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, sl.h2dDone, 0));
-    if (launch_split_f32(ctx, sl.stageIn, in)) return 1;
+    if (u8 ? launch_split_u8(ctx, reinterpret_cast<const uint8_t*>(sl.stageIn), in, mean, norm) : launch_split_f32(ctx, sl.stageIn, in)) return 1;
     SNNB_CUDA_OK(cudaEventRecord(sl.stageFree, ctx->stream));
     if (forward()) return 1;
     if (hostOutput) {

@@ -311,6 +311,9 @@ public:
     int run(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1);
     // streaming: double-buffered submit/wait (H2D of batch i+1 overlaps compute of batch i)
     int submit(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
+    // same with a u8 NHWC image batch, normalised on the device as (x - mean[c]) * norm[c] (imageTexture.h:114)
+    int submitU8(const uint8_t* hostInput, const float mean[4], const float norm[4], float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
+    int submitImpl(const void* hostInput, bool u8, const float* mean, const float* norm, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
     int wait(int ticket);
     int layerOutput(int layerId, float* host, size_t capacityFloats);
     int timeLayers(std::vector<float>& ms);

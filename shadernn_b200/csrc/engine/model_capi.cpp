@@ -102,6 +102,12 @@ int snnb_model_submit(snnb_model* m, const float* host_input, float* host_output
     SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->submit(host_input, host_output, out_capacity, classes, ticket);
 }
+int snnb_model_submit_u8(snnb_model* m, const uint8_t* host_input_u8, const float* mean4, const float* norm4, float* host_output, size_t out_capacity, int* classes,
+                         int* ticket) {
+    SNNB_REQUIRE(m, "snnb_model_submit_u8: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
+    return m->core->submitU8(host_input_u8, mean4, norm4, host_output, out_capacity, classes, ticket);
+}
 int snnb_model_wait(snnb_model* m, int ticket) {
     SNNB_REQUIRE(m, "snnb_model_wait: null model");
     return m->core->wait(ticket);

@@ -909,6 +909,24 @@ __global__ void split_kernel(const float* __restrict__ src, TV t) {
     for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? __ldg(src + px * t.C + c + j) : 0.0f;
     store8(t.hi, t.lo, gid * 8, v);
 }
+// u8 image (dense pitch C) -> (x - mean[c]) * norm[c] -> split-bf16: the reference's convertToRGBA32FAndNormalize
+// (core/inc/snn/imageTexture.h:114) done on the device, so only a quarter of the fp32 bytes cross PCIe.
+struct U8Norm {
+    float mean[4], norm[4];
+};
+__global__ void split_u8_kernel(const uint8_t* __restrict__ src, TV t, U8Norm q) {
+    pdl_wait();
+    const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG    = t.Cp >> 3;
+    const size_t px = gid / CG;
+    const int c     = (int) (gid % CG) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? ((float) __ldg(src + px * t.C + c + j) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3] : 0.0f;
+    store8(t.hi, t.lo, gid * 8, v);
+}
 __global__ void merge_kernel(TV t, float* __restrict__ dst) {
     pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
@@ -925,6 +943,13 @@ __global__ void merge_kernel(TV t, float* __restrict__ dst) {
 }
 int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t) {
     launch_k(split_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc, view(t));
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_split_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, snnb_tensor* t, const float mean[4], const float norm[4]) {
+    U8Norm q;
+    for (int i = 0; i < 4; ++i) q.mean[i] = mean[i], q.norm[i] = norm[i];
+    launch_k(split_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc_u8, view(t), q);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -175,6 +175,7 @@ int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int p
 int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, float* scratch = nullptr);
 int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int r);
 int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t);       // fp32 NHWC (pitch C) -> hi/lo
+int launch_split_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, snnb_tensor* t, const float mean[4], const float norm[4]); // (u8 - mean[c&3]) * norm[c&3]
 int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc);       // hi/lo -> fp32 NHWC (pitch C)
 
 // ---- host-side weight folding/packing (pack.cpp) -----------------------------------------------------------

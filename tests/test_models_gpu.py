@@ -159,6 +159,25 @@ def test_batch_consistency_at_baseline_size(ctx, model_dir):
     assert np.all((cls >= 1) & (cls <= 10))
 
 
+def test_u8_input_normalised_on_device(ctx, model_dir):
+    # snnb_model_submit_u8 = ImageTexture::convertToRGBA32FAndNormalize on the device (imageTexture.h:114) + the fp32 path:
+    # identical logits to feeding (u8 - mean) * norm as fp32 (ResNet-18 constants of demo/common/modelInference.cpp:135)
+    path, _ = modelzoo.build("resnet18", model_dir, input_hw=(64, 64))
+    m = core.MixedInferenceCore(ctx, path, batch=3, input_hw=(64, 64), fuse=True, use_cuda_graph=True)
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (3, 64, 64, 3), dtype=np.uint8)
+    mean, norm = [127.5] * 4, [1.0 / 127.5] * 4
+    ref, cref = m.run((img.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5))
+    out, cls = m.run_u8(img, mean, norm)
+    assert np.array_equal(cls, cref)
+    assert float(np.abs(out - ref).max()) <= 1e-6 * max(1.0, float(np.abs(ref).max()))
+    # per-channel constants (index c & 3)
+    mean2, norm2 = [10.0, 20.0, 30.0, 0.0], [0.01, 0.02, 0.03, 1.0]
+    ref2, _ = m.run((img.astype(np.float32) - np.array(mean2[:3], np.float32)) * np.array(norm2[:3], np.float32))
+    out2, _ = m.run_u8(img, mean2, norm2)
+    assert float(np.abs(out2 - ref2).max()) <= 1e-5 * max(1.0, float(np.abs(ref2).max()))
+
+
 def test_model_error_paths(ctx, tmp_path):
     from shadernn_b200._lib import SnnbError
     with pytest.raises(SnnbError):
