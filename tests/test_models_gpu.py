@@ -224,3 +224,33 @@ def test_streaming_submit_wait_matches_synchronous_run(ctx, model_dir):
         m.submit_raw(ins[2].ctypes.data_as(C.c_void_p), outs[2].ctypes.data_as(C.c_void_p), outs[2].size, clss[2])
     m.wait(t0)
     m.wait(t1)
+
+
+@pytest.mark.parametrize("name", ["resnet18", "mobilenet_v2"])
+def test_torchvision_export_runs_like_torch(ctx, tmp_path, name):
+    # independent cross-check (SURVEY §8c "torch-CPU as a secondary check"): a torchvision module exported with
+    # shadernn_b200/convert.py and run by the CUDA engine gives torch's own logits for the same input, top-1 identical.
+    torch = pytest.importorskip("torch")
+    torchvision = pytest.importorskip("torchvision")
+    from shadernn_b200 import convert
+    torch.manual_seed(11)
+    model = getattr(torchvision.models, name)(weights=None, num_classes=37)
+    g = torch.Generator().manual_seed(12)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5, generator=g)
+            m.bias.data.uniform_(-0.1, 0.1, generator=g)
+            m.running_mean.uniform_(-0.1, 0.1, generator=g)
+            m.running_var.uniform_(0.5, 1.5, generator=g)
+    model.eval()
+    path = str(tmp_path / (name + ".json"))
+    convert.export(model, path, input_hw=(96, 96), split=True)
+    x = np.random.default_rng(4).uniform(-1, 1, (5, 96, 96, 3)).astype(np.float32)
+    with torch.no_grad():
+        want = model(torch.from_numpy(x).permute(0, 3, 1, 2).contiguous()).numpy()
+    m = core.MixedInferenceCore(ctx, path, batch=5, fuse=True, use_cuda_graph=True)
+    out, cls = m.run(x)
+    got = out.reshape(5, -1)
+    scale = float(np.abs(want).max())
+    assert float(np.abs(got - want).max()) <= EPS * scale, (float(np.abs(got - want).max()), scale)
+    assert np.array_equal(cls - 1, want.argmax(1))
