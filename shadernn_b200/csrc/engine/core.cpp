@@ -178,6 +178,9 @@ bool MixedInferenceCore::init(std::string& err) {
             int ph = 0, pw = 0;
             snnb_weights probe_w;
             probe_w.w_hi = probe_w.w_lo = reinterpret_cast<__nv_bfloat16*>(1);
+            // ... and the row-window operand a pre-padded small-channel stem will be packed with (stride, pad 0; packWeights)
+            probe_w.w_row_hi = probe_w.w_row_lo = reinterpret_cast<__nv_bfloat16*>(1);
+            probe_w.row_stride = (int) cl->_desc.stride, probe_w.row_pad = 0;
             std::swap(cl->weights, probe_w);
             const bool prepad = cl->wantsPrepad(L->inputs[0], L->output, options.convAlgo, ph, pw);
             std::swap(cl->weights, probe_w);

@@ -213,7 +213,7 @@ public:
     void packWeights(snnb::PackedHost& p) override;
     int run(snnb_context* ctx, const ExecOptions& opt) override;
     void setScratch() { _scratchBytes = 0; }
-    void computeScratch(int n) { _scratchBytes = (size_t) n * snnb::round_up((int) numOutputPlanes, 8) * 2 * sizeof(float); }
+    void computeScratch(int n) { _scratchBytes = snnb::instnorm_scratch_floats(n, snnb::round_up((int) numOutputPlanes, 8)) * sizeof(float); }
 };
 class ActivationLayer : public GenericModelLayer { // activation.h:27-48 (creatable, not registered in the reference)
 public:

@@ -75,7 +75,9 @@ void Conv2DLayer::packWeights(PackedHost& p) {
         uint32_t offs[4];
         _desc.padding.offsets((int) _desc.kernelSize, true, offs);
         const int mode = padModeId(_desc.padding.mode);
+        // reflect / replicate convolutions run on a pre-padded copy of the input with pad 0 (wantsPrepad)
         if (mode == SNNB_PAD_NONE || mode == SNNB_PAD_CONSTANT) pack_rowwin_host(p, (int) _desc.stride, _desc.kernelSize == 1 ? 0 : (int) offs[0]);
+        else pack_rowwin_host(p, (int) _desc.stride, 0);
     }
     std::vector<float>().swap(_desc.weights); // host copy no longer needed
 }

@@ -8,6 +8,7 @@
 //
 // Semantics follow the reference's Vulkan compute shaders (cited per kernel; paths relative to the reference repo
 // core/data/assets/shaders/).
+#include <algorithm>
 #include <cstdlib>
 
 #include "snnb_internal.h"
@@ -779,60 +780,60 @@ int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int p
 }
 
 // InstanceNorm (+act) (vk_instancenorm.comp:53-175): per (n, c) mean and biased variance over H*W, eps 1e-5.
-// Pass 1: one CTA per (n, 8-channel group): two-pass mean / variance in fp32 with a fixed reduction tree
-// (deterministic), stats -> global. Pass 2: elementwise normalise + act.
-__global__ void __launch_bounds__(256) instnorm_stats_kernel(TV in, float* __restrict__ stats) {
+// Pass 1 (instnorm_partial_kernel): grid (n x 8-channel group, spatial chunk) so that even an 8-image batch with 32 channels
+// fills the GPU (the first version ran one CTA per (n, group): 32 CTAs, 500 GB/s). Each CTA reduces sum(x - K) and
+// sum((x - K)^2) of its pixel range with K = the image's first pixel (shifted data: no catastrophic cancellation, one read of
+// the input instead of two) through a fixed-shape tree. Pass 2 (instnorm_finalize_kernel): one thread per (n, c) adds the
+// chunk partials in chunk order (deterministic) -> (mean, rstd). Pass 3: elementwise normalise + act.
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(TV in, float* __restrict__ partial, int chunks, int chunk_px) {
     pdl_wait();
-    __shared__ float red[8][8]; // [warp][channel]
-    __shared__ float meanv[8];
+    __shared__ float red[8][16]; // [warp][sum(x-K) x8 | sum((x-K)^2) x8]
     const int CG = in.Cp >> 3;
-    const int n = blockIdx.x / CG, c = (blockIdx.x % CG) * 8;
+    const int n = blockIdx.x / CG, cg = blockIdx.x % CG, c = cg * 8;
     const int HW   = in.H * in.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc[8];
+    const int px0 = blockIdx.y * chunk_px, px1 = min(HW, px0 + chunk_px);
+    float K[8];
+    load8(in.hi, in.lo, (size_t) n * HW * in.Cp + c, K);
+    float a1[8], a2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    for (int px = threadIdx.x; px < HW; px += 256) {
+    for (int j = 0; j < 8; ++j) a1[j] = 0.0f, a2[j] = 0.0f;
+    for (int px = px0 + threadIdx.x; px < px1; px += 256) {
         float v[8];
         load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + c, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        for (int j = 0; j < 8; ++j) {
+            const float d = v[j] - K[j];
+            a1[j] += d;
+            a2[j] = fmaf(d, d, a2[j]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-        if (lane == 0) red[warp][j] = acc[j];
+        for (int o = 16; o > 0; o >>= 1) a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o), a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], o);
+        if (lane == 0) red[warp][j] = a1[j], red[warp][8 + j] = a2[j];
     }
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < 16) {
         float s = 0.0f;
         for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        meanv[threadIdx.x] = s / (float) HW;
+        partial[(((size_t) n * CG + cg) * chunks + blockIdx.y) * 16 + threadIdx.x] = s;
     }
-    __syncthreads();
-    float mean[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mean[j] = meanv[j], acc[j] = 0.0f;
-    for (int px = threadIdx.x; px < HW; px += 256) {
-        float v[8];
-        load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + c, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += (v[j] - mean[j]) * (v[j] - mean[j]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-        if (lane == 0) red[warp][j] = acc[j];
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        float s = 0.0f;
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        const float var                                  = s / (float) HW;
-        stats[((size_t) n * in.Cp + c + threadIdx.x) * 2 + 0] = meanv[threadIdx.x];
-        stats[((size_t) n * in.Cp + c + threadIdx.x) * 2 + 1] = 1.0f / sqrtf(var + 0.00001f);
-    }
+}
+__global__ void __launch_bounds__(128) instnorm_finalize_kernel(TV in, const float* __restrict__ partial, float* __restrict__ stats, int chunks) {
+    pdl_wait();
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= in.N * in.Cp) return;
+    const int n = gid / in.Cp, c = gid % in.Cp, CG = in.Cp >> 3;
+    const float HW = (float) (in.H * in.W);
+    const float K  = load1(in.hi, in.lo, (size_t) n * in.H * in.W * in.Cp + c);
+    const float* p = partial + ((size_t) n * CG + (c >> 3)) * chunks * 16 + (c & 7);
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int k = 0; k < chunks; ++k) s1 += p[k * 16], s2 += p[k * 16 + 8];
+    const float m   = s1 / HW;
+    const float var = fmaxf(s2 / HW - m * m, 0.0f);
+    stats[(size_t) gid * 2 + 0] = K + m;
+    stats[(size_t) gid * 2 + 1] = 1.0f / sqrtf(var + 0.00001f);
 }
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(TV in, TV out, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, int act, float alpha) {
@@ -854,14 +855,22 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(TV in, TV out, cons
     store8(out.hi, out.lo, (size_t) gid * 8, v);
 }
 int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, float* scratch) {
-    // scratch: n*cp*2 floats of (mean, rstd); the engine passes a model-owned buffer (stable under CUDA graphs)
+    // scratch: instnorm_scratch_floats(n, cp) floats = (mean, rstd) per (n, c) + the chunk partials; the engine passes a
+    // model-owned buffer (stable under CUDA graphs)
     float* stats = scratch;
     if (!stats) {
-        const size_t stat_bytes = (size_t) in->n * in->cp * 2 * sizeof(float);
-        if (ensure_stage(ctx, stat_bytes)) return 1;
+        if (ensure_stage(ctx, instnorm_scratch_floats(in->n, in->cp) * sizeof(float))) return 1;
         stats = ctx->stage_dev;
     }
-    launch_k(instnorm_stats_kernel, dim3((unsigned) (in->n * (in->cp >> 3))), dim3(256), 0, ctx->stream, view(in), stats);
+    float* partial = stats + (size_t) in->n * in->cp * 2;
+    const int groups = in->n * (in->cp >> 3), HW = in->h * in->w;
+    int chunks = std::min(INSTNORM_MAX_CHUNKS, std::max(1, (4 * ctx->sm_count + groups - 1) / groups));
+    chunks     = std::max(1, std::min(chunks, (HW + 2047) / 2048)); // at least ~2 k pixels per CTA
+    const int chunk_px = (HW + chunks - 1) / chunks;
+    chunks             = (HW + chunk_px - 1) / chunk_px;
+    launch_k(instnorm_partial_kernel, dim3((unsigned) groups, (unsigned) chunks), dim3(256), 0, ctx->stream, view(in), partial, chunks, chunk_px);
+    SNNB_LAUNCH_CHECK(ctx);
+    launch_k(instnorm_finalize_kernel, dim3((unsigned) ((in->n * in->cp + 127) / 128)), dim3(128), 0, ctx->stream, view(in), (const float*) partial, stats, chunks);
     SNNB_LAUNCH_CHECK(ctx);
     launch_k(instnorm_apply_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), stats, w->gamma, w->beta, act, alpha);
     SNNB_LAUNCH_CHECK(ctx);

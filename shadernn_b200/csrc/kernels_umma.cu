@@ -697,16 +697,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // gathered 16-byte requests. The weight panel [kh][n_blk][64] (hi + lo, K columns in RowPlan order) is loaded once per
 // persistent CTA and stays resident. Tiles = up to 128 consecutive output pixels of one output row.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RW_STAGES        = 6;
+constexpr int RW_STAGES        = 5;
 constexpr int RW_EPI_WARPS     = 8;
 constexpr int RW_THREADS       = 64 + 32 * RW_EPI_WARPS;
-constexpr int RW_MAX_KH        = 8;
 constexpr int RW_MAX_N         = 64;
 constexpr int RW_BOXW          = 144;                          // 128 tile pixels + up to 8 of window overhang, padded
 constexpr int RW_ARR_BYTES     = RW_BOXW * 16;                 // one (plane, parity) pixel row segment
 constexpr int RW_STAGE_BYTES   = 4 * RW_ARR_BYTES;             // hi/lo x parity 0/1 = 9216 B
-constexpr int RW_B_PLANE_BYTES = RW_MAX_KH * RW_MAX_N * 128;   // [ky][n_blk rows x 128 B]
-constexpr int RW_SMEM_BYTES    = 2 * RW_B_PLANE_BYTES + RW_STAGES * RW_STAGE_BYTES + UM_STG_BYTES + 1024 + 256;
+constexpr int RW_B_BYTES       = 144 * 1024;                   // resident weight panels: [ky][panel][B_hi rows ; B_lo rows] x 128 B
+constexpr int RW_SMEM_BYTES    = RW_B_BYTES + RW_STAGES * RW_STAGE_BYTES + UM_STG_BYTES + 1024 + 256;
 
 struct RowWinParams {
     __nv_bfloat16* out_hi;
@@ -716,7 +715,7 @@ struct RowWinParams {
     int kh, stride, pad_y;
     int tiles_x;
     int parities, dmin[2];
-    int ksteps, ks_parity[4], ks_erel[4];
+    int ksteps, panels, ks_parity[8], ks_erel[8]; // panels = ceil(ksteps / 4) weight panels of 64 K columns per filter row
     int act;
     float alpha;
     long long* trace; // profiling aid, see UmmaParams
@@ -733,7 +732,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB = smem_base; // weight panel: per kernel row ky, [n_blk rows of B_hi ; n_blk rows of B_lo] x 128 B
-    const uint32_t stg      = smem_base + 2 * RW_B_PLANE_BYTES; // epilogue staging (1024-aligned)
+    const uint32_t stg      = smem_base + RW_B_BYTES; // epilogue staging (1024-aligned)
     const uint32_t sA0      = stg + UM_STG_BYTES;
     const uint32_t bar_base = sA0 + RW_STAGES * RW_STAGE_BYTES;
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
@@ -782,10 +781,11 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         {
             // weight panel: once per CTA
             if (elect_one()) {
-                mbar_expect_tx(b_bar, 2u * (uint32_t) p.kh * (uint32_t) p.n_blk * 128u);
-                for (int ky = 0; ky < p.kh; ++ky) {
-                    tma_load_2d(sB + (2 * ky) * p.n_blk * 128, &tmB_hi, b_bar, 0, ky * p.ocr);
-                    tma_load_2d(sB + (2 * ky + 1) * p.n_blk * 128, &tmB_lo, b_bar, 0, ky * p.ocr);
+                const int vrows = p.kh * p.panels; // (filter row, panel)
+                mbar_expect_tx(b_bar, 2u * (uint32_t) vrows * (uint32_t) p.n_blk * 128u);
+                for (int v = 0; v < vrows; ++v) {
+                    tma_load_2d(sB + (2 * v) * p.n_blk * 128, &tmB_hi, b_bar, 0, v * p.ocr);
+                    tma_load_2d(sB + (2 * v + 1) * p.n_blk * 128, &tmB_lo, b_bar, 0, v * p.ocr);
                 }
             }
             __syncwarp();
@@ -819,11 +819,12 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         const uint32_t idesc_cat = make_idesc(UM_BLOCK_M, 2 * p.n_blk), idesc = make_idesc(UM_BLOCK_M, p.n_blk); // see conv_umma_kernel
         if (elect_one()) { // one thread owns the issue loop (see conv_umma_kernel)
             // window descriptor (16-byte address field) offsets of the K steps, relative to the stage's hi plane
-            uint32_t koff[4];
+            uint32_t koff[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) koff[q] = q < p.ksteps ? (((uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u) >> 4) : 0u;
+            for (int q = 0; q < 8; ++q) koff[q] = q < p.ksteps ? (((uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u) >> 4) : 0u;
             const uint64_t wdesc0 = make_window_desc(sA0), bdesc0 = make_smem_desc(sB);
-            const uint32_t b_ky   = (uint32_t) (2 * p.n_blk * 128) >> 4; // one kernel row of [B_hi ; B_lo]
+            const uint32_t b_panel = (uint32_t) (2 * p.n_blk * 128) >> 4;  // one [B_hi ; B_lo] panel (64 K columns)
+            const uint32_t b_ky    = b_panel * (uint32_t) p.panels;         // one filter row
             const int last_q      = p.ksteps - 1;
             const uint32_t koff_last = ((uint32_t) p.ks_parity[last_q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[last_q] * 16u) >> 4;
             int stage = 0, it = 0, tr = 0;
@@ -842,18 +843,20 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     UM_TRACE(1, tr);
                     const uint64_t a0 = wdesc0 + (uint64_t) (uint32_t) (stage * (RW_STAGE_BYTES >> 4));
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 8; ++q) { // K step q lives in weight panel q / 4, columns 16 (q % 4) ..
                         if (q < last_q) {
-                            umma_bf16(d_tmem, a0 + koff[q], b_cat + 2u * q, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u);   // -> [hi.hi | hi.lo]
-                            umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff[q], b_cat + 2u * q, idesc, 1u);     // lo.hi onto the first block
+                            const uint64_t bq = b_cat + (uint64_t) ((q >> 2) * b_panel + 2u * (q & 3));
+                            umma_bf16(d_tmem, a0 + koff[q], bq, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u);           // -> [hi.hi | hi.lo]
+                            umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff[q], bq, idesc, 1u);             // lo.hi onto the first block
                         }
                     }
+                    const uint64_t b_last = b_cat + (uint64_t) ((last_q >> 2) * b_panel + 2u * (last_q & 3));
                     const int cur = stage;
                     phase ^= (stage == RW_STAGES - 1) ? 1u : 0u;
                     stage = stage == RW_STAGES - 1 ? 0 : stage + 1;
                     ready = mbar_test_wait(full_bar(stage), phase); // look-ahead, overlaps with the MMAs already queued
-                    umma_bf16(d_tmem, a0 + koff_last, b_cat + 2u * last_q, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
-                    umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff_last, b_cat + 2u * last_q, idesc, 1u);
+                    umma_bf16(d_tmem, a0 + koff_last, b_last, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
+                    umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff_last, b_last, idesc, 1u);
                     umma_commit(empty_bar(cur));
                     if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
                     UM_TRACE(2, tr);
@@ -1064,8 +1067,9 @@ static bool rowwin_supported(const ConvArgs& a) {
     // small-C stems: IC <= 8 (one 16-byte vector per pixel), stride 1 or 2, <= 4 K steps per filter row, weights packed
     // for exactly this (stride, pad_x), whole panel resident in smem
     RowPlan rp;
-    return a.in->cp == 8 && a.w && a.w->w_row_hi && a.w->w_row_lo && a.w->row_stride == a.stride && a.w->row_pad == a.pad_x && a.k <= RW_MAX_KH &&
-           a.out->c <= RW_MAX_N && a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW;
+    return a.in->cp == 8 && a.w && a.w->w_row_hi && a.w->w_row_lo && a.w->row_stride == a.stride && a.w->row_pad == a.pad_x &&
+           a.out->c <= RW_MAX_N && a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW &&
+           a.k * ((rp.ksteps + 3) / 4) * 2 * round_up(a.out->c, 16) * 128 <= RW_B_BYTES; // the whole weight panel set stays resident
 }
 
 bool conv2d_umma_supported(const ConvArgs& a) {
@@ -1093,8 +1097,8 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     p.kh = a.k, p.stride = a.stride, p.pad_y = a.pad_y;
     p.tiles_x  = (out->w + UM_BLOCK_M - 1) / UM_BLOCK_M;
     p.parities = rp.parities, p.dmin[0] = rp.dmin[0], p.dmin[1] = rp.dmin[1];
-    p.ksteps   = rp.ksteps;
-    for (int q = 0; q < 4; ++q) p.ks_parity[q] = q < rp.ksteps ? rp.ks_parity[q] : 0, p.ks_erel[q] = q < rp.ksteps ? rp.ks_erel[q] : 0;
+    p.ksteps   = rp.ksteps, p.panels = (rp.ksteps + 3) / 4;
+    for (int q = 0; q < 8; ++q) p.ks_parity[q] = q < rp.ksteps ? rp.ks_parity[q] : 0, p.ks_erel[q] = q < rp.ksteps ? rp.ks_erel[q] : 0;
     p.act = a.act, p.alpha = a.alpha;
 
     // A: per plane and column parity a 4-D view (8 ch | de-interleaved pixel index | row | image) of the NHWC plane
@@ -1113,7 +1117,7 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, rowwin) failed: %d", (int) r);
         }
     {
-        const cuuint64_t dims[2]    = {64, (cuuint64_t) a.k * a.w->ocr};
+        const cuuint64_t dims[2]    = {64, (cuuint64_t) a.k * p.panels * a.w->ocr}; // [ky][panel][OCr] rows of 64 K columns
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2]     = {64, (cuuint32_t) p.n_blk};
         const cuuint32_t estr[2]    = {1, 1};

@@ -84,8 +84,9 @@ void pack_rowwin_host(PackedHost& p, int stride, int pad_x) {
     if (p.kind != 1 || p.in_ch > 8 || p.out_ch > 64 || !make_row_plan(p.kernel, stride, pad_x, rp)) return;
     const int k = p.kernel, IC = p.in_ch, OC = p.out_ch;
     p.row_stride = stride, p.row_pad = pad_x;
-    p.w_row_hi.assign((size_t) k * p.ocr * 64, __float2bfloat16_rn(0.0f));
-    p.w_row_lo.assign((size_t) k * p.ocr * 64, __float2bfloat16_rn(0.0f));
+    const int panels = (rp.ksteps + 3) / 4; // 64 K columns (4 K steps) per panel: [ky][panel][OCr][64]
+    p.w_row_hi.assign((size_t) k * panels * p.ocr * 64, __float2bfloat16_rn(0.0f));
+    p.w_row_lo.assign((size_t) k * panels * p.ocr * 64, __float2bfloat16_rn(0.0f));
     for (int ky = 0; ky < k; ++ky)
         for (int o = 0; o < OC; ++o)
             for (int q = 0; q < rp.ksteps; ++q)
@@ -94,7 +95,7 @@ void pack_rowwin_host(PackedHost& p, int stride, int pad_x) {
                     if (j < 0) continue;
                     for (int c = 0; c < IC; ++c) {
                         const float wv        = p.w_f32[(size_t) ((ky * k + j) * IC + c) * p.ocw + o]; // BN already folded in
-                        const size_t idx      = ((size_t) ky * p.ocr + o) * 64 + q * 16 + h * 8 + c;
+                        const size_t idx      = (((size_t) ky * panels + q / 4) * p.ocr + o) * 64 + (q % 4) * 16 + h * 8 + c;
                         const __nv_bfloat16 hh = __float2bfloat16_rn(wv);
                         p.w_row_hi[idx]       = hh;
                         p.w_row_lo[idx]       = __float2bfloat16_rn(wv - __bfloat162float(hh));

@@ -172,6 +172,9 @@ int launch_flatten(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
 int launch_concat(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out);
 int launch_upsample(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, float scale, bool bilinear);
 int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int pad_x, int pad_y, int mode);
+// InstanceNorm scratch: (mean, rstd) per (n, c) followed by up to INSTNORM_MAX_CHUNKS x 16 partial sums per (n, 8-channel group)
+constexpr int INSTNORM_MAX_CHUNKS = 64;
+static inline size_t instnorm_scratch_floats(int n, int cp) { return (size_t) n * cp * 2 + (size_t) n * (cp >> 3) * INSTNORM_MAX_CHUNKS * 16; }
 int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, float* scratch = nullptr);
 int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int r);
 int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t);       // fp32 NHWC (pitch C) -> hi/lo
@@ -187,15 +190,15 @@ struct RowPlan {
     int dmin[2]  = {0, 0}; // pixel offset (in de-interleaved index) of the first tap of each parity, relative to the output index
     int ntaps[2] = {0, 0};
     int ksteps   = 0;
-    int ks_parity[4], ks_erel[4], ks_tap[4][2];
+    int ks_parity[8], ks_erel[8], ks_tap[8][2]; // up to 8 K steps = 2 weight panels of 64 K columns per filter row (9x9 taps)
     int span = 0; // pixels needed beyond the 128 of the tile
 };
 static inline bool make_row_plan(int k, int stride, int pad_x, RowPlan& rp) {
-    if (k < 1 || k > 8 || !(stride == 1 || stride == 2)) return false;
+    if (k < 1 || k > 9 || !(stride == 1 || stride == 2)) return false;
     rp = RowPlan();
     rp.parities = stride;
     for (int par = 0; par < stride; ++par) {
-        int js[8], t = 0;
+        int js[9], t = 0;
         for (int j = 0; j < k; ++j)
             if ((((j - pad_x) % stride) + stride) % stride == par) js[t++] = j;
         rp.ntaps[par] = t;
@@ -203,7 +206,7 @@ static inline bool make_row_plan(int k, int stride, int pad_x, RowPlan& rp) {
         const int a  = js[0] - pad_x;
         rp.dmin[par] = a >= 0 ? a / stride : -((-a + stride - 1) / stride);
         for (int q = 0; q < (t + 1) / 2; ++q) {
-            if (rp.ksteps >= 4) return false;
+            if (rp.ksteps >= 8) return false;
             rp.ks_parity[rp.ksteps] = par;
             rp.ks_erel[rp.ksteps]   = 2 * q;
             rp.ks_tap[rp.ksteps][0] = js[2 * q];

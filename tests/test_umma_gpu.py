@@ -82,6 +82,9 @@ def test_other_kernel_sizes_and_asymmetric_padding(ctx):
     (1, 40, 40, 1, 16, 5, 1, "same", "relu"),        # ESPCN first conv: 1 input channel
     (1, 33, 29, 4, 24, 3, 1, (1, 0, 1, 0), "tanh"),  # 4 channels, asymmetric padding, transcendental epilogue
     (3, 9, 9, 8, 40, 1, 1, "valid", ""),             # 8 channels 1x1, OC not a multiple of 16
+    (2, 40, 52, 3, 32, 9, 1, (4, 4, 4, 4), "relu"),  # style-transfer 9x9 stem: 5 K steps = two weight panels per filter row
+    (1, 37, 41, 3, 24, 9, 2, (4, 4, 4, 4), ""),      # 9x9 stride 2: both column parities, 5 K steps
+    (1, 30, 30, 2, 16, 8, 1, "same", "relu6"),       # even 8x8: exactly one full panel
 ])
 def test_small_channel_rowgemm(ctx, n, h, w, ic, oc, k, s, padding, act):
     run_case(ctx, n, h, w, ic, oc, k, s=s, padding=padding, act=act, seed=k + ic)
