@@ -138,6 +138,18 @@ int snnb_timer_stop(snnb_timer* t);
 int snnb_timer_elapsed_ms(snnb_timer* t, float* ms); /* synchronises on the stop event */
 int snnb_timer_destroy(snnb_timer* t);
 
+/* ---- launch capture for backend-level integration -------------------------------------------------------------
+ * A DeviceBackend built on the per-operator calls (depth B) records its stage loop once and replays it:
+ * everything launched on the context between capture_begin and capture_end becomes one CUDA graph (the counterpart of
+ * recording the reference's single command buffer, vulkanBackend.cpp:97-106). Run the same launches eagerly once before
+ * capturing: lazily created resources (tensor-map encoder, split-K scratch) must exist, because allocation is illegal
+ * while capturing. Tensors and weights referenced by the graph must outlive it. */
+typedef struct snnb_graph snnb_graph;
+int snnb_graph_capture_begin(snnb_context* ctx);
+int snnb_graph_capture_end(snnb_context* ctx, snnb_graph** out);
+int snnb_graph_launch(snnb_graph* g); /* asynchronous on the context's stream */
+int snnb_graph_destroy(snnb_graph* g);
+
 /* ---- whole-model engine: dp::loadFromJsonModel + generateInferenceGraph + MixedInferenceCore ------------------- */
 typedef struct {
     int batch;          /* images per run() on this GPU (the reference is fixed at 1, inferencegraph.h:58-64) */

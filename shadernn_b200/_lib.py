@@ -94,6 +94,10 @@ SIGNATURES = {
     "snnb_model_input_dims": (C.c_int, [vp, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]),
     "snnb_model_output_dims": (C.c_int, [vp, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]),
     "snnb_model_run": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "snnb_graph_capture_begin": (C.c_int, [vp]),
+    "snnb_graph_capture_end": (C.c_int, [vp, C.POINTER(C.c_void_p)]),
+    "snnb_graph_launch": (C.c_int, [vp]),
+    "snnb_graph_destroy": (C.c_int, [vp]),
     "snnb_model_submit": (C.c_int, [vp, vp, vp, C.c_size_t, vp, c_int_p]),
     "snnb_model_submit_u8": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, vp, c_int_p]),
     "snnb_model_wait": (C.c_int, [vp, C.c_int]),

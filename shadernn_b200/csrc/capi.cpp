@@ -396,4 +396,49 @@ int snnb_timer_destroy(snnb_timer* t) {
     return 0;
 }
 
+// ---- launch capture -----------------------------------------------------------------------------------------
+int snnb_graph_capture_begin(snnb_context* ctx) {
+    SNNB_REQUIRE(ctx, "snnb_graph_capture_begin: null context");
+    SNNB_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    SNNB_CUDA_OK(cudaStreamIsCapturing(ctx->stream, &st));
+    SNNB_REQUIRE(st == cudaStreamCaptureStatusNone, "snnb_graph_capture_begin: the context is already capturing");
+    SNNB_CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    return 0;
+}
+int snnb_graph_capture_end(snnb_context* ctx, snnb_graph** out) {
+    SNNB_REQUIRE(ctx && out, "snnb_graph_capture_end: null argument");
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        set_error("snnb_graph_capture_end: capture failed (%s); a launch inside the region reported an error or allocated memory", cudaGetErrorString(e));
+        return 1;
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&ex, g, 0);
+    if (e2 != cudaSuccess) {
+        cudaGraphDestroy(g);
+        set_error("snnb_graph_capture_end: cudaGraphInstantiate failed (%s)", cudaGetErrorString(e2));
+        return 1;
+    }
+    auto* h = new snnb_graph();
+    h->ctx = ctx, h->graph = g, h->exec = ex;
+    *out = h;
+    return 0;
+}
+int snnb_graph_launch(snnb_graph* g) {
+    SNNB_REQUIRE(g && g->exec, "snnb_graph_launch: null graph");
+    SNNB_CUDA_OK(cudaSetDevice(g->ctx->device));
+    SNNB_CUDA_OK(cudaGraphLaunch(g->exec, g->ctx->stream));
+    return 0;
+}
+int snnb_graph_destroy(snnb_graph* g) {
+    if (!g) return 0;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
+}
+
 } // extern "C"

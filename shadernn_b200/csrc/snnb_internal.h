@@ -138,6 +138,12 @@ struct snnb_context {
     std::vector<void*> scratch_blocks;
 };
 
+struct snnb_graph {
+    snnb_context* ctx     = nullptr;
+    cudaGraph_t graph     = nullptr;
+    cudaGraphExec_t exec  = nullptr;
+};
+
 struct snnb_timer {
     snnb_context* ctx = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;

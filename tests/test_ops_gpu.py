@@ -241,3 +241,47 @@ def test_error_paths(ctx):
     with pytest.raises(SnnbError):  # tcgen05 forced on a shape it cannot take
         core.conv2d(ctx, np.zeros((1, 4, 4, 3), np.float32), np.zeros((8, 3, 7, 7), np.float32), out_hw=(4, 4), pad_x=3, pad_y=3, pad_mode="reflect",
                     algo="tcgen05")
+
+
+def test_backend_level_launch_capture(ctx):
+    # INTEGRATION.md depth B: a DeviceBackend built on the per-operator calls records its stage loop once
+    # (snnb_graph_capture_begin / _end) and replays it. conv3x3(+relu) -> add(+relu) -> maxpool, replayed on new input.
+    import ctypes as C
+    from shadernn_b200._lib import lib, check
+    rng = np.random.default_rng(21)
+    n, h, w, ic, oc = 2, 28, 28, 64, 64
+    wt = (rng.standard_normal((oc, ic, 3, 3)) * np.sqrt(2.0 / (9 * ic))).astype(np.float32)
+    bias = rng.uniform(-0.1, 0.1, oc).astype(np.float32)
+    d = core.conv_desc(ic, oc, 3, 1, 1, 1, "constant", "relu", 0.0, "auto")
+    wh = C.c_void_p()
+    check(lib().snnb_weights_pack_conv2d(ctx.h, C.byref(d), wt.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p), None, None, None, None, C.byref(wh)))
+    wobj = core.Weights(wh)
+    tin, tmid, tsum, tout = (core.ImageTexture(ctx, n, h, w, c) for c in (ic, oc, oc, oc))
+    tpool = core.ImageTexture(ctx, n, 14, 14, oc)
+
+    def stage_loop():
+        check(lib().snnb_conv2d_launch(ctx.h, C.byref(d), wobj.h, tin.h, None, tmid.h))
+        check(lib().snnb_add_launch(ctx.h, core.ACT["relu"], 0.0, tmid.h, tin.h, tsum.h))
+        check(lib().snnb_maxpool_launch(ctx.h, 2, 2, tsum.h, tpool.h))
+
+    def expected(x):
+        y = oracle.conv2d(x, wt, bias=bias, stride=1, pad_x=1, pad_y=1, activation="relu", out_hw=(h, w))
+        return oracle.pool2d(oracle.add(y, x, activation="relu"), 2, 2, False, (14, 14))
+
+    x0 = rng.uniform(-1, 1, (n, h, w, ic)).astype(np.float32)
+    tin.upload(x0)
+    stage_loop()  # eager pass first: lazily created resources must exist before capture
+    ctx.sync()
+    check(lib().snnb_graph_capture_begin(ctx.h))
+    stage_loop()
+    g = C.c_void_p()
+    check(lib().snnb_graph_capture_end(ctx.h, C.byref(g)))
+    try:
+        for seed in (1, 2):
+            x = np.random.default_rng(seed).uniform(-1, 1, (n, h, w, ic)).astype(np.float32)
+            tin.upload(x)
+            check(lib().snnb_graph_launch(g))
+            got = tpool.download()
+            assert_close(got, expected(x))
+    finally:
+        lib().snnb_graph_destroy(g)
