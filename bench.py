@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames per step of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer roofline table to stderr")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch per GPU (the metric's config is the default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -202,6 +203,8 @@ def main():
     dev = "cuda:%d" % local_rank
 
     key, batch, desc = WORKLOADS[args.workload]
+    if args.batch > 0 and args.batch != batch:
+        batch, desc = args.batch, desc + " [batch overridden to %d]" % args.batch
     hw = modelzoo.MODELS[key][1]
     d = tempfile.mkdtemp(prefix="snnb_bench_r%d_" % rank)
     path, layers = modelzoo.build(key, d)
@@ -369,12 +372,18 @@ def main():
     tmin = sum(max(by / (pk["hbm_gbs"] * 1e9), fl / (pk["bf16_tflops_sustained"] * 1e12)) for (_, fl, by) in work)
     roof["graph_frac"] = tmin / (dev_ms / args.steps * 1e-3)
     if args.layers:
+        sys.stderr.write("# %s, batch %d per GPU; per-layer event pairs (eager pass, %d repetitions). roofline%% = max(bytes/HBM, flops/bf16) / t with the\n"
+                         "# algorithmic work of SURVEY 8d (fp32 bytes, 2*MAC flops); tensor_exec%% = 3 x flops / bf16 peak / t (each product is three bf16 MMAs)\n"
+                         % (desc, batch, reps))
+        sys.stderr.write("# %-3s %-22s %9s %9s %9s %9s %9s %6s %10s %12s\n" % ("id", "layer", "ms", "GFLOP", "MB", "TF/s", "GB/s", "bound", "roofline%", "tensor_exec%"))
         for i, ((t, fl, by), ms_l) in enumerate(zip(work, lt)):
             if ms_l <= 0:
                 continue
-            tm_l = max(by / (pk["hbm_gbs"] * 1e9), fl / (pk["bf16_tflops_sustained"] * 1e12))
-            sys.stderr.write("[%02d] %-18s %8.3f ms  %8.2f GFLOP %8.2f MB  %7.1f TF/s %7.0f GB/s  roofline %.1f%%\n" %
-                             (i, t, ms_l, fl / 1e9, by / 1e6, fl / ms_l / 1e9, by / ms_l / 1e6, 100 * tm_l / (ms_l * 1e-3)))
+            t_h, t_t = by / (pk["hbm_gbs"] * 1e9), fl / (pk["bf16_tflops_sustained"] * 1e12)
+            sys.stderr.write("[%02d] %-22s %9.3f %9.2f %9.2f %9.1f %9.0f %6s %9.1f%% %11.1f%%\n" %
+                             (i, t, ms_l, fl / 1e9, by / 1e6, fl / ms_l / 1e9, by / ms_l / 1e6, "tensor" if t_t > t_h else "hbm",
+                              100 * max(t_h, t_t) / (ms_l * 1e-3), 100 * 3 * t_t / (ms_l * 1e-3)))
+        sys.stderr.write("# total eager %.3f ms; CUDA-graph step %.3f ms\n" % (float(lt.sum()), dev_ms / args.steps))
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only) ----
     cpu = None
