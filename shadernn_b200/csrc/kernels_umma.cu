@@ -44,6 +44,7 @@ constexpr int UM_ACC_COLS    = 2 * UM_MAX_N; // one accumulator buffer: [A_hi.B_
 constexpr int UM_TMEM_COLS   = 2 * UM_ACC_COLS; // double-buffered: all 512 columns
 constexpr int UM_STG_BYTES   = 2 * UM_BLOCK_M * 128; // epilogue staging: one 64-channel slab, hi + lo planes (32 KB)
 constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int UM_SMEM_BYTES_SPLIT = (UM_STAGES - 1) * UM_STAGE_BYTES + 2 * UM_STG_BYTES + 1024 + 256; // two epilogue groups, one ring stage less
 
 struct UmmaParams {
     __nv_bfloat16* out_hi;
@@ -227,6 +228,7 @@ struct EpiArgs {
     uint32_t stg;       // staging smem (hi plane; lo plane at + UM_BLOCK_M * 128)
     uint32_t res_bar;   // mbarrier for the residual TMA load
     uint32_t tmem_empty;
+    int bar_id;         // named barrier of this epilogue group (1, or 1 + group when two groups work on alternate tiles)
     // split-K finalisation: accumulator values come from `part_splits` fp32 partial tiles [128][n_blk] in global memory
     // (summed in split order) instead of TMEM
     const float* part_src;
@@ -275,10 +277,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
         const int slab_oc    = oc0 + sl * 64;
         if (e.has_res && sl > 0) epilogue_residual_load(e, sl, oc0, c1, c2, c3, leader); // slab 0's was issued before the accumulator wait
         // ---- phase 1: TMEM -> registers -> bias (+ residual) -> activation -> packed split-bf16, nothing written yet ----
-        uint32_t oh[MAXC][8], ol[MAXC][8];
         bool res_ready = false;
 #pragma unroll
-        for (int k0 = 0; k0 < MAXC; k0 += 2) { // two chunks at a time: their four TMEM loads and bias loads are in flight together
+        for (int k0 = 0; k0 < MAXC; k0 += 2) { // two chunks at a time: their four TMEM loads are in flight together
+            uint32_t oh[2][8], ol[2][8];
             uint32_t r[2][16], r2[2][16];
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
@@ -354,46 +356,52 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                         for (int j = 0; j < 16; ++j) v[j] = (oc0 + c + j < e.OC) ? umma_act(v[j], e.act, e.alpha) : 0.0f; // out-of-line call
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) um_split2(v[2 * j], v[2 * j + 1], oh[k][j], ol[k][j]);
+                    for (int j = 0; j < 8; ++j) um_split2(v[2 * j], v[2 * j + 1], oh[kk][j], ol[kk][j]);
                 }
             }
-        }
-        EPI_STAMP(1); // phase 1 done
-        if (e.has_res && !res_ready) mbar_wait(e.res_bar, res_phase); // warps without a chunk in this slab still consume the phase
-        if (e.has_res) res_phase ^= 1u;
-        if (sl == nslabs - 1 && !e.part_src) { // this warp has issued its last tcgen05.ld of the tile: the accumulator buffer may be reused
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(e.tmem_empty);
-        }
-        // ---- phase 2: staging buffer. The previous slab's / tile's bulk store has had all of phase 1 (and usually the whole
-        // wait for the next accumulator) to finish READING the buffer; only now does anyone wait for it. ----
-        if (!e.has_res) {
-            if (leader) {
-                if (elect_one()) bulk_wait_read0();
-                __syncwarp();
+            if (k0 + 2 >= MAXC) { // the slab's last chunk pair is in registers
+                EPI_STAMP(1);     // phase 1 done
+                if (e.has_res && !res_ready) mbar_wait(e.res_bar, res_phase); // warps without a chunk in this slab still consume the phase
+                if (e.has_res) res_phase ^= 1u;
+                if (sl == nslabs - 1 && !e.part_src) { // last tcgen05.ld of the tile issued: the accumulator buffer may be reused
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(e.tmem_empty);
+                }
             }
-            EPI_STAMP(2); // leader's wait for the previous store's reads
-            named_bar_sync(1, NWARPS * 32);
-        }
-        EPI_STAMP(3); // bar A
+            // ---- staging buffer. The previous slab's / tile's bulk store has had the whole first chunk pair (and usually the
+            // wait for the next accumulator) to finish READING the buffer; only now does anyone wait for it. ----
+            if (k0 == 0) {
+                if (!e.has_res) {
+                    if (leader) {
+                        if (elect_one()) bulk_wait_read0();
+                        __syncwarp();
+                    }
+                    EPI_STAMP(2); // leader's wait for the previous store's reads
+                    named_bar_sync(e.bar_id, NWARPS * 32);
+                }
+                EPI_STAMP(3); // bar A
+            }
 #pragma unroll
-        for (int k = 0; k < MAXC; ++k) {
-            const int ci = NWARPS == 8 ? half + 2 * k : k;
-            if (ci < (w >> 4)) {
+            for (int kk = 0; kk < 2; ++kk) {
+                const int k = k0 + kk, ci = NWARPS == 8 ? half + 2 * k : k;
+                if (ci < (w >> 4)) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[k][4 * g]), "r"(oh[k][4 * g + 1]), "r"(oh[k][4 * g + 2]), "r"(oh[k][4 * g + 3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[k][4 * g]), "r"(ol[k][4 * g + 1]), "r"(ol[k][4 * g + 2]), "r"(ol[k][4 * g + 3])
-                                 : "memory");
+                    for (int g = 0; g < 2; ++g) {
+                        const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[kk][4 * g]), "r"(oh[kk][4 * g + 1]), "r"(oh[kk][4 * g + 2]), "r"(oh[kk][4 * g + 3])
+                                     : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[kk][4 * g]), "r"(ol[kk][4 * g + 1]), "r"(ol[kk][4 * g + 2]),
+                                     "r"(ol[kk][4 * g + 3])
+                                     : "memory");
+                    }
                 }
             }
         }
         EPI_STAMP(4); // STS issued
         fence_async_smem();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
         EPI_STAMP(5); // fence
-        named_bar_sync(1, NWARPS * 32);
+        named_bar_sync(e.bar_id, NWARPS * 32);
         EPI_STAMP(6); // bar B
         if (leader) {
             if (elect_one()) {
@@ -443,6 +451,12 @@ __device__ __forceinline__ void epilogue_drain(bool leader) {
         if (p.trace && blockIdx.x == 0 && lane == 0 && (idx) < 256) p.trace[(role) * 256 + (idx)] = clock64(); \
     } while (0)
 
+// STAGES: depth of the operand ring. SPLIT_EPI: the eight epilogue warps work as TWO independent groups of four, group g
+// owning accumulator buffer g (tiles alternate between the buffers) with its own staging buffer, named barrier, residual
+// barrier and bulk-store queue, so one group's barrier / TMA-store latencies overlap the other group's arithmetic. Used for
+// layers with a short K loop (1x1 convolutions), which run at the speed of the epilogue; pays for the second staging buffer
+// with one ring stage (2 instead of 3).
+template <int STAGES, bool SPLIT_EPI>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO_hi64, const __grid_constant__ CUtensorMap tmO_lo64,
@@ -451,33 +465,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t stg       = smem_base + UM_STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned)
-    const uint32_t bar_base  = stg + UM_STG_BYTES;
+    const uint32_t stg       = smem_base + STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned), one buffer per epilogue group
+    const uint32_t bar_base  = stg + (SPLIT_EPI ? 2 : 1) * UM_STG_BYTES;
     // barrier slots (8 bytes each): full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), TMEM base slot, residual barrier
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar      = [&](int s) { return bar_base + 8u * (UM_STAGES + s); };
-    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * UM_STAGES + a); };
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * UM_STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * UM_STAGES + 4);
-    const uint32_t res_bar   = bar_base + 8u * (2 * UM_STAGES + 5);
+    auto empty_bar      = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t res_bar   = bar_base + 8u * (2 * STAGES + 5); // SPLIT_EPI: group 1 uses the slot after the split-K flag (+16)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger(); // the next kernel may start launching; it waits for this grid's completion before touching memory
     if (warp == 0 && lane == 0) {
         mbar_init(res_bar, 1);
+        mbar_init(res_bar + 16u, 1);
         tma_prefetch_desc(&tmO_hi64);
         tma_prefetch_desc(&tmO_lo64);
         tma_prefetch_desc(&tmA_hi);
         tma_prefetch_desc(&tmA_lo);
         tma_prefetch_desc(&tmB_hi);
         tma_prefetch_desc(&tmB_lo);
-        for (int s = 0; s < UM_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), UM_EPI_WARPS); // one arrive per epilogue warp
+            mbar_init(tmem_empty_bar(a), SPLIT_EPI ? UM_EPI_WARPS / 2 : UM_EPI_WARPS); // one arrive per epilogue warp that drains the buffer
         }
         fence_barrier_init();
     }
@@ -542,7 +557,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
                         }
                     }
-                    if (++stage == UM_STAGES) stage = 0, phase ^= 1u;
+                    if (++stage == STAGES) stage = 0, phase ^= 1u;
                     if (++cb == cbs) {
                         cb = 0, wk += icp;
                         if (++kx == ks) kx = 0, ++ky;
@@ -590,8 +605,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         umma_bf16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
                     }
                     const int cur         = stage;
-                    const uint32_t nphase = phase ^ (stage == UM_STAGES - 1 ? 1u : 0u);
-                    stage                 = stage == UM_STAGES - 1 ? 0 : stage + 1;
+                    const uint32_t nphase = phase ^ (stage == STAGES - 1 ? 1u : 0u);
+                    stage                 = stage == STAGES - 1 ? 0 : stage + 1;
                     phase                 = nphase;
                     ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking
                     if (!no_mma) {
@@ -615,21 +630,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         e.o_hi64 = &tmO_hi64, e.o_lo64 = &tmO_lo64, e.o_hiT = &tmO_hiT, e.o_loT = &tmO_loT;
         e.r_hi64 = &tmR_hi64, e.r_lo64 = &tmR_lo64, e.r_hiT = &tmR_hiT, e.r_loT = &tmR_loT;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = p.has_res, e.rows_box = p.rows_used, e.alpha = p.alpha;
-        e.stg = stg, e.res_bar = res_bar;
+        const int grp = SPLIT_EPI ? half : 0;                 // epilogue group of this warp
+        const bool leader = warp == (SPLIT_EPI ? 2 + 4 * grp : 2); // the group's TMA-issuing warp
+        e.stg = stg + grp * UM_STG_BYTES, e.res_bar = res_bar + 16u * grp, e.bar_id = 1 + grp;
         e.part_src = nullptr, e.part_splits = 0;
-        const uint32_t last_flag = bar_base + 8u * (2 * UM_STAGES + 6); // split-K: "this CTA arrived last" broadcast slot
+        const uint32_t last_flag = bar_base + 8u * (2 * STAGES + 6); // split-K: "this CTA arrived last" broadcast slot
         uint32_t res_phase = 0;
         int it = 0;
         for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
             const int tile = work % total_tiles, split = work / total_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
+            if (SPLIT_EPI && acc != grp) continue; // the other group's accumulator buffer
             const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
             const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
-            if (p.has_res && p.ksplit == 1) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, warp == 2);
+            if (p.has_res && p.ksplit == 1 && !(p.ablate & 1)) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
-            if (warp == 2) UM_TRACE(3, it);
+            if (leader) UM_TRACE(3, it);
             e.tmem_empty = tmem_empty_bar(acc);
             e.trace = p.trace, e.trace_seq = it;
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * UM_ACC_COLS);
@@ -656,13 +674,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (!last) continue;
                 __threadfence();
                 e.part_src = tile_parts, e.part_splits = p.ksplit;
-                if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, warp == 2);
+                if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             }
-            epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, warp == 2, lane, res_phase);
+            if (SPLIT_EPI)
+                epilogue_tile<UM_EPI_WARPS / 2>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, 0, leader, lane, res_phase);
+            else
+                epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, leader, lane, res_phase);
             e.part_src = nullptr;
-            if (warp == 2) UM_TRACE(4, it);
+            if (leader) UM_TRACE(4, it);
         }
-        epilogue_drain(warp == 2);
+        epilogue_drain(leader);
     }
 
     if (warp == 0) UM_TRACE(5, 2); // producer done
@@ -875,7 +896,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         e.o_hi64 = &tmO_hi, e.o_lo64 = &tmO_lo, e.o_hiT = &tmO_hi, e.o_loT = &tmO_lo;
         e.r_hi64 = e.r_lo64 = e.r_hiT = e.r_loT = &tmO_hi;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = 0, e.rows_box = UM_BLOCK_M, e.alpha = p.alpha;
-        e.stg = stg, e.res_bar = 0;
+        e.stg = stg, e.res_bar = 0, e.bar_id = 1;
         e.part_src = nullptr, e.part_splits = 0;
         uint32_t res_phase = 0;
         int it = 0;
@@ -1229,19 +1250,26 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         if (encode_nhwc_box_maps(encode, res, wT ? wT : 64, p.tw, p.th, p.tn, wT == 0, tmRT)) return 2;
     }
     if (!g_attr_set) {
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
         g_attr_set = true;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles * p.ksplit, ctx->sm_count);
+    // short K loop (1x1 convolutions): the layer runs at the speed of the epilogue -> two independent epilogue groups
+    static const bool no_split_epi = getenv("SNNB_NO_SPLIT_EPI") != nullptr;
+    const bool split_epi           = !no_split_epi && p.ksplit == 1 && p.ksize * p.ksize * p.cblocks <= 3 && total_tiles >= 2 * grid;
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
-    const cudaError_t le = launch_k_pdl(conv_umma_kernel, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1],
-                                    tmR64[0], tmR64[1], tmRT[0], tmRT[1], p);
+    const cudaError_t le =
+        split_epi ? launch_k_pdl(conv_umma_kernel<UM_STAGES - 1, true>, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES_SPLIT, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0],
+                                 tmO64[1], tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0], tmRT[1], p)
+                  : launch_k_pdl(conv_umma_kernel<UM_STAGES, false>, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1],
+                                 tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0], tmRT[1], p);
     if (p.trace) {
         char hdr[256];
         snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d ksplit %d", a.k, a.stride, in->c, out->c, out->n, out->h, out->w,
-                 p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, p.ksplit);
+                 p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -1 : p.ksplit); // ksplit -1 = split-epilogue variant
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
