@@ -43,8 +43,9 @@ constexpr int UM_THREADS     = 64 + 32 * UM_EPI_WARPS; // warp 0 TMA, warp 1 MMA
 constexpr int UM_ACC_COLS    = 2 * UM_MAX_N; // one accumulator buffer: [A_hi.B_hi + A_lo.B_hi | A_hi.B_lo], up to 2 x 128 fp32 columns
 constexpr int UM_TMEM_COLS   = 2 * UM_ACC_COLS; // double-buffered: all 512 columns
 constexpr int UM_STG_BYTES   = 2 * UM_BLOCK_M * 128; // epilogue staging: one 64-channel slab, hi + lo planes (32 KB)
-constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int UM_SMEM_BYTES_SPLIT = (UM_STAGES - 1) * UM_STAGE_BYTES + 2 * UM_STG_BYTES + 1024 + 256; // two epilogue groups, one ring stage less
+constexpr int UM_SCHED_SLOTS = 8;                        // ring of work-item ids handed from the producer warp to the MMA / epilogue warps
+constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 320 /*barriers + scheduler ring*/;
+constexpr int UM_SMEM_BYTES_SPLIT = (UM_STAGES - 1) * UM_STAGE_BYTES + 2 * UM_STG_BYTES + 1024 + 320; // two epilogue groups, one ring stage less
 
 struct UmmaParams {
     __nv_bfloat16* out_hi;
@@ -64,6 +65,7 @@ struct UmmaParams {
     // dumps its fp32 partial tile to `partials`, bumps the tile's arrival counter, and the LAST arriver sums all partials
     // in split order (deterministic) and runs the normal epilogue.
     int ksplit, kb_per_split;
+    int* sched_counter; // dynamic work distribution: next work item = gridDim.x + atomicAdd(counter, 1); zero between launches
     float* partials; // [tile][split][128 rows][n_blk]
     int* counters;   // [tile], zero between launches (the last arriver resets it)
     long long* trace; // profiling aid (env SNNB_UMMA_TRACE): CTA 0 writes clock64 stamps per role, [6][256]
@@ -474,6 +476,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     const uint32_t res_bar   = bar_base + 8u * (2 * STAGES + 5); // SPLIT_EPI: group 1 uses the slot after the split-K flag (+16)
+    // Dynamic work distribution. CTA b starts with work item b; every further item is drawn from a global counter by the
+    // producer warp (persistent CTAs on a statically striped grid finished up to 17 % apart on store-heavy layers) and handed
+    // to the MMA thread and the epilogue warps through this ring: id in sched_id[slot], full/empty mbarriers per slot.
+    auto sched_full  = [&](int s) { return bar_base + 128u + 8u * s; };
+    auto sched_empty = [&](int s) { return bar_base + 192u + 8u * s; };
+    auto sched_id    = [&](int s) { return bar_base + 256u + 4u * s; };
+    // consumer side: wait for sequence number `seq`, read its work id, release the slot (one arrive per consuming warp)
+    auto sched_take = [&](int seq, bool arrive) {
+        const int slot = seq & (UM_SCHED_SLOTS - 1);
+        mbar_wait(sched_full(slot), (uint32_t) (seq / UM_SCHED_SLOTS) & 1u);
+        int w;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sched_id(slot)) : "memory");
+        if (arrive) mbar_arrive(sched_empty(slot));
+        return w;
+    };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger(); // the next kernel may start launching; it waits for this grid's completion before touching memory
@@ -489,6 +506,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < UM_SCHED_SLOTS; ++s) {
+            mbar_init(sched_full(s), 1);
+            mbar_init(sched_empty(s), 1 + UM_EPI_WARPS); // the MMA thread + one lane of every epilogue warp
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
@@ -528,7 +549,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const bool skip_tma = (p.ablate & 2) != 0;
             const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u; // B_lo rows follow B_hi's: one [2 n_blk x 64] operand
             int tr = 0;
-            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+            const int draws_total = max(0, total_work - (int) gridDim.x) + (int) gridDim.x; // every CTA's last draw is past the end
+            int work = blockIdx.x;
+            for (int seq = 0;; ++seq) {
+                {   // publish this sequence number's work id
+                    const int slot = seq & (UM_SCHED_SLOTS - 1);
+                    mbar_wait(sched_empty(slot), ((uint32_t) (seq / UM_SCHED_SLOTS) & 1u) ^ 1u);
+                    if (elect_one()) {
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sched_id(slot)), "r"(work) : "memory");
+                        mbar_arrive(sched_full(slot));
+                    }
+                }
+                if (work >= total_work) break;
+                int next = 0; // drawn now, needed only after this item's loads are issued: the atomic's latency is hidden
+                if (elect_one()) {
+                    const int c = atomicAdd(p.sched_counter, 1);
+                    next        = (int) gridDim.x + c;
+                    if (c == draws_total - 1) *p.sched_counter = 0; // the very last draw of the launch: ready for the next one
+                }
                 const int tile = work % total_tiles, split = work / total_tiles;
                 const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
@@ -563,6 +601,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (++kx == ks) kx = 0, ++ky;
                     }
                 }
+                work = __shfl_sync(0xffffffffu, next, 0); // elect.sync picks lane 0 of the converged warp
             }
         }
     } else if (warp == 1) {
@@ -584,7 +623,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             int it = 0, tr = 0;
             bool ready = false; // full_bar(stage) already observed complete by the look-ahead
             const bool no_mma = (p.ablate & 4) != 0;
-            for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+            for (;; ++it) {
+                const int work = sched_take(it, true);
+                if (work >= total_work) break;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
@@ -637,7 +678,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t last_flag = bar_base + 8u * (2 * STAGES + 6); // split-K: "this CTA arrived last" broadcast slot
         uint32_t res_phase = 0;
         int it = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+        for (;; ++it) {
+            const int work = sched_take(it, lane == 0);
+            if (work >= total_work) break;
             const int tile = work % total_tiles, split = work / total_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
@@ -1197,6 +1240,17 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     SNNB_REQUIRE(op.n_blk > 0, "launch_conv2d_umma: no output-channel plan");
     p.n_blk = op.n_blk, p.tiles_oc = op.tiles_oc, p.ksplit = op.ksplit, p.kb_per_split = op.kb_per_split;
     p.partials = nullptr, p.counters = nullptr;
+    if (!ctx->sched_counter) { // created by the first (eager) launch; graph capture replays use the same word
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        SNNB_CUDA_OK(cudaStreamIsCapturing(ctx->stream, &cap));
+        SNNB_REQUIRE(cap == cudaStreamCaptureStatusNone, "launch_conv2d_umma: the scheduler counter must be allocated by an eager pass before graph capture");
+        void* pnew = nullptr;
+        SNNB_CUDA_OK(cudaMalloc(&pnew, 256));
+        SNNB_CUDA_OK(cudaMemset(pnew, 0, 256));
+        ctx->scratch_blocks.push_back(pnew);
+        ctx->sched_counter = static_cast<int*>(pnew);
+    }
+    p.sched_counter = ctx->sched_counter;
     if (p.ksplit > 1) {
         const size_t tiles = (size_t) tp.tiles_x * tp.tiles_y * tp.tiles_n * p.tiles_oc;
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;

@@ -135,6 +135,7 @@ struct snnb_context {
     size_t splitk_bytes    = 0;
     int* splitk_counters   = nullptr;
     size_t splitk_counter_n = 0;
+    int* sched_counter      = nullptr; // dynamic tile scheduler of conv_umma_kernel (self-resetting)
     std::vector<void*> scratch_blocks;
 };
 
