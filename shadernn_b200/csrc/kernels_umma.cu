@@ -6,19 +6,24 @@
 //   D[M = 128 output pixels, N = n_blk <= 128 output channels] += A[M, K] * B[N, K]^T,   K = (tap, 64-channel block)
 //
 // fp32-faithful arithmetic out of bf16 tensor cores: activations and weights are stored as hi + lo bf16 pairs
-// (snnb_internal.h); every K block issues three MMA groups into the same fp32 TMEM accumulator,
+// (snnb_internal.h); every K block accumulates into fp32 TMEM
 //       A_hi*B_hi  +  A_lo*B_hi  +  A_hi*B_lo                      (the dropped A_lo*B_lo term is ~2^-18 relative),
-// which keeps ~16 mantissa bits per operand — far inside the 1e-3 per-layer parity budget — at 3 bf16 MMAs per
+// which keeps ~16 mantissa bits per operand — far inside the 1e-3 per-layer parity budget — at 3 bf16 MMA-units per
 // product, i.e. 1.5x the cost of one TF32 pass but with fp32-class accuracy (TF32's 10-bit mantissa would not hold 1e-3).
+// The three terms are issued as TWO instructions per K=16 step: A_hi x [B_hi ; B_lo] (N = 2 n_blk, two accumulator column
+// blocks) and A_lo x B_hi (onto the first block); the epilogue adds the blocks.
 //
 // A tile = a (tw x th x tn)-pixel box of the OUTPUT grid (tw*th*tn <= 128): for filter tap (ky,kx) the producer issues
 // ONE 4-D TMA box load at input coordinate (ox0*s + kx - pad_x, oy0*s + ky - pad_y); out-of-range rows/columns are
 // zero-filled by the TMA unit, which is exactly the reference's constant padding (vk_conv2d.comp:168-172), and the
 // channel tail (c >= IC) is zero-filled too, so no im2col buffer and no boundary code exist anywhere.
 //
-// Roles (320 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-9 = epilogue (two warps per TMEM lane quarter, interleaved over 16-column chunks). Pipelines: smem full/empty ring (UM_STAGES deep) and a
-// double-buffered TMEM accumulator (tmem_full/tmem_empty), so the epilogue of tile i overlaps the mainloop of tile i+1.
+// Roles (320 threads, persistent CTAs, one per SM): warp 0 = TMA producer (also draws work items from a global counter),
+// warp 1 = TMEM allocator + one thread that owns the MMA issue loop, warps 2-9 = epilogue (TMEM -> registers -> swizzled smem
+// -> TMA bulk store). Pipelines: smem full/empty ring and a double-buffered TMEM accumulator (tmem_full/tmem_empty), so the
+// epilogue of tile i overlaps the mainloop of tile i+1. Layers with few tiles split K over several CTAs (fp32 partials, last
+// arriver reduces); layers with a short K loop use two independent epilogue groups. Also in this file: the row-window kernel
+// for small-channel stems and the TMA-staged depthwise kernel. DESIGN.md section 3 has the measurements behind each choice.
 //
 // Reference semantics: shadertemplate_vk_conv2d.comp:148-347, vk_conv2d_1x1.comp:68-211 (+ fused vk_add.comp:41-90).
 #include <cuda.h>
