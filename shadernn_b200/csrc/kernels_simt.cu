@@ -424,8 +424,8 @@ int launch_depthwise(snnb_context* ctx, const ConvArgs& a) {
 // top/left, maxpool2dVulkan.cpp:57-60), taps clipped to the input, max starts at -100000, avg divides by the
 // number of valid taps. One thread = 8 channels x 1 output pixel.
 // ------------------------------------------------------------------------------------------------------------
-// K > 0: window size known at compile time, all K*K taps' loads are issued before any is consumed (the generic loop keeps
-// only one tap in flight per thread and ran at 40% of the HBM roofline on ResNet's 3x3/2 max pool).
+// K > 0: window size known at compile time, a window row's taps are loaded together (the generic loop keeps only one tap
+// in flight per thread and ran at 40% of the HBM roofline on ResNet's 3x3/2 max pool).
 template <int K>
 __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int stride, int avg) {
     pdl_wait();
@@ -448,24 +448,25 @@ __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int str
     for (int j = 0; j < 8; ++j) acc[j] = avg ? 0.0f : -100000.0f;
     float num = 0.0f;
     if (K > 0) {
-        constexpr int KK = K > 0 ? K * K : 1;
-        uint4 th[KK], tl[KK]; // raw hi / lo planes of every tap; clipped taps re-read the window origin (always valid)
+        // one window row at a time: its K taps' loads are issued before any is consumed (K x 2 x 16 B in flight per thread) and
+        // the register footprint stays small enough for 5+ resident blocks per SM; clipped taps re-read the window origin
+        constexpr int KW = K > 0 ? K : 1;
 #pragma unroll
-        for (int fy = 0; fy < K; ++fy)
+        for (int fy = 0; fy < KW; ++fy) {
+            uint4 th[KW], tl[KW];
+            const bool oky = fy < efy;
 #pragma unroll
-            for (int fx = 0; fx < K; ++fx) {
-                const bool ok  = fy < efy && fx < efx;
+            for (int fx = 0; fx < KW; ++fx) {
+                const bool ok  = oky && fx < efx;
                 const size_t o = (((size_t) n * in.H + sy + (ok ? fy : 0)) * in.W + sx + (ok ? fx : 0)) * in.Cp + c;
-                th[fy * K + fx] = __ldg(reinterpret_cast<const uint4*>(in.hi + o));
-                tl[fy * K + fx] = __ldg(reinterpret_cast<const uint4*>(in.lo + o));
+                th[fx] = __ldg(reinterpret_cast<const uint4*>(in.hi + o));
+                tl[fx] = __ldg(reinterpret_cast<const uint4*>(in.lo + o));
             }
 #pragma unroll
-        for (int fy = 0; fy < K; ++fy)
-#pragma unroll
-            for (int fx = 0; fx < K; ++fx) {
-                if (fy < efy && fx < efx) {
+            for (int fx = 0; fx < KW; ++fx) {
+                if (oky && fx < efx) {
                     float v[8];
-                    unpack8(th[fy * K + fx], tl[fy * K + fx], v);
+                    unpack8(th[fx], tl[fx], v);
                     if (avg) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[j] += v[j];
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int str
                     }
                 }
             }
+        }
     } else {
         for (int fy = 0; fy < efy; ++fy)
             for (int fx = 0; fx < efx; ++fx) {
