@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -96,32 +96,55 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, region=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, sm_in, mx, reasons = [], [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
+                v0 = float(f[0])
                 mx = float(f[1])
             except ValueError:
                 continue
+            sm.append(v0)
+            # a sample is read a few ms after the driver took it: count it for the timed region if it arrived inside it or just after
+            if region and region[0] <= ts <= region[1] + 0.02:
+                sm_in.append(v0)
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        use = sm_in if sm_in else sm
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": mx, "samples": len(use), "samples_in_timed_region": len(sm_in),
+                "samples_under_load": len(sm), "reasons": sorted(reasons)}
+
+
+def tune_oracle_threads(oracle_mod, model, x1):
+    """Pick the OpenMP team size that runs the oracle fastest on this host (all logical CPUs is often slower than the physical
+    cores on an SMT box); torchrun exports OMP_NUM_THREADS=1, so the count is always set explicitly."""
+    n = os.cpu_count() or 1
+    best_t, best_dt = n, None
+    for t in sorted({n, max(1, n // 2), max(1, n // 4)}, reverse=True):
+        oracle_mod.lib().orc_set_num_threads(t)
+        model.run(x1)
+        t0 = time.perf_counter()
+        model.run(x1)
+        dt = time.perf_counter() - t0
+        if best_dt is None or dt < best_dt:
+            best_t, best_dt = t, dt
+    oracle_mod.lib().orc_set_num_threads(best_t)
+    return best_t
 
 
 def run_reference(args, rank, world):
@@ -139,7 +162,7 @@ def run_reference(args, rank, world):
     sample = max(1, min(batch, args.cpu_sample))
     x = modelzoo.synthetic_input(key, sample)
     m = oracle.Model(path)
-    oracle.lib().orc_set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
+    tune_oracle_threads(oracle, m, x[:1])
     threads = oracle.lib().orc_num_threads()
     for _ in range(max(1, min(args.warmup, 2))):
         m.run(x)
@@ -226,10 +249,18 @@ def main():
     tm = C.c_void_p()
     check(lib().snnb_timer_create(ctx.h, C.byref(tm)))
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    # keep the GPU under the same load while nvidia-smi starts up (~0.1 s), so that its 10 ms samples fall inside the timed
+    # region and every sample it ever takes is a sample under load
+    t_load = time.perf_counter()
+    while not sampler.lines and time.perf_counter() - t_load < 3.0:
+        for _ in range(8):
+            model.forward()
+        ctx.sync()
     parallel.barrier()
     ctx.sync()
-    sampler.start()
     launches0 = ctx.launches
+    t_region0 = time.perf_counter()
     check(lib().snnb_timer_start(tm))
     for _ in range(args.steps):
         model.forward()
@@ -237,8 +268,9 @@ def main():
     ms = C.c_float()
     check(lib().snnb_timer_elapsed_ms(tm, C.byref(ms)))
     ctx.sync()
+    t_region1 = time.perf_counter()
     launches = ctx.launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop((t_region0, t_region1))
     parallel.barrier()
     dev_ms = parallel.max_over_ranks(ms.value, dev)
 
@@ -355,7 +387,7 @@ def main():
         import csv
         rows = list(csv.reader(open(prof)))
         col = {n.split("[")[0]: i for i, n in enumerate(rows[0])}
-        sel = [r for r in rows[1:] if r[col["kernel"]].startswith("conv_umma") and not r[col["grid"]].startswith("(1,")]
+        sel = [r for r in rows[1:] if "conv_umma" in r[col["kernel"]] and not r[col["grid"]].startswith("(1,")]
         if sel:
             mb = [float(r[col["dram_read_MB"]]) + float(r[col["dram_write_MB"]]) * (1e-3 if "Kbyte" in rows[0][col["dram_write_MB"]] else 1.0) for r in sel]
             l2 = [float(r[col["l2_to_sm_read_MB"]]) for r in sel]
@@ -389,10 +421,10 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle
-        oracle.lib().orc_set_num_threads(os.cpu_count() or 1)
         sample = max(1, min(batch, args.cpu_sample))
         om = oracle.Model(path)
         xs = x[:sample]
+        tune_oracle_threads(oracle, om, x[:1])
         om.run(xs)
         t0 = time.perf_counter()
         reps_c = 3

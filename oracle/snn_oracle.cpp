@@ -145,6 +145,7 @@ int orc_conv2d(const float* x, int N, int H, int W, int IC, const float* w, cons
     // repack OIHW -> [ky][kx][ic][oc] so the oc loop vectorises while each oc keeps the shader's
     // sequential (ky,kx,ic) accumulation order.
     std::vector<float> wp((size_t) k * k * IC * OC);
+#pragma omp parallel for collapse(2) schedule(static)
     for (int o = 0; o < OC; ++o)
         for (int i = 0; i < IC; ++i)
             for (int ky = 0; ky < k; ++ky)
@@ -154,7 +155,7 @@ int orc_conv2d(const float* x, int N, int H, int W, int IC, const float* w, cons
     {
         std::vector<float> acc(OC);
         std::vector<double> accd(acc_double ? OC : 0);
-#pragma omp for collapse(2) schedule(static)
+#pragma omp for collapse(3) schedule(static) // (n, oy, ox): small feature maps (7x7) still give every host core work
         for (int n = 0; n < N; ++n) {
             for (int oy = 0; oy < OH; ++oy) {
                 for (int ox = 0; ox < OW; ++ox) {
@@ -248,7 +249,7 @@ int orc_conv2d(const float* x, int N, int H, int W, int IC, const float* w, cons
 // ---------------------------------------------------------------------------------------------
 int orc_depthwise(const float* x, int N, int H, int W, int C, const float* w, const float* bias, const float* bn, int k, int stride, int pad_x, int pad_y,
                   int act, float alpha, float* y, int OH, int OW) {
-#pragma omp parallel for collapse(2) schedule(static)
+#pragma omp parallel for collapse(3) schedule(static)
     for (int n = 0; n < N; ++n) {
         for (int oy = 0; oy < OH; ++oy) {
             for (int ox = 0; ox < OW; ++ox) {
@@ -276,7 +277,7 @@ int orc_depthwise(const float* x, int N, int H, int W, int C, const float* w, co
 // to the input; max starts at -100000; avg divides by the number of valid taps.
 // ---------------------------------------------------------------------------------------------
 int orc_pool2d(const float* x, int N, int H, int W, int C, int k, int stride, int is_avg, float* y, int OH, int OW) {
-#pragma omp parallel for collapse(2) schedule(static)
+#pragma omp parallel for collapse(3) schedule(static)
     for (int n = 0; n < N; ++n) {
         for (int oy = 0; oy < OH; ++oy) {
             for (int ox = 0; ox < OW; ++ox) {
