@@ -122,6 +122,23 @@ bool MixedInferenceCore::init(std::string& err) {
                     alias[conv]      = L;              // conv output == add output
                 }
             }
+            // (4) global AveragePooling2D -> [Flatten] -> Dense with few units: one classifier-head launch (gap_dense_kernel).
+            if (L->typeName == "Dense" && L->prevLayers.size() == 1) {
+                GenericModelLayer* f = L->prevLayers[0];
+                GenericModelLayer* pool = (f->typeName == "Flatten" && f->prevLayers.size() == 1 && f->nextLayers.size() == 1 &&
+                                           static_cast<FlattenLayer*>(f)->activation.id == SNNB_ACT_NONE)
+                                              ? f->prevLayers[0]
+                                              : f;
+                auto dimsOf = [&](GenericModelLayer* x) { return graph.outputDims[order[x]]; };
+                if (pool->typeName == "AveragePooling2D" && static_cast<PoolingLayer*>(pool)->isAvg && pool->nextLayers.size() == 1 && pool->prevLayers.size() == 1 &&
+                    !pool->fusedAway && dimsOf(pool).width * dimsOf(pool).height == 1 && static_cast<DenseLayer*>(L)->units <= 256 &&
+                    dimsOf(pool->prevLayers[0]).width * dimsOf(pool->prevLayers[0]).height >= 4 && dimsOf(pool->prevLayers[0]).depth <= 4096 &&
+                    static_cast<PoolingLayer*>(pool)->_desc.kernelSize >= dimsOf(pool->prevLayers[0]).width &&
+                    static_cast<PoolingLayer*>(pool)->_desc.kernelSize >= dimsOf(pool->prevLayers[0]).height) {
+                    static_cast<DenseLayer*>(L)->gapSource = pool->prevLayers[0];
+                    pool->fusedAway = true; // launches nothing; keeps its own (unwritten) 1x1 tensor so that shapes downstream still check
+                }
+            }
             // (3) Flatten of a 1x1xC tensor without activation is the identity.
             if (L->typeName == "Flatten" && L->inputDims.size() == 1 && L->inputDims[0].width * L->inputDims[0].height == 1 &&
                 static_cast<FlattenLayer*>(L)->activation.id == SNNB_ACT_NONE) {
@@ -459,6 +476,9 @@ int MixedInferenceCore::layerOutput(int layerId, float* host, size_t capacityFlo
     SNNB_REQUIRE(L->output, "layerOutput: layer %d (%s) has no device tensor", layerId, L->name.c_str());
     SNNB_REQUIRE(!(L->typeName == "Conv2D" && static_cast<Conv2DLayer*>(L)->fusedAct >= 0),
                  "layerOutput: layer %d (%s) was fused into its Add; load the model with fuse=0 to observe it", layerId, L->name.c_str());
+    SNNB_REQUIRE(!(L->fusedAway && L->typeName == "AveragePooling2D"),
+                 "layerOutput: layer %d (%s) was fused into the classifier head (pool + Dense in one launch); load the model with fuse=0 to observe it", layerId,
+                 L->name.c_str());
     const size_t floats = L->output->pixels() * L->output->c;
     SNNB_REQUIRE(capacityFloats >= floats, "layerOutput: buffer too small (%zu < %zu floats)", capacityFloats, floats);
     return snnb_tensor_download_nhwc(ctx, L->output, host);

@@ -230,6 +230,7 @@ public:
     void packWeights(snnb::PackedHost& p) override;
     int run(snnb_context* ctx, const ExecOptions& opt) override;
     snnb_tensor* flat = nullptr; // staging when the input is not 1x1
+    GenericModelLayer* gapSource = nullptr; // fused head: global average pool of this layer's output feeds the Dense (core.cpp, fusion 4)
 };
 class FlattenLayer : public GenericModelLayer { // flattenlayer.cpp:29-62 (CPU flavour: HWC order)
 public:

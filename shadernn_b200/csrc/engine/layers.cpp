@@ -200,6 +200,9 @@ void DenseLayer::packWeights(PackedHost& p) {
     std::vector<float>().swap(kernel);
 }
 int DenseLayer::run(snnb_context* ctx, const ExecOptions&) {
+    if (gapSource && gapSource->output && gap_dense_supported(gapSource->output, output, &weights))
+        return launch_gap_dense(ctx, gapSource->output, output, &weights, activation.id == SNNB_ACT_SOFTMAX ? SNNB_ACT_NONE : activation.id, activation.alpha,
+                                activation.id == SNNB_ACT_SOFTMAX);
     const snnb_tensor* x = inputs[0];
     if (x->h * x->w != 1) { // CPU Flatten order = HWC (cpulayer.h:94-115)
         if (launch_flatten(ctx, x, flat)) return 1;

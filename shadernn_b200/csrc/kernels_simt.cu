@@ -531,6 +531,64 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(TV in, TV out) {
     }
 }
 
+// Classifier head in one launch: global average pool (AveragePooling2D with pool == H == W) -> Dense (+ activation / softmax),
+// i.e. the tail of ResNet-18 (7x7x512 -> 10). Four tiny launches (pool, 1x1 tensor-core GEMM for a single tile, softmax) cost
+// more in ramp-up than in work. One CTA per image: pooled vector in shared memory (sequential sum per channel, deterministic),
+// one warp per output unit (lanes over input channels, shuffle tree), then the activation or a max-subtracted softmax
+// (cpulayer.h:175-191). Weights fp32 [IC][OCw] (the CUDA-core conv layout).
+__global__ void __launch_bounds__(256) gap_dense_kernel(TV in, TV out, const float* __restrict__ w, int ocw, const float* __restrict__ bias, int act, float alpha,
+                                                        int softmax) {
+    pdl_wait();
+    extern __shared__ float hs[]; // [in.Cp] pooled vector, then [out.Cp] logits
+    float* xs     = hs;
+    float* logits = hs + in.Cp;
+    const int n = blockIdx.x, HW = in.H * in.W, CG = in.Cp >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int cg = threadIdx.x; cg < CG; cg += blockDim.x) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        for (int px = 0; px < HW; ++px) {
+            float v[8];
+            load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + cg * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xs[cg * 8 + j] = acc[j] / (float) HW;
+    }
+    __syncthreads();
+    for (int oc = warp; oc < out.C; oc += (int) (blockDim.x >> 5)) {
+        float s = 0.0f;
+        for (int c = lane; c < in.C; c += 32) s = fmaf(xs[c], __ldg(w + (size_t) c * ocw + oc), s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) logits[oc] = softmax ? s + bias[oc] : apply_act(s + bias[oc], act, alpha);
+    }
+    __syncthreads();
+    if (softmax && warp == 0) { // max-subtracted softmax over the units, fixed-shape tree
+        float m = -3.402823466e+38f;
+        for (int oc = lane; oc < out.C; oc += 32) m = fmaxf(m, logits[oc]);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float z = 0.0f;
+        for (int oc = lane; oc < out.C; oc += 32) z += expf(logits[oc] - m);
+        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        for (int oc = lane; oc < out.C; oc += 32) logits[oc] = expf(logits[oc] - m) / z;
+    }
+    __syncthreads();
+    for (int oc = threadIdx.x; oc < out.Cp; oc += blockDim.x) store1(out.hi, out.lo, (size_t) n * out.Cp + oc, oc < out.C ? logits[oc] : 0.0f);
+}
+
+bool gap_dense_supported(const snnb_tensor* in, const snnb_tensor* out, const snnb_weights* w) {
+    return w && w->w_f32 && in->h * in->w >= 4 && in->cp <= 4096 && out->c <= 256 && out->h * out->w == 1 && in->n == out->n;
+}
+int launch_gap_dense(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, bool softmax) {
+    const size_t smem = (size_t) (in->cp + out->cp) * sizeof(float);
+    launch_k(gap_dense_kernel, dim3((unsigned) in->n), dim3(256), smem, ctx->stream, view(in), view(out), (const float*) w->w_f32, w->ocw, (const float*) w->bias, act, alpha,
+             softmax ? 1 : 0);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int k, int stride, bool avg) {
     TV vi = view(in), vo = view(out);
     if (avg && out->h == 1 && out->w == 1 && k >= in->h && k >= in->w && in->h * in->w >= 16) {

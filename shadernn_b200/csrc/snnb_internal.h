@@ -170,6 +170,9 @@ int launch_depthwise(snnb_context* ctx, const ConvArgs& a);
 bool depthwise_tma_supported(const ConvArgs& a);          // 3x3 stride 1/2: TMA-staged, register-tiled (kernels_umma.cu)
 int launch_depthwise_tma(snnb_context* ctx, const ConvArgs& a);
 int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int k, int stride, bool avg);
+// global average pool -> Dense (+ activation / softmax) in one launch (small classifier heads)
+bool gap_dense_supported(const snnb_tensor* in, const snnb_tensor* out, const snnb_weights* w);
+int launch_gap_dense(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, bool softmax);
 int launch_add(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out, int act, float alpha);
 int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha);
 int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int act, float alpha);
