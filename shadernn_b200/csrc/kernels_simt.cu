@@ -539,23 +539,31 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(TV in, TV out) {
 __global__ void __launch_bounds__(256) gap_dense_kernel(TV in, TV out, const float* __restrict__ w, int ocw, const float* __restrict__ bias, int act, float alpha,
                                                         int softmax) {
     pdl_wait();
-    extern __shared__ float hs[]; // [in.Cp] pooled vector, then [out.Cp] logits
-    float* xs     = hs;
-    float* logits = hs + in.Cp;
+    extern __shared__ float hs[]; // [parts][in.Cp] partial sums (row 0 becomes the pooled vector), then [out.Cp] logits
     const int n = blockIdx.x, HW = in.H * in.W, CG = in.Cp >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int cg = threadIdx.x; cg < CG; cg += blockDim.x) {
+    const int parts = max(1, min((int) blockDim.x / CG, 8)); // pixel ranges summed by different threads (49 dependent loads otherwise)
+    float* xs     = hs;
+    float* logits = hs + parts * in.Cp;
+    for (int item = threadIdx.x; item < CG * parts; item += blockDim.x) {
+        const int cg = item % CG, part = item / CG;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-        for (int px = 0; px < HW; ++px) {
+        for (int px = part; px < HW; px += parts) {
             float v[8];
             load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + cg * 8, v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += v[j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xs[cg * 8 + j] = acc[j] / (float) HW;
+        for (int j = 0; j < 8; ++j) xs[part * in.Cp + cg * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < in.Cp; c += blockDim.x) { // fixed order over the parts: deterministic
+        float t = xs[c];
+        for (int q = 1; q < parts; ++q) t += xs[q * in.Cp + c];
+        xs[c] = t / (float) HW;
     }
     __syncthreads();
     for (int oc = warp; oc < out.C; oc += (int) (blockDim.x >> 5)) {
@@ -582,7 +590,8 @@ bool gap_dense_supported(const snnb_tensor* in, const snnb_tensor* out, const sn
     return w && w->w_f32 && in->h * in->w >= 4 && in->cp <= 4096 && out->c <= 256 && out->h * out->w == 1 && in->n == out->n;
 }
 int launch_gap_dense(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, bool softmax) {
-    const size_t smem = (size_t) (in->cp + out->cp) * sizeof(float);
+    const int parts   = std::max(1, std::min(256 / (in->cp >> 3), 8));
+    const size_t smem = (size_t) (parts * in->cp + out->cp) * sizeof(float);
     launch_k(gap_dense_kernel, dim3((unsigned) in->n), dim3(256), smem, ctx->stream, view(in), view(out), (const float*) w->w_f32, w->ocw, (const float*) w->bias, act, alpha,
              softmax ? 1 : 0);
     SNNB_LAUNCH_CHECK(ctx);

@@ -48,7 +48,6 @@ constexpr int UM_THREADS     = 64 + 32 * UM_EPI_WARPS; // warp 0 TMA, warp 1 MMA
 constexpr int UM_ACC_COLS    = 2 * UM_MAX_N; // one accumulator buffer: [A_hi.B_hi + A_lo.B_hi | A_hi.B_lo], up to 2 x 128 fp32 columns
 constexpr int UM_TMEM_COLS   = 2 * UM_ACC_COLS; // double-buffered: all 512 columns
 constexpr int UM_STG_BYTES   = 2 * UM_BLOCK_M * 128; // epilogue staging: one 64-channel slab, hi + lo planes (32 KB)
-constexpr int UM_MAX_GROUP   = 4;                        // pixel tiles per accumulator buffer when n_blk <= 64 / group
 constexpr int UM_SCHED_SLOTS = 8;                        // ring of work-item ids handed from the producer warp to the MMA / epilogue warps
 constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 320 /*barriers + scheduler ring*/;
 constexpr int UM_SMEM_BYTES_SPLIT = (UM_STAGES - 1) * UM_STAGE_BYTES + 2 * UM_STG_BYTES + 1024 + 320; // two epilogue groups, one ring stage less
@@ -71,7 +70,6 @@ struct UmmaParams {
     // dumps its fp32 partial tile to `partials`, bumps the tile's arrival counter, and the LAST arriver sums all partials
     // in split order (deterministic) and runs the normal epilogue.
     int ksplit, kb_per_split;
-    int group; // pixel tiles per accumulator buffer / epilogue pass (1 unless n_blk <= 32, see EpiArgs::ntiles)
     int* sched_counter; // dynamic work distribution: next work item = gridDim.x + atomicAdd(counter, 1); zero between launches
     float* partials; // [tile][split][128 rows][n_blk]
     int* counters;   // [tile], zero between launches (the last arriver resets it)
@@ -238,11 +236,6 @@ struct EpiArgs {
     uint32_t res_bar;   // mbarrier for the residual TMA load
     uint32_t tmem_empty;
     int bar_id;         // named barrier of this epilogue group (1, or 1 + group when two groups work on alternate tiles)
-    // Tile group (narrow output-channel tiles, n_blk <= 32): up to UM_MAX_GROUP consecutive pixel tiles share one accumulator
-    // buffer (tile g in TMEM columns [g * 2 n_blk, (g+1) * 2 n_blk)) and ONE epilogue pass, which spreads its fixed costs
-    // (barriers, fence, bulk-store issue) over ntiles x n_blk <= 64 columns. Box coordinates per tile; ntiles == 1 otherwise.
-    int ntiles;
-    int c1[4], c2[4], c3[4];
     // split-K finalisation: accumulator values come from `part_splits` fp32 partial tiles [128][n_blk] in global memory
     // (summed in split order) instead of TMEM
     const float* part_src;
@@ -254,31 +247,28 @@ struct EpiArgs {
 // Fused residual (Conv2D -> Add): TMA box load of the residual tile's slab into the staging buffer. The previous bulk store
 // must have finished READING the buffer. Called for slab 0 BEFORE the wait for the accumulator, so the load's latency
 // hides behind the tile's MMAs. `leader` is warp-uniform: the whole leader warp calls, one lane issues.
-__device__ __forceinline__ void epilogue_residual_load(const EpiArgs& e, int sl, int oc0, bool leader) {
+__device__ __forceinline__ void epilogue_residual_load(const EpiArgs& e, int sl, int oc0, int c1, int c2, int c3, bool leader) {
     if (!leader) return;
     const int w          = min(64, e.n_blk - sl * 64);
-    const bool sw        = w == 64 && e.ntiles == 1;
+    const bool sw        = w == 64;
     const uint32_t pitch = sw ? 128u : (uint32_t) w * 2u;
     if (elect_one()) {
         bulk_wait_read0();
-        mbar_expect_tx(e.res_bar, (uint32_t) e.ntiles * 2u * (uint32_t) e.rows_box * pitch); // every box has rows_box rows (<= 128)
-        for (int g = 0; g < e.ntiles; ++g) {
-            const uint32_t dst = e.stg + (uint32_t) g * UM_BLOCK_M * pitch;
-            tma_load_4d(dst, sw ? e.r_hi64 : e.r_hiT, e.res_bar, oc0 + sl * 64, e.c1[g], e.c2[g], e.c3[g]);
-            tma_load_4d(dst + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, oc0 + sl * 64, e.c1[g], e.c2[g], e.c3[g]);
-        }
+        mbar_expect_tx(e.res_bar, 2u * (uint32_t) e.rows_box * pitch); // the box has rows_box rows (<= 128)
+        tma_load_4d(e.stg, sw ? e.r_hi64 : e.r_hiT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
+        tma_load_4d(e.stg + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
     }
     __syncwarp();
 }
 
 template <int NWARPS>
-__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, int oc0, int row, int half, bool leader, int lane, uint32_t& res_phase) {
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, int oc0, int c1, int c2, int c3, int row, int half, bool leader, int lane,
+                                              uint32_t& res_phase) {
     constexpr int MAXC  = NWARPS == 8 ? 2 : 4; // 16-column chunks of one 64-column slab owned by this warp
     const bool fast_act = e.act == SNNB_ACT_NONE || e.act == SNNB_ACT_RELU || e.act == SNNB_ACT_RELU6 || e.act == SNNB_ACT_LEAKY_RELU;
     const float slope   = (e.act == SNNB_ACT_RELU || e.act == SNNB_ACT_RELU6) ? 0.0f : (e.act == SNNB_ACT_LEAKY_RELU ? e.alpha : 1.0f);
     const float hi_clip = e.act == SNNB_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
-    const int nslabs    = (e.n_blk + 63) >> 6; // a tile group (ntiles > 1) has n_blk <= 32: one pass over ntiles * n_blk <= 64 columns
-    const int cpt       = e.n_blk >> 4;        // 16-column chunks per tile (group mode)
+    const int nslabs    = (e.n_blk + 63) >> 6;
 #define EPI_STAMP(k)                                                                                      \
     do {                                                                                                  \
         if (e.trace && leader && lane == 0 && blockIdx.x == 0 && tseq < 16) e.trace[4 * 256 + 64 + 8 * tseq + (k)] = clock64(); \
@@ -286,15 +276,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
     for (int sl = 0; sl < nslabs; ++sl) {
         const int tseq     = e.trace_seq * nslabs + sl;
         EPI_STAMP(0);
-        const bool grouped = e.ntiles > 1;
-        const int wt       = min(64, e.n_blk - sl * 64); // one tile's slab width in channels (multiple of 16)
-        const int w        = grouped ? e.ntiles * e.n_blk : wt; // columns handled by this pass
-        const bool sw      = wt == 64 && !grouped;        // full slab: 128-byte rows, SWIZZLE_128B
-        const uint32_t pitch = sw ? 128u : (uint32_t) wt * 2u;
-        const uint32_t srow  = e.stg + (uint32_t) row * pitch; // + g * UM_BLOCK_M * pitch for tile g of a group
+        const int w        = min(64, e.n_blk - sl * 64); // slab width in channels (multiple of 16)
+        const bool sw      = w == 64;                    // full slab: 128-byte rows, SWIZZLE_128B
+        const uint32_t pitch = sw ? 128u : (uint32_t) w * 2u;
+        const uint32_t srow  = e.stg + (uint32_t) row * pitch;
         const uint32_t xr    = sw ? (uint32_t) (row & 7) : 0u;
         const int slab_oc    = oc0 + sl * 64;
-        if (e.has_res && sl > 0) epilogue_residual_load(e, sl, oc0, leader); // slab 0's was issued before the accumulator wait
+        if (e.has_res && sl > 0) epilogue_residual_load(e, sl, oc0, c1, c2, c3, leader); // slab 0's was issued before the accumulator wait
         // ---- phase 1: TMEM -> registers -> bias (+ residual) -> activation -> packed split-bf16, nothing written yet ----
         bool res_ready = false;
 #pragma unroll
@@ -305,10 +293,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
             for (int kk = 0; kk < 2; ++kk) {
                 const int ci = NWARPS == 8 ? half + 2 * (k0 + kk) : k0 + kk;
                 if (ci < (w >> 4)) {
-                    const int gt = grouped ? ci / cpt : 0;                  // tile of the group
-                    const int lc = grouped ? ci - gt * cpt : ci;            // its 16-column chunk
-                    const int c  = sl * 64 + lc * 16;                       // channel offset within the oc tile
-                    const uint32_t tcol = (uint32_t) (gt * 2 * e.n_blk + c); // accumulator column of the main block
+                    const int c = sl * 64 + ci * 16;
                     if (e.part_src) {
                         // all loads of the chunk are issued before the first add (L2 latency once, not once per split);
                         // summed in split order: the result does not depend on which CTA arrived last
@@ -332,8 +317,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) r[kk][j] = __float_as_uint(a16[j]), r2[kk][j] = 0u;
                     } else {
-                        tmem_ld16(taddr + tcol, r[kk]);
-                        tmem_ld16(taddr + tcol + (uint32_t) e.n_blk, r2[kk]);
+                        tmem_ld16(taddr + (uint32_t) c, r[kk]);
+                        tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2[kk]);
                     }
                 }
             }
@@ -342,9 +327,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
             for (int kk = 0; kk < 2; ++kk) {
                 const int k = k0 + kk, ci = NWARPS == 8 ? half + 2 * k : k;
                 if (ci < (w >> 4)) {
-                    const int gt = grouped ? ci / cpt : 0, lc = grouped ? ci - gt * cpt : ci;
-                    const int c  = sl * 64 + lc * 16;
-                    const uint32_t srow_g = srow + (uint32_t) gt * UM_BLOCK_M * pitch;
+                    const int c = sl * 64 + ci * 16;
                     float v[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) { // the bias slice of a tile stays L1-resident across the CTA's tiles
@@ -361,7 +344,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                         }
 #pragma unroll
                         for (int g = 0; g < 2; ++g) { // this thread later overwrites exactly the 16-byte pieces it reads here
-                            const uint32_t a = srow_g + ((((uint32_t) (lc * 2 + g)) ^ xr) << 4);
+                            const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
                             uint32_t hh[4], ll[4];
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]) : "r"(a));
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(a + UM_BLOCK_M * 128));
@@ -410,11 +393,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
             for (int kk = 0; kk < 2; ++kk) {
                 const int k = k0 + kk, ci = NWARPS == 8 ? half + 2 * k : k;
                 if (ci < (w >> 4)) {
-                    const int gt = grouped ? ci / cpt : 0, lc = grouped ? ci - gt * cpt : ci;
-                    const uint32_t srow_g = srow + (uint32_t) gt * UM_BLOCK_M * pitch;
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        const uint32_t a = srow_g + ((((uint32_t) (lc * 2 + g)) ^ xr) << 4);
+                        const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[kk][4 * g]), "r"(oh[kk][4 * g + 1]), "r"(oh[kk][4 * g + 2]), "r"(oh[kk][4 * g + 3])
                                      : "memory");
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[kk][4 * g]), "r"(ol[kk][4 * g + 1]), "r"(ol[kk][4 * g + 2]),
@@ -431,11 +412,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
         EPI_STAMP(6); // bar B
         if (leader) {
             if (elect_one()) {
-                for (int g = 0; g < e.ntiles; ++g) {
-                    const uint32_t src = e.stg + (uint32_t) g * UM_BLOCK_M * pitch;
-                    tma_store_4d(sw ? e.o_hi64 : e.o_hiT, src, slab_oc, e.c1[g], e.c2[g], e.c3[g]);
-                    tma_store_4d(sw ? e.o_lo64 : e.o_loT, src + UM_BLOCK_M * 128, slab_oc, e.c1[g], e.c2[g], e.c3[g]);
-                }
+                tma_store_4d(sw ? e.o_hi64 : e.o_hiT, e.stg, slab_oc, c1, c2, c3);
+                tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
                 bulk_commit();
             }
             __syncwarp();
@@ -562,8 +540,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 0) UM_TRACE(5, 1); // setup done
 
     const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
-    const int m_groups    = (m_tiles + p.group - 1) / p.group; // work item = `group` consecutive pixel tiles of one oc tile
-    const int total_tiles = m_groups * p.tiles_oc;             // (group == 1: one output tile)
+    const int total_tiles = m_tiles * p.tiles_oc;
     const int num_kb      = p.ksize * p.ksize * p.cblocks;
     const int total_work  = total_tiles * p.ksplit; // work item = (tile, K range); ksplit == 1: one item per tile
 
@@ -596,14 +573,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (c == draws_total - 1) *p.sched_counter = 0; // the very last draw of the launch: ready for the next one
                 }
                 const int tile = work % total_tiles, split = work / total_tiles;
-                const int mg = tile % m_groups, oc_idx = tile / m_groups;
-                const int oc0 = oc_idx * p.n_blk;
-                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-                for (int g = 0; g < p.group; ++g) {
-                const int m_idx = mg * p.group + g;
-                if (m_idx >= m_tiles) break;
+                const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
                 const int ix0 = bx * p.tw * p.stride - p.pad_x, iy0 = by * p.th * p.stride - p.pad_y, n0 = bn * p.tn;
+                const int oc0 = oc_idx * p.n_blk;
+                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 // Keep this loop lean: it runs once per K block and every stall here delays the whole pipeline (no divisions,
                 // no parameter loads: ncu r01 showed ~60 dependent scalar instructions/iteration bounding the kernel).
                 // K block kb = (ky * ks + kx) * cbs + cb; the counters are decoded once per work item and then stepped.
@@ -632,7 +606,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (++kx == ks) kx = 0, ++ky;
                     }
                 }
-                } // tiles of the group
                 work = __shfl_sync(0xffffffffu, next, 0); // elect.sync picks lane 0 of the converged warp
             }
         }
@@ -662,10 +635,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
                 tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_ACC_COLS);
                 const int kb0 = (work / total_tiles) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-                const int ng = min(p.group, m_tiles - ((work % total_tiles) % m_groups) * p.group); // tiles in this group
-                for (int g = 0; g < ng; ++g) {
-                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_ACC_COLS + g * 2 * p.n_blk);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!ready) mbar_wait(full_bar(stage), phase); // TMA bytes have landed
                     tc_fence_after();
@@ -689,11 +660,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         umma_bf16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
                     }
                     umma_commit(empty_bar(cur));                           // smem slot free once these MMAs retire
-                    if (kb == kb1 - 1 && g == ng - 1) umma_commit(tmem_full_bar(acc)); // accumulator(s) complete -> epilogue
+                    if (kb == kb1 - 1) umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
                     UM_TRACE(2, tr);
                     ++tr;
                 }
-                } // tiles of the group
             }
         }
         __syncwarp();
@@ -720,13 +690,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             if (SPLIT_EPI && acc != grp) continue; // the other group's accumulator buffer
-            const int mg = tile % m_groups, oc_idx = tile / m_groups;
-            e.ntiles = min(p.group, m_tiles - mg * p.group);
-            for (int g = 0; g < e.ntiles; ++g) {
-                const int m_idx = mg * p.group + g;
-                e.c1[g] = (m_idx % p.tiles_x) * p.tw, e.c2[g] = ((m_idx / p.tiles_x) % p.tiles_y) * p.th, e.c3[g] = (m_idx / (p.tiles_x * p.tiles_y)) * p.tn;
-            }
-            if (p.has_res && p.ksplit == 1 && !(p.ablate & 1)) epilogue_residual_load(e, 0, oc_idx * p.n_blk, leader);
+            const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
+            const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
+            if (p.has_res && p.ksplit == 1 && !(p.ablate & 1)) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             if (leader) UM_TRACE(3, it);
@@ -756,12 +722,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (!last) continue;
                 __threadfence();
                 e.part_src = tile_parts, e.part_splits = p.ksplit;
-                if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, leader);
+                if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             }
             if (SPLIT_EPI)
-                epilogue_tile<UM_EPI_WARPS / 2>(e, taddr, oc_idx * p.n_blk, row, 0, leader, lane, res_phase);
+                epilogue_tile<UM_EPI_WARPS / 2>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, 0, leader, lane, res_phase);
             else
-                epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, row, half, leader, lane, res_phase);
+                epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, leader, lane, res_phase);
             e.part_src = nullptr;
             if (leader) UM_TRACE(4, it);
         }
@@ -992,8 +958,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             e.tmem_empty = tmem_empty_bar(acc);
             e.trace = p.trace, e.trace_seq = it;
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * 2 * RW_MAX_N);
-            e.ntiles = 1, e.c1[0] = xt * UM_BLOCK_M, e.c2[0] = oy, e.c3[0] = n;
-            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, row, half, warp == 2, lane, res_phase);
+            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, half, warp == 2, lane, res_phase);
             if (warp == 2) UM_TRACE(4, it);
         }
         epilogue_drain(warp == 2);
@@ -1348,16 +1313,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
         g_attr_set = true;
     }
-    // narrow oc tiles: several pixel tiles per accumulator buffer and epilogue pass (EpiArgs::ntiles), as long as every SM
-    // still gets at least two work items
-    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    static const bool no_group = getenv("SNNB_NO_TILE_GROUP") != nullptr;
-    p.group = 1;
-    if (!no_group && p.ksplit == 1 && p.n_blk <= 32) {
-        p.group = std::min(UM_MAX_GROUP, 64 / p.n_blk);
-        while (p.group > 1 && (long long) ((m_tiles + p.group - 1) / p.group) * p.tiles_oc < 2LL * ctx->sm_count) --p.group;
-    }
-    const int total_tiles = (m_tiles + p.group - 1) / p.group * p.tiles_oc; // work items per K range
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles * p.ksplit, ctx->sm_count);
     // short K loop (1x1 convolutions): the layer runs at the speed of the epilogue -> two independent epilogue groups
     static const bool no_split_epi = getenv("SNNB_NO_SPLIT_EPI") != nullptr;
@@ -1372,7 +1328,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     if (p.trace) {
         char hdr[256];
         snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d ksplit %d", a.k, a.stride, in->c, out->c, out->n, out->h, out->w,
-                 p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -p.group : p.ksplit); // negative = split-epilogue variant, |value| = tile group
+                 p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -1 : p.ksplit); // ksplit -1 = split-epilogue variant
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

@@ -112,15 +112,3 @@ def test_split_k(ctx, n, h, w, ic, oc, k, residual, act):
     # arriver in split order. Run twice: the second launch checks that the arrival counters were left at zero.
     run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=ic + h)
     run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=ic + h + 1)
-
-
-@pytest.mark.parametrize("n,h,w,ic,oc,k,residual,act", [
-    (16, 112, 112, 32, 16, 1, False, ""),       # MobileNetV2 first projection: n_blk 16 -> 4 pixel tiles per accumulator buffer
-    (32, 56, 56, 96, 24, 1, False, "relu6"),    # n_blk 32 -> 2 tiles per group
-    (32, 56, 56, 144, 24, 1, True, ""),         # ... with the fused residual (inverted-residual block with skip connection)
-    (12, 100, 99, 16, 16, 3, False, "relu"),    # 3x3 with several K blocks per tile, ragged edges, odd group count
-    (9, 64, 64, 64, 32, 1, True, "leakyRelu"),  # last group of an oc tile is partial
-])
-def test_tile_groups_for_narrow_output_tiles(ctx, n, h, w, ic, oc, k, residual, act):
-    # n_blk <= 32: several consecutive pixel tiles share one TMEM accumulator buffer and one epilogue pass
-    run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=oc + h)
