@@ -8,6 +8,7 @@
 Every call goes through libsnn_b200.so; nothing here computes.
 """
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -51,6 +52,8 @@ class GpuContext:
             self.h = vp()
 
     def __del__(self):
+        if sys.is_finalizing():  # interpreter shutdown: the CUDA runtime may already be gone, leave the handle to the OS
+            return
         try:
             self.close()
         except Exception:
@@ -105,6 +108,8 @@ class ImageTexture:
             self.h = vp()
 
     def __del__(self):
+        if sys.is_finalizing():
+            return
         try:
             self.free()
         except Exception:
@@ -121,6 +126,8 @@ class Weights:
             self.h = vp()
 
     def __del__(self):
+        if sys.is_finalizing():
+            return
         try:
             self.free()
         except Exception:
@@ -431,6 +438,8 @@ class MixedInferenceCore:
             self.h = vp()
 
     def __del__(self):
+        if sys.is_finalizing():  # interpreter shutdown: the CUDA runtime may already be gone, leave the handle to the OS
+            return
         try:
             self.close()
         except Exception:

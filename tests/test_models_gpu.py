@@ -6,6 +6,8 @@ tolerance 1e-3 (abs-or-rel, the reference's comparator) instead of 0.01; classif
 Sizes are kept small enough for the oracle to finish in seconds; BASELINE-size runs are checked through
 size-independent properties (batch consistency, fused == unfused, CUDA-graph replay == eager).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -254,3 +256,30 @@ def test_torchvision_export_runs_like_torch(ctx, tmp_path, name):
     scale = float(np.abs(want).max())
     assert float(np.abs(got - want).max()) <= EPS * scale, (float(np.abs(got - want).max()), scale)
     assert np.array_equal(cls - 1, want.argmax(1))
+
+
+def test_dump_outputs_diff_against_oracle_dumps(ctx, model_dir, tmp_path):
+    # the --dump_outputs workflow (vulkanBackend.cpp:108-143): every layer's output as a reference-format .dump file, diffed
+    # with tools/compare_dumps.py's machinery against dumps of the ground truth (here the oracle; elsewhere a ShaderNN/ncnn run)
+    from shadernn_b200 import dumpio
+    path, layers = modelzoo.build("resnet18", model_dir, input_hw=(64, 64))
+    x = modelzoo.synthetic_input("resnet18", 2, (64, 64))
+    want = oracle.Model(path).run(x, return_all=True)
+    m = core.MixedInferenceCore(ctx, path, batch=2, input_hw=(64, 64), fuse=False)
+    m.run(x)
+    got_dir, ref_dir = tmp_path / "got", tmp_path / "ref"
+    got_dir.mkdir(), ref_dir.mkdir()
+    m.dump_outputs(str(got_dir))
+    files = set(os.listdir(got_dir))
+    expected = set()
+    for i in range(m.num_layers):
+        lname, _, _ = m.layer_info(i)
+        for n in range(2):
+            fname = "%s pass[0].dump.n%d" % (lname, n)
+            expected.add(fname)
+            dumpio.write_dump(str(ref_dir / fname), want[i][n])
+    assert files == expected, (sorted(files - expected)[:3], sorted(expected - files)[:3])
+    # the tool's default tolerance is the reference's own (0.01 abs-and-rel, testutil.cpp:351-361); the strict per-layer check at
+    # 1e-3 relative to each tensor's range is layerwise_check above
+    rows = dumpio.compare_dirs(str(got_dir), str(ref_dir), eps=0.01)
+    assert len(rows) == 2 * m.num_layers and all(r[4] == "ok" for r in rows), [r for r in rows if r[4] != "ok"][:3]
