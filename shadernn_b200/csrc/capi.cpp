@@ -275,10 +275,14 @@ int snnb_depthwise_launch(snnb_context* ctx, const snnb_conv_desc* d, const snnb
 }
 int snnb_maxpool_launch(snnb_context* ctx, int kernel, int stride, const snnb_tensor* in, snnb_tensor* out) {
     SNNB_REQUIRE(ctx && in && out && kernel > 0 && stride > 0 && in->c == out->c && in->n == out->n, "snnb_maxpool_launch: bad argument");
+    // every window must START inside the input (pool windows are clipped at the bottom/right edge, never padded top/left)
+    SNNB_REQUIRE((long long) (out->w - 1) * stride < in->w && (long long) (out->h - 1) * stride < in->h, "snnb_maxpool_launch: output %dx%d does not fit input %dx%d at stride %d", out->h, out->w, in->h, in->w, stride);
     return launch_pool(ctx, in, out, kernel, stride, false);
 }
 int snnb_avgpool_launch(snnb_context* ctx, int kernel, int stride, const snnb_tensor* in, snnb_tensor* out) {
     SNNB_REQUIRE(ctx && in && out && kernel > 0 && stride > 0 && in->c == out->c && in->n == out->n, "snnb_avgpool_launch: bad argument");
+    // every window must START inside the input (pool windows are clipped at the bottom/right edge, never padded top/left)
+    SNNB_REQUIRE((long long) (out->w - 1) * stride < in->w && (long long) (out->h - 1) * stride < in->h, "snnb_avgpool_launch: output %dx%d does not fit input %dx%d at stride %d", out->h, out->w, in->h, in->w, stride);
     return launch_pool(ctx, in, out, kernel, stride, true);
 }
 int snnb_add_launch(snnb_context* ctx, int act, float alpha, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out) {

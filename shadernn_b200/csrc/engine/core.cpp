@@ -228,6 +228,43 @@ bool MixedInferenceCore::init(std::string& err) {
             err = L->name + ": expects exactly two inputs";
             return false;
         }
+        // The kernels index weights and operands with the RUNTIME tensors' extents: a model whose declared planes disagree with
+        // what the graph produces would read out of bounds on the device. Reject it here, as a load error.
+        auto dimsStr = [](const snnb_tensor* t) { return std::to_string(t->h) + "x" + std::to_string(t->w) + "x" + std::to_string(t->c); };
+        if (L->typeName == "Conv2D" || L->typeName == "SeparableConv2D" || L->typeName == "BatchNormalization" || L->typeName == "InstanceNorm") {
+            if (L->inputs.empty() || !L->output) {
+                err = L->name + ": layer has no input";
+                return false;
+            }
+            if ((uint32_t) L->inputs[0]->c != L->numInputPlanes) {
+                err = L->name + ": inputPlanes " + std::to_string(L->numInputPlanes) + " but the producing layer has " + std::to_string(L->inputs[0]->c) + " channels";
+                return false;
+            }
+            const uint32_t wantOut = (L->typeName == "Conv2D") ? L->numOutputPlanes : L->numInputPlanes;
+            if ((uint32_t) L->output->c != wantOut) {
+                err = L->name + ": output tensor has " + std::to_string(L->output->c) + " channels, weights are packed for " + std::to_string(wantOut);
+                return false;
+            }
+        }
+        if (L->typeName == "Add") {
+            for (auto* in : L->inputs)
+                if (in->h != L->output->h || in->w != L->output->w || in->c != L->output->c) {
+                    err = L->name + ": Add operand " + dimsStr(in) + " does not match the output " + dimsStr(L->output);
+                    return false;
+                }
+        }
+        if (L->typeName == "Conv2D" && L->residual &&
+            (L->residual->h != L->output->h || L->residual->w != L->output->w || L->residual->c != L->output->c)) {
+            err = L->name + ": fused Add operand " + dimsStr(L->residual) + " does not match the output " + dimsStr(L->output);
+            return false;
+        }
+        if (L->typeName == "Concatenate") {
+            if (L->inputs[0]->h != L->inputs[1]->h || L->inputs[0]->w != L->inputs[1]->w || L->inputs[0]->c + L->inputs[1]->c != L->output->c ||
+                L->inputs[0]->h != L->output->h || L->inputs[0]->w != L->output->w) {
+                err = L->name + ": Concatenate operands " + dimsStr(L->inputs[0]) + " and " + dimsStr(L->inputs[1]) + " do not stack into " + dimsStr(L->output);
+                return false;
+            }
+        }
     }
 
     // ---- weights: fold + pack on the host, then ONE device arena (broadcastable with a single NCCL call) ----
@@ -510,6 +547,9 @@ int MixedInferenceCore::timeLayers(std::vector<float>& ms) {
 int MixedInferenceCore::dumpOutputs(const std::string& dir) {
     for (auto& l : layers) {
         if (!l->output || l->fusedAway) continue;
+        // a Conv2D fused into its Add writes the ADD's tensor (post-add, post-activation): under the conv's name the file would
+        // not be what a reference run dumps for that layer (layerOutput() refuses the same case)
+        SNNB_REQUIRE(!(l->typeName == "Conv2D" && l->fusedAct >= 0), "dumpOutputs: %s was fused into its Add; load the model with fuse=0 to dump every layer", l->name.c_str());
         std::string path = dir + "/" + l->name + " pass[0].dump"; // vulkanBackend.cpp:108-143 naming
         if (snnb_tensor_dump(ctx, l->output, path.c_str())) return 1;
     }

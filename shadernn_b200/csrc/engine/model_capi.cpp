@@ -45,6 +45,7 @@ int snnb_model_load_json(snnb_context* ctx, const char* json_path, const snnb_mo
 }
 
 int snnb_model_destroy(snnb_model* m) {
+    if (m && m->core && m->core->ctx) cudaSetDevice(m->core->ctx->device);
     delete m;
     return 0;
 }
@@ -110,30 +111,37 @@ int snnb_model_submit_u8(snnb_model* m, const uint8_t* host_input_u8, const floa
 }
 int snnb_model_wait(snnb_model* m, int ticket) {
     SNNB_REQUIRE(m, "snnb_model_wait: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->wait(ticket);
 }
 int snnb_model_set_input(snnb_model* m, int idx, const float* host_input) {
     SNNB_REQUIRE(m, "snnb_model_set_input: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->setInput(idx, host_input);
 }
 int snnb_model_forward(snnb_model* m) {
     SNNB_REQUIRE(m, "snnb_model_forward: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->forward();
 }
 int snnb_model_get_output(snnb_model* m, int idx, float* host_output, size_t cap) {
     SNNB_REQUIRE(m, "snnb_model_get_output: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->getOutput(idx, host_output, cap);
 }
 int snnb_model_layer_output(snnb_model* m, int layer, float* host, size_t cap) {
     SNNB_REQUIRE(m, "snnb_model_layer_output: null model");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->layerOutput(layer, host, cap);
 }
 int snnb_model_dump_outputs(snnb_model* m, const char* dir) {
     SNNB_REQUIRE(m && dir, "snnb_model_dump_outputs: null argument");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->dumpOutputs(dir);
 }
 int snnb_model_time_layers(snnb_model* m, float* times_ms, int capacity) {
     SNNB_REQUIRE(m && times_ms && capacity >= (int) m->core->layers.size(), "snnb_model_time_layers: bad argument");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     std::vector<float> ms;
     if (m->core->timeLayers(ms)) return 1;
     for (size_t i = 0; i < ms.size(); ++i) times_ms[i] = ms[i];

@@ -366,6 +366,7 @@ static GenericModelLayer* DenseCreator(ModelParser& parser, int i) { // modelpar
     common(L, parser, i);
     const json::Value& l = parser.layer(i);
     L->units             = l.has("units") ? (uint32_t) l.at("units").asNumber() : L->numOutputPlanes;
+    if (L->units == 0) throw std::runtime_error("Dense layer " + std::to_string(i) + ": units must be positive");
     const json::Value* wobj = l.find("weights");
     if (parser.isBinWeight()) {
         readFloats(parser, nullptr, (size_t) L->numInputPlanes * L->units, L->kernel, "kernel");

@@ -1152,7 +1152,7 @@ bool conv2d_umma_supported(const ConvArgs& a) {
     return true;
 }
 
-static bool g_attr_set = false, g_attr_set_rg = false;
+enum { ATTR_UMMA = 1u, ATTR_ROWWIN = 2u, ATTR_DW1 = 4u, ATTR_DW2 = 8u }; // bits of snnb_context::func_attr_mask
 
 static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
     const snnb_tensor* in = a.in;
@@ -1199,9 +1199,9 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     }
     CUtensorMap tmO[2];
     if (encode_nhwc_box_maps(encode, out, p.n_blk, UM_BLOCK_M, 1, 1, p.n_blk == 64, tmO)) return 2;
-    if (!g_attr_set_rg) {
+    if (!(ctx->func_attr_mask & ATTR_ROWWIN)) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
-        g_attr_set_rg = true;
+        ctx->func_attr_mask |= ATTR_ROWWIN;
     }
     const int total_tiles = p.N * p.OH * p.tiles_x;
     const int grid        = std::min(total_tiles, ctx->sm_count);
@@ -1308,10 +1308,10 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         if (encode_nhwc_box_maps(encode, res, p.n_blk >= 64 ? 64 : wT, p.tw, p.th, p.tn, p.n_blk >= 64, tmR64)) return 2;
         if (encode_nhwc_box_maps(encode, res, wT ? wT : 64, p.tw, p.th, p.tn, wT == 0, tmRT)) return 2;
     }
-    if (!g_attr_set) {
+    if (!(ctx->func_attr_mask & ATTR_UMMA)) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
-        g_attr_set = true;
+        ctx->func_attr_mask |= ATTR_UMMA;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles * p.ksplit, ctx->sm_count);
@@ -1545,10 +1545,10 @@ template <int S> static int launch_depthwise_tma_s(snnb_context* ctx, const Conv
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(depthwise input) failed: %d", (int) r);
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    const uint32_t attr_bit = S == 1 ? ATTR_DW1 : ATTR_DW2;
+    if (!(ctx->func_attr_mask & attr_bit)) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(depthwise_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-        attr_set = true;
+        ctx->func_attr_mask |= attr_bit;
     }
     const long long total = (long long) p.N * p.tiles_y * p.tiles_x * p.chunks;
     const int grid        = (int) std::min<long long>(total, ctx->sm_count);

@@ -136,6 +136,9 @@ struct snnb_context {
     int* splitk_counters   = nullptr;
     size_t splitk_counter_n = 0;
     int* sched_counter      = nullptr; // dynamic tile scheduler of conv_umma_kernel (self-resetting)
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: one bit per kernel, per context
+    // (= per device), not a process-wide flag
+    uint32_t func_attr_mask = 0;
     std::vector<void*> scratch_blocks;
 };
 

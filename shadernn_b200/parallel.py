@@ -63,6 +63,10 @@ def broadcast_model_weights(model, device, src=0):
     ptr, nbytes = model.weight_arena()
     t = arena_as_tensor(ptr, nbytes, device)
     broadcast_buffer(t, src)
+    # NCCL ran on torch's stream; the engine computes on its own non-blocking stream, which has no implicit ordering with it:
+    # the arena must be complete before the first forward pass reads it
+    if t.is_cuda:
+        torch.cuda.synchronize(t.device)
     return nbytes
 
 

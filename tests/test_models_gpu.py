@@ -2,9 +2,10 @@
 
 Mirrors the reference's model tests (demo/test/unittest/resnet18Test.cpp:85-198, mobilenetv2Test.cpp:82-211): dump
 every layer's output and compare it, layer by layer, with the CPU ground truth — here the oracle instead of ncnn,
-tolerance 1e-3 (abs-or-rel, the reference's comparator) instead of 0.01; classification top-1 index bit-exact.
-Sizes are kept small enough for the oracle to finish in seconds; BASELINE-size runs are checked through
-size-independent properties (batch consistency, fused == unfused, CUDA-graph replay == eager).
+tolerance 1e-3 of each tensor's range (assert_layer_close) instead of the reference's 0.01; classification top-1 index
+bit-exact. The BASELINE.json configurations are checked AT THEIR SIZE (every layer of a sample of the batch, fused and
+unfused, soft-max outputs and pre-soft-max logits) as well as through size-independent properties (batch consistency,
+fused == unfused, CUDA-graph replay == eager).
 """
 import os
 
@@ -32,6 +33,47 @@ def assert_same_boxes(got, ref, tol=3e-3):
                 break
 
 
+def assert_layer_close(got, want, eps, what):
+    """THE parity criterion (north_star: "within 1e-3 relative fp32 per layer"): the largest absolute difference of a layer's
+    output is at most eps times the largest magnitude of the reference output, i.e. error relative to the tensor's range.
+    Nothing else passes a layer (round 1 also accepted "no element outside the reference's abs-or-rel comparator")."""
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = float(np.abs(want).max())
+    err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max())
+    assert err <= eps * max(scale, 1e-30), "%s: max |err| %.3g = %.3g of the tensor's range %.3g (limit %g)" % (what, err, err / max(scale, 1e-30), scale, eps)
+    return err / max(scale, 1e-30)
+
+
+def baseline_size_check(ctx, name, hw, batch, sample, model_dir, fuse, eps=EPS, min_layers=0, **build_kw):
+    """Per-layer parity AT BASELINE.json's size (demo/test/unittest/resnet18Test.cpp:85-198 compares its 20 checkpoints at the
+    real input size): the engine runs the full batch, the oracle the first `sample` images of the same batch; every layer
+    output the engine can show (all of them with fuse=0; with fuse=1 the tensors that survive fusion) must agree."""
+    from shadernn_b200._lib import SnnbError
+    path, layers = modelzoo.build(name, model_dir, input_hw=hw, **build_kw)
+    x = modelzoo.synthetic_input(name, batch, hw)
+    want = oracle.Model(path).run(x[:sample], return_all=True)
+    m = core.MixedInferenceCore(ctx, path, batch=batch, input_hw=hw, fuse=fuse, use_cuda_graph=fuse)
+    m.set_input(x)
+    m.forward()
+    ctx.sync()
+    worst, compared = 0.0, 0
+    for i in range(m.num_layers):
+        lname, ltype, shape = m.layer_info(i)
+        if ltype == "YOLO":
+            continue
+        try:
+            got = m.layer_output(i)
+        except SnnbError:
+            assert fuse, lname  # only fusion may hide a layer
+            continue
+        if fuse and layers[i]["type"] in ("ZeroPadding2D", "Flatten"):
+            continue  # fused away: an alias of the producer's tensor (a folded Pad, the Flatten of a 1x1 map)
+        worst = max(worst, assert_layer_close(got[:sample], want[i], eps, lname))
+        compared += 1
+    assert compared >= min_layers, (compared, min_layers)
+    return m, x, want, worst
+
+
 def layerwise_check(ctx, name, hw, batch, model_dir, eps=EPS, **build_kw):
     path, layers = modelzoo.build(name, model_dir, input_hw=hw, **build_kw)
     x = modelzoo.synthetic_input(name, batch, hw)
@@ -50,12 +92,7 @@ def layerwise_check(ctx, name, hw, batch, model_dir, eps=EPS, **build_kw):
             continue
         assert shape == want[i].shape, (lname, shape, want[i].shape)
         got = m.layer_output(i)
-        bad = oracle.compare(got, want[i], eps)
-        scale = max(1.0, float(np.abs(want[i]).max()))
-        # cumulative drift through the network is allowed to reach eps relative to the tensor's range
-        err = float(np.abs(got - want[i]).max()) / scale
-        worst = max(worst, err)
-        assert bad == 0 or err < eps, "%s: %d/%d elements outside eps=%g (max err/scale %.3g)" % (lname, bad, got.size, eps, err)
+        worst = max(worst, assert_layer_close(got, want[i], eps, lname))
     return m, om, x, want, worst
 
 
@@ -76,15 +113,50 @@ def test_resnet18_layerwise_and_top1(ctx, model_dir):
     assert np.allclose(out.sum(axis=-1), 1.0, atol=1e-4)  # softmax rows
 
 
-def test_resnet18_224_top1_vs_oracle(ctx, model_dir):
-    # the BASELINE shape (224x224x3) on a small batch: top-1 must agree image by image
-    path, _ = modelzoo.build("resnet18", model_dir, input_hw=(224, 224))
-    x = modelzoo.synthetic_input("resnet18", 2, (224, 224))
-    want = oracle.Model(path).run(x)
-    m = core.MixedInferenceCore(ctx, path, batch=2, fuse=True, use_cuda_graph=True)
+@pytest.mark.parametrize("fuse", [False, True])
+def test_resnet18_baseline_size_every_layer(ctx, model_dir, fuse):
+    # BASELINE.json configs[1]: ResNet-18 224x224x3, batch 32. Every layer of a 4-image sample vs the oracle, fuse=0 and fuse=1
+    m, x, want, worst = baseline_size_check(ctx, "resnet18", (224, 224), 32, 4, model_dir, fuse, min_layers=20 if fuse else 33)
     out, cls = m.run(x)
-    assert np.array_equal(cls, oracle.argmax1(want))
-    assert oracle.compare(out, want, EPS) == 0
+    assert np.array_equal(cls[:4], oracle.argmax1(want[-1]))
+    assert len(set(cls.tolist())) >= 5, cls  # the arg-max is decided by the image (round 1: one constant class)
+    assert float(out.max()) < 0.999  # ... and the soft-max is not saturated
+    assert worst < 2e-4
+
+
+def test_resnet18_baseline_size_logits(ctx, model_dir):
+    # the pre-soft-max logits of the same graph, all 32 images (the oracle needs ~1.5 s per 8 images on 8 cores)
+    path, _ = modelzoo.build("resnet18", model_dir + "/lin", input_hw=(224, 224), head_activation="linear")
+    x = modelzoo.synthetic_input("resnet18", 32, (224, 224))
+    want = oracle.Model(path).run(x).reshape(32, 10)
+    m = core.MixedInferenceCore(ctx, path, batch=32, fuse=True, use_cuda_graph=True)
+    out, cls = m.run(x)
+    rel = assert_layer_close(out.reshape(32, 10), want, EPS, "ResNet-18 logits")
+    assert rel < 2e-4
+    assert np.array_equal(cls - 1, want.argmax(1))
+    assert len(set(want.argmax(1).tolist())) >= 5
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_mobilenetv2_baseline_size_every_layer(ctx, model_dir, fuse):
+    # BASELINE.json configs[2]: MobileNetV2 224x224x3, batch 64 (1000 classes); 2-image sample
+    m, x, want, worst = baseline_size_check(ctx, "mobilenetv2", (224, 224), 64, 2, model_dir, fuse, min_layers=50 if fuse else 72)
+    out, cls = m.run(x)
+    assert np.array_equal(cls[:2], oracle.argmax1(want[-1]))
+    assert len(set(cls.tolist())) >= 8, cls
+    assert worst < 2e-4
+
+
+def test_yolov3tiny_baseline_size_every_layer(ctx, model_dir):
+    # BASELINE.json configs[3]: YOLOv3-tiny 416x416x3, batch 16; 1-image sample
+    baseline_size_check(ctx, "yolov3tiny", (416, 416), 16, 1, model_dir, False, min_layers=20)
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_candy_baseline_size_every_layer(ctx, model_dir, fuse):
+    # BASELINE.json configs[4]'s per-GPU shard: Candy 720x720x3, one image (inputs in [0,255])
+    m, x, want, worst = baseline_size_check(ctx, "candy", (720, 720), 1, 1, model_dir, fuse, min_layers=35)
+    assert worst < 2e-4
 
 
 def test_mobilenetv2_layerwise(ctx, model_dir):
@@ -119,7 +191,7 @@ def test_yolo_decode_with_planted_detection(ctx, model_dir):
 
 def test_candy_layerwise(ctx, model_dir):
     # reflect padding, instance norm, nearest upsample, residual adds; inputs in [0,255]
-    layerwise_check(ctx, "candy", (64, 64), 1, model_dir, eps=2e-3)
+    layerwise_check(ctx, "candy", (64, 64), 1, model_dir)
 
 
 @pytest.mark.parametrize("name,hw,kw", [("resnet18", (96, 96), {}), ("mobilenetv2", (96, 96), {"classes": 50}), ("candy", (48, 48), {})])
@@ -189,6 +261,17 @@ def test_model_error_paths(ctx, tmp_path):
     with pytest.raises(SnnbError) as e:
         core.MixedInferenceCore(ctx, str(bad))
     assert "Not found layer" in str(e.value)  # layerFactory.cpp:155-157
+    # declared planes that disagree with the graph are load errors, not device faults
+    import json
+    path, _ = modelzoo.build("espcn", str(tmp_path), input_hw=(32, 32))
+    root = json.load(open(path))
+    root["Layer_2"]["inputPlanes"] = 8  # the producer has 16 channels; weights shrunk to match the declaration
+    root["Layer_2"]["weights"]["kernel"] = root["Layer_2"]["weights"]["kernel"][:16 * 8 * 9]
+    lie = tmp_path / "lie.json"
+    lie.write_text(json.dumps(root))
+    with pytest.raises(SnnbError) as e:
+        core.MixedInferenceCore(ctx, str(lie), input_hw=(32, 32))
+    assert "inputPlanes" in str(e.value)
     trunc = tmp_path / "trunc.json"
     trunc.write_text('{"numLayers": {"count": 2}')
     with pytest.raises(SnnbError):

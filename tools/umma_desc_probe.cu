@@ -12,7 +12,7 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(128, 1) probe(uint64_t desc_hi_bits, uint32_t a_byte_off, int b_swizzled, float* out) {
+__global__ void __launch_bounds__(128, 1) probe(uint64_t desc_hi_bits, uint32_t a_byte_off, int b_swizzled, float* out, int b_fp16 = 0) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen        = smem_raw + (base - smem_u32(smem_raw));
@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(128, 1) probe(uint64_t desc_hi_bits, uint32_t 
         // B stored as SW128 K-major rows of 128 B: row n, chunk c = k/8 at physical chunk c ^ (n & 7)
         const int chunk = k / 8, phys = b_swizzled ? (chunk ^ (n & 7)) : chunk;
         B[n * 64 + phys * 8 + (k & 7)] = __float2bfloat16(1.0f);
+        // (3) mixed operand formats: B holds the FP16 value 1 + 2^-10 (0x3C01; read as bf16 it would be ~0.0079)
+        if (b_fp16) reinterpret_cast<uint16_t*>(B)[n * 64 + phys * 8 + (k & 7)] = 0x3C01;
     }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(128, 1) probe(uint64_t desc_hi_bits, uint32_t 
     if (threadIdx.x == 0) {
         const uint64_t a_desc = desc_hi_bits | (uint64_t) (((base + a_byte_off) >> 4) & 0x3FFFu);
         const uint64_t b_desc = (uint64_t) (((base + 49152) >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-        const uint32_t idesc  = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (16 >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+        // a_format bits [7,10), b_format bits [10,13): 0 = F16, 1 = BF16
+        const uint32_t idesc  = (1u << 4) | (1u << 7) | ((b_fp16 ? 0u : 1u) << 10) | ((uint32_t) (16 >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(a_desc), "l"(b_desc),
                      "r"(idesc), "r"(0u)
                      : "memory");
@@ -93,10 +96,31 @@ static void run(const char* what, uint64_t hi_bits, uint32_t a_off, float* d) {
     printf("\n");
 }
 
+static void run_mixed(float* d) {
+    const uint64_t SW128 = (1ull << 16) | (1ull << 46) | (2ull << 61);
+    probe<<<1, 128, 60 * 1024>>>(SW128 | (64ull << 32), 0, 1, d, 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("MIXED bf16(A) x fp16(B): ERROR %s\n", cudaGetErrorString(e));
+        exit(1);
+    }
+    float h[512];
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    int ok = 1;
+    printf("MIXED A = bf16, B = fp16 (idesc a_format 1, b_format 0): D[m][0] vs (piece & 255) * (1 + 2^-10):");
+    for (int m = 0; m < 128; ++m) {
+        const float want = (float) ((m * 8 + (0 ^ (m & 7))) & 255) * (1.0f + 1.0f / 1024.0f);
+        if (m < 6) printf(" m%d: %.6f (want %.6f)", m, h[m * 4 + 0], want);
+        if (h[m * 4 + 0] != want) ok = 0;
+    }
+    printf("\n  => mixed-format MMA %s\n", ok ? "EXACT: legal and computed as fp16 x bf16" : "MISMATCH");
+}
+
 int main() {
     float* d;
     cudaMalloc(&d, 512 * sizeof(float));
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+    run_mixed(d);
     const uint64_t SW128 = (1ull << 16) | (1ull << 46) | (2ull << 61);
     // (1) SWIZZLE_128B: aligned reference, then start shifted by r0 rows with and without base_offset, SBO = 1024 and 2048
     run("SW128 start+0 rows, SBO 1024, base_offset 0 (reference: row m chunk c -> piece m*8 + (c ^ (m&7)))", SW128 | (64ull << 32), 0, d);
