@@ -13,8 +13,8 @@
  * Tensor layout at this boundary: host fp32, either NHWC (N added — the reference is N==1) or the
  * reference's own texture layout "C4HW4" (core/inc/snn/imageTexture.h; element (x,y,c) at
  * (((c/4)*H + y)*W + x)*4 + c%4, demo/common/shaderUnitTest.cpp:87-131). Device storage is private:
- * two bf16 planes (hi, lo = value - hi) in NHWC with the channel pitch padded to 8 — an fp32-faithful
- * (17 significant bits) format that TMA can feed straight to tcgen05 tensor cores.
+ * two fp16 planes (hi, lo = value - hi) in NHWC with the channel pitch padded to 8 — an fp32-faithful
+ * (22 significant bits, range +-65504) format that TMA can feed straight to tcgen05 tensor cores.
  */
 #ifndef SNNB_H_
 #define SNNB_H_
@@ -40,6 +40,14 @@ enum { SNNB_ACT_NONE = 0, SNNB_ACT_RELU = 1, SNNB_ACT_RELU6 = 2, SNNB_ACT_TANH =
 enum { SNNB_PAD_NONE = 0, SNNB_PAD_CONSTANT = 1, SNNB_PAD_REPLICATE = 2, SNNB_PAD_REFLECT = 3 };
 /* Kernel selection for convolutions. AUTO picks the tcgen05 implicit-GEMM path when the shape allows. */
 enum { SNNB_ALGO_AUTO = 0, SNNB_ALGO_SIMT = 1, SNNB_ALGO_TCGEN05 = 2 };
+/* Arithmetic / storage precision of the tensor-core convolution path (the reference's counterpart is
+ * ShaderGenOptions::preferrHalfPrecision, core/inc/snn/layeroption.h:43: fp32 by default, RGBA16F when set).
+ *   FP32X3: activations AND weights as fp16 hi+lo pairs, three fp16 MMAs per product: fp32-class (~22 bits per operand).
+ *   FP16W : activations as fp16 hi+lo pairs, weights rounded once to fp16 (<= 2^-12 relative per weight), two MMAs per product.
+ *   FP16  : the half-precision storage mode (= the reference's RGBA16F textures): one fp16 plane per tensor and per weight,
+ *           one MMA per product, half the bytes. Meets the reference's half-precision tolerance (0.1,
+ *           demo/common/testutil.h:1195), NOT the 1e-3 fp32 bar. */
+enum { SNNB_PRECISION_FP32X3 = 0, SNNB_PRECISION_FP16W = 1, SNNB_PRECISION_FP16 = 2 };
 
 /* ---- context / errors -------------------------------------------------------------------------------------- */
 /* dp::BackendBuilder::build (core/src/ic2/backendBuilder.cpp:28-50) + context creation (core/src/contextFactory.cpp). */
@@ -54,6 +62,9 @@ const char* snnb_last_error(void);
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 uint64_t snnb_launch_count(snnb_context* ctx);
 int snnb_version(void);
+/* Default precision of per-operator convolution launches on this context (SNNB_PRECISION_FP32X3 or _FP16W; models carry
+ * their own in snnb_model_options). */
+int snnb_context_set_precision(snnb_context* ctx, int precision);
 
 /* ---- tensors ------------------------------------------------------------------------------------------------ */
 /* ImageTextureAllocator / ImageTexture::resetTexture + upload()/download() (imageTexture.h:60-147). */
@@ -158,6 +169,7 @@ typedef struct {
     int conv_algo;      /* SNNB_ALGO_*: AUTO by default */
     int use_cuda_graph; /* replay the captured forward pass instead of re-launching kernels */
     int fuse;           /* graph-level fusion passes (conv+add+act, pad->conv); 0 keeps 1 kernel per reference layer */
+    int precision;      /* SNNB_PRECISION_*; FP16 = the reference's preferrHalfPrecision (layeroption.h:43) */
 } snnb_model_options;
 
 /* MixedInferenceCore::create(ctx, modelFileName, options) (core.h:115-116) = dp::loadFromJsonModel (dp.cpp:115-167:

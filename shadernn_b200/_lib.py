@@ -39,6 +39,7 @@ class ModelOptions(C.Structure):
         ("conv_algo", C.c_int),
         ("use_cuda_graph", C.c_int),
         ("fuse", C.c_int),
+        ("precision", C.c_int),
     ]
 
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "snnb_sync": (C.c_int, [vp]),
     "snnb_context_stream": (vp, [vp]),
     "snnb_launch_count": (C.c_uint64, [vp]),
+    "snnb_context_set_precision": (C.c_int, [vp, C.c_int]),
     "snnb_tensor_alloc": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "snnb_tensor_free": (C.c_int, [vp]),
     "snnb_tensor_dims": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, c_int_p]),

@@ -19,6 +19,7 @@ ACT = {"": 0, "linear": 0, "identity": 0, "none": 0, "relu": 1, "relu6": 2, "tan
        "softmax": 7}
 PAD_MODE = {"": 0, "none": 0, "constant": 1, "replicate": 2, "reflect": 3}
 ALGO = {"auto": 0, "simt": 1, "tcgen05": 2}
+PRECISION = {"fp32x3": 0, "fp16w": 1, "fp16": 2}
 
 
 def _f32(a):
@@ -37,6 +38,10 @@ class GpuContext:
 
     def sync(self):
         check(lib().snnb_sync(self.h), "snnb_sync")
+
+    def set_precision(self, precision):
+        """Default product form of per-operator convolution launches: "fp32x3" (three bf16 MMAs) or "fp16w" (fp16 weights, two)."""
+        check(lib().snnb_context_set_precision(self.h, PRECISION[precision]), "snnb_context_set_precision")
 
     @property
     def stream(self):
@@ -307,11 +312,11 @@ def subpixel(ctx, x, r):
 class MixedInferenceCore:
     """snn::MixedInferenceCore: create(ctx, modelFileName, options) then run(images)."""
 
-    def __init__(self, ctx, json_path, batch=1, input_hw=None, conv_algo="auto", use_cuda_graph=False, fuse=False):
+    def __init__(self, ctx, json_path, batch=1, input_hw=None, conv_algo="auto", use_cuda_graph=False, fuse=False, precision="fp32x3"):
         self.ctx = ctx
         self.batch = int(batch)
         opt = ModelOptions(self.batch, int(input_hw[1]) if input_hw else 0, int(input_hw[0]) if input_hw else 0, ALGO[conv_algo], int(bool(use_cuda_graph)),
-                           int(bool(fuse)))
+                           int(bool(fuse)), PRECISION[precision])
         self.h = vp()
         check(lib().snnb_model_load_json(ctx.h, json_path.encode(), C.byref(opt), C.byref(self.h)), "snnb_model_load_json")
 

@@ -53,9 +53,9 @@ int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** ou
     t->n = n, t->h = h, t->w = w, t->c = c, t->cp = round_up(c, 8);
     size_t elems   = (size_t) n * h * w * t->cp;
     t->plane_elems = (elems + 63) / 64 * 64;
-    SNNB_CUDA_OK(cudaMalloc(&t->hi, t->plane_elems * 2 * sizeof(__nv_bfloat16)));
+    SNNB_CUDA_OK(cudaMalloc(&t->hi, t->plane_elems * 2 * sizeof(__half)));
     t->lo = t->hi + t->plane_elems;
-    SNNB_CUDA_OK(cudaMemsetAsync(t->hi, 0, t->plane_elems * 2 * sizeof(__nv_bfloat16), ctx->stream));
+    SNNB_CUDA_OK(cudaMemsetAsync(t->hi, 0, t->plane_elems * 2 * sizeof(__half), ctx->stream));
     *out = t.release();
     return 0;
 }
@@ -69,6 +69,11 @@ using namespace snnb;
 extern "C" {
 
 int snnb_version(void) { return SNNB_VERSION; }
+int snnb_context_set_precision(snnb_context* ctx, int precision) {
+    SNNB_REQUIRE(ctx && (precision == SNNB_PRECISION_FP32X3 || precision == SNNB_PRECISION_FP16W), "snnb_context_set_precision: FP32X3 or FP16W (FP16 storage is a model option)");
+    ctx->precision = precision;
+    return 0;
+}
 const char* snnb_last_error(void) { return get_error(); }
 
 int snnb_context_create(int device, snnb_context** out) {

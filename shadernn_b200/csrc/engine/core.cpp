@@ -194,9 +194,9 @@ bool MixedInferenceCore::init(std::string& err) {
             // weights are not packed yet: probe with a weights stub that says "tensor path available"
             int ph = 0, pw = 0;
             snnb_weights probe_w;
-            probe_w.w_hi = probe_w.w_lo = reinterpret_cast<__nv_bfloat16*>(1);
+            probe_w.w_hi = probe_w.w_lo = reinterpret_cast<__half*>(1);
             // ... and the row-window operand a pre-padded small-channel stem will be packed with (stride, pad 0; packWeights)
-            probe_w.w_row_hi = probe_w.w_row_lo = reinterpret_cast<__nv_bfloat16*>(1);
+            probe_w.w_row_hi = probe_w.w_row_lo = reinterpret_cast<__half*>(1);
             probe_w.row_stride = (int) cl->_desc.stride, probe_w.row_pad = 0;
             std::swap(cl->weights, probe_w);
             const bool prepad = cl->wantsPrepad(L->inputs[0], L->output, options.convAlgo, ph, pw);
@@ -369,7 +369,7 @@ bool MixedInferenceCore::init(std::string& err) {
 
 int MixedInferenceCore::enqueueForward(bool) {
     ExecOptions eo;
-    eo.convAlgo = options.convAlgo;
+    eo.convAlgo = options.convAlgo, eo.precision = options.precision;
     for (auto* L : graph.sorted) {
         if (L->fusedAway || L->isInputLayer || L->typeName == "YOLO") continue;
         if (int rc = L->run(ctx, eo)) return rc;
@@ -526,7 +526,7 @@ int MixedInferenceCore::timeLayers(std::vector<float>& ms) {
     std::vector<cudaEvent_t> ev(graph.sorted.size() + 1);
     for (auto& e : ev) SNNB_CUDA_OK(cudaEventCreate(&e));
     ExecOptions eo;
-    eo.convAlgo = options.convAlgo;
+    eo.convAlgo = options.convAlgo, eo.precision = options.precision;
     SNNB_CUDA_OK(cudaEventRecord(ev[0], ctx->stream));
     for (size_t i = 0; i < graph.sorted.size(); ++i) {
         GenericModelLayer* L = graph.sorted[i];

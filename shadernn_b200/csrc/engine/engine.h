@@ -8,7 +8,7 @@
 //   snn::MixedInferenceCore         core/inc/snn/core.h, core/src/ic2/core.cpp   stage list, init, run
 //   snn::dp::CudaBackend            (new) backend.h's DeviceBackend role  streams, graphs, timers, dumps
 //
-// What differs by design: a batch dimension N, NHWC split-bf16 device tensors, weights BN-folded and packed once
+// What differs by design: a batch dimension N, NHWC split-fp16 device tensors, weights BN-folded and packed once
 // into a single device arena, one CUDA kernel launch per layer (fewer with fusion), optional CUDA-graph replay.
 #pragma once
 
@@ -279,9 +279,11 @@ struct ShaderGenOptions { // layeroption.h:27-48, trimmed to what a CUDA backend
     int convAlgo               = SNNB_ALGO_AUTO;
     bool fuse                  = false;
     bool useCudaGraph          = false;
+    int precision              = SNNB_PRECISION_FP32X3; // layeroption.h:43 preferrHalfPrecision <-> SNNB_PRECISION_FP16
 };
 struct ExecOptions {
-    int convAlgo = SNNB_ALGO_AUTO;
+    int convAlgo  = SNNB_ALGO_AUTO;
+    int precision = SNNB_PRECISION_FP32X3;
 };
 
 std::vector<std::shared_ptr<GenericModelLayer>> loadFromJsonModel(const std::string& fileName); // dp.cpp:115-167

@@ -100,6 +100,7 @@ int Conv2DLayer::run(snnb_context* ctx, const ExecOptions& opt) {
         if (launch_pad(ctx, inputs[0], prepadded, (int) offs[0], (int) offs[2], padModeId(_desc.padding.mode))) return 1;
         ConvArgs a {prepadded, residual, output, &weights, (int) _desc.kernelSize, (int) _desc.stride, 0, 0, SNNB_PAD_CONSTANT,
                     fusedAct >= 0 ? fusedAct : _desc.activation.id, fusedAct >= 0 ? fusedAlpha : _desc.activation.alpha};
+        a.precision = opt.precision;
         return launch_conv2d_umma(ctx, a);
     }
     ConvArgs a;
@@ -111,6 +112,7 @@ int Conv2DLayer::run(snnb_context* ctx, const ExecOptions& opt) {
     a.pad_mode = padModeId(_desc.padding.mode);
     a.act      = fusedAct >= 0 ? fusedAct : _desc.activation.id;
     a.alpha    = fusedAct >= 0 ? fusedAlpha : _desc.activation.alpha;
+    a.precision = opt.precision;
     const int want = algo != SNNB_ALGO_AUTO ? algo : opt.convAlgo;
     if (want != SNNB_ALGO_SIMT && conv2d_umma_supported(a)) return launch_conv2d_umma(ctx, a);
     if (want == SNNB_ALGO_TCGEN05) {
@@ -199,7 +201,7 @@ void DenseLayer::packWeights(PackedHost& p) {
     p.kind = 3;
     std::vector<float>().swap(kernel);
 }
-int DenseLayer::run(snnb_context* ctx, const ExecOptions&) {
+int DenseLayer::run(snnb_context* ctx, const ExecOptions& opt) {
     if (gapSource && gapSource->output && gap_dense_supported(gapSource->output, output, &weights))
         return launch_gap_dense(ctx, gapSource->output, output, &weights, activation.id == SNNB_ACT_SOFTMAX ? SNNB_ACT_NONE : activation.id, activation.alpha,
                                 activation.id == SNNB_ACT_SOFTMAX);
@@ -210,6 +212,7 @@ int DenseLayer::run(snnb_context* ctx, const ExecOptions&) {
     }
     const bool softmax = activation.id == SNNB_ACT_SOFTMAX;
     ConvArgs a {x, nullptr, output, &weights, 1, 1, 0, 0, SNNB_PAD_NONE, softmax ? SNNB_ACT_NONE : activation.id, activation.alpha};
+    a.precision = opt.precision;
     // SiLU on the CPU Dense path is a by-value no-op in the reference (cpulayer.h:245-252); we apply the real SiLU.
     if (conv2d_umma_supported(a) ? launch_conv2d_umma(ctx, a) : launch_conv2d_simt(ctx, a)) return 1;
     if (softmax) return launch_softmax(ctx, output, output);

@@ -27,6 +27,8 @@ int snnb_model_load_json(snnb_context* ctx, const char* json_path, const snnb_mo
         o.convAlgo           = opt->conv_algo;
         o.useCudaGraph       = opt->use_cuda_graph != 0;
         o.fuse               = opt->fuse != 0;
+        o.precision          = opt->precision;
+        SNNB_REQUIRE(o.precision >= SNNB_PRECISION_FP32X3 && o.precision <= SNNB_PRECISION_FP16, "snnb_model_load_json: unknown precision %d", o.precision);
     }
     SNNB_CUDA_OK(cudaSetDevice(ctx->device));
     std::string err;

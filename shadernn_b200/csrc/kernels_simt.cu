@@ -2,7 +2,7 @@
 // and the generic direct/implicit-GEMM fp32 convolution used where the tcgen05 path does not apply
 // (IC = 3 stems, 1-channel ESPCN layers, reflect/replicate padding).
 //
-// All activation tensors are split-bf16 NHWC (see snnb_internal.h): every kernel reads hi+lo, computes in fp32
+// All activation tensors are split-fp16 NHWC (see snnb_internal.h): every kernel reads hi+lo, computes in fp32
 // and writes hi/lo. Channel groups of 8 (= one 16-byte vector per plane) are the unit of work; channels in
 // [C, Cp) are written as zero so they never pollute a consumer.
 //
@@ -16,45 +16,38 @@
 namespace snnb {
 
 // ------------------------------------------------------------------------------------------------------------
-// split-bf16 helpers
+// split-fp16 helpers (snnb_internal.h): a 32-bit word holds two consecutive channels of one plane
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float bf16lo_to_f32(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi_to_f32(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+// (a, b) -> packed fp16 pair, round to nearest, saturated to +-65504 (one F2FP.SATFINITE.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+    return h;
+}
 
 // 8 channels: v[i] = hi[i] + lo[i]
 __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float v[8]) {
-    v[0] = bf16lo_to_f32(h.x) + bf16lo_to_f32(l.x);
-    v[1] = bf16hi_to_f32(h.x) + bf16hi_to_f32(l.x);
-    v[2] = bf16lo_to_f32(h.y) + bf16lo_to_f32(l.y);
-    v[3] = bf16hi_to_f32(h.y) + bf16hi_to_f32(l.y);
-    v[4] = bf16lo_to_f32(h.z) + bf16lo_to_f32(l.z);
-    v[5] = bf16hi_to_f32(h.z) + bf16hi_to_f32(l.z);
-    v[6] = bf16lo_to_f32(h.w) + bf16lo_to_f32(l.w);
-    v[7] = bf16hi_to_f32(h.w) + bf16hi_to_f32(l.w);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = h2_to_f2(hh[j]), b = h2_to_f2(ll[j]);
+        v[2 * j] = a.x + b.x, v[2 * j + 1] = a.y + b.y;
+    }
 }
-__device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t off, float v[8]) {
+__device__ __forceinline__ void load8(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off, float v[8]) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
     const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
-    v[0] = bf16lo_to_f32(h.x) + bf16lo_to_f32(l.x);
-    v[1] = bf16hi_to_f32(h.x) + bf16hi_to_f32(l.x);
-    v[2] = bf16lo_to_f32(h.y) + bf16lo_to_f32(l.y);
-    v[3] = bf16hi_to_f32(h.y) + bf16hi_to_f32(l.y);
-    v[4] = bf16lo_to_f32(h.z) + bf16lo_to_f32(l.z);
-    v[5] = bf16hi_to_f32(h.z) + bf16hi_to_f32(l.z);
-    v[6] = bf16lo_to_f32(h.w) + bf16lo_to_f32(l.w);
-    v[7] = bf16hi_to_f32(h.w) + bf16hi_to_f32(l.w);
+    unpack8(h, l, v);
 }
 
 __device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-    h                 = *reinterpret_cast<uint32_t*>(&hh);
-    float ra          = a - bf16lo_to_f32(h);
-    float rb          = b - bf16hi_to_f32(h);
-    __nv_bfloat162 ll = __floats2bfloat162_rn(ra, rb);
-    l                 = *reinterpret_cast<uint32_t*>(&ll);
+    h               = f2_to_h2(a, b);
+    const float2 hf = h2_to_f2(h);
+    l               = f2_to_h2(a - hf.x, b - hf.y);
 }
 
-__device__ __forceinline__ void store8(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t off, const float v[8]) {
+__device__ __forceinline__ void store8(__half* __restrict__ hi, __half* __restrict__ lo, size_t off, const float v[8]) {
     uint4 h, l;
     split2(v[0], v[1], h.x, l.x);
     split2(v[2], v[3], h.y, l.y);
@@ -64,13 +57,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* __restrict__ hi, __nv_bflo
     *reinterpret_cast<uint4*>(lo + off) = l;
 }
 
-__device__ __forceinline__ float load1(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t off) {
-    return __bfloat162float(hi[off]) + __bfloat162float(lo[off]);
+__device__ __forceinline__ float load1(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off) {
+    return __half2float(hi[off]) + __half2float(lo[off]);
 }
-__device__ __forceinline__ void store1(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t off, float v) {
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[off]         = h;
-    lo[off]         = __float2bfloat16_rn(v - __bfloat162float(h));
+__device__ __forceinline__ void store1(__half* __restrict__ hi, __half* __restrict__ lo, size_t off, float v) {
+    uint32_t h, l;
+    split2(v, 0.0f, h, l);
+    hi[off] = __ushort_as_half((unsigned short) (h & 0xffffu));
+    lo[off] = __ushort_as_half((unsigned short) (l & 0xffffu));
 }
 
 // Activations: ids of conv2dVulkan.cpp:57-71; math of shadertemplate_vk_conv2d.comp:290-340 (SiLU computed
@@ -103,8 +97,8 @@ __device__ __forceinline__ int src_coord(int s, int n, int mode) {
 }
 
 struct TV { // kernel-side tensor view
-    __nv_bfloat16* hi;
-    __nv_bfloat16* lo;
+    __half* hi;
+    __half* lo;
     int N, H, W, C, Cp;
 };
 static TV view(const snnb_tensor* t) { return TV {t->hi, t->lo, t->n, t->h, t->w, t->c, t->cp}; }
@@ -123,7 +117,7 @@ static TV view(const snnb_tensor* t) { return TV {t->hi, t->lo, t->n, t->h, t->w
 // Conv2D, fp32 CUDA-core implicit GEMM (shadertemplate_vk_conv2d.comp:148-347; 1x1: vk_conv2d_1x1.comp:68-211).
 //   M = N*OH*OW pixels, Ngemm = OC, K = k*k*IC with k index = (ky*k + kx)*IC + ic.
 // Block tile 64 pixels x 64 oc, K chunk 16, 128 threads, 4x8 outputs per thread.
-// A is gathered from the split-bf16 input (vector path when IC % 8 == 0, scalar otherwise), B is the packed
+// A is gathered from the split-fp16 input (vector path when IC % 8 == 0, scalar otherwise), B is the packed
 // fp32 weight matrix [K][OCw] with BN folded. Epilogue: + bias (+ residual) -> activation -> split -> store.
 // ------------------------------------------------------------------------------------------------------------
 struct ConvKParams {
@@ -972,7 +966,7 @@ int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// API edge: fp32 NHWC (dense pitch C) <-> split-bf16 (pitch Cp).
+// API edge: fp32 NHWC (dense pitch C) <-> split-fp16 (pitch Cp).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void split_kernel(const float* __restrict__ src, TV t) {
     pdl_wait();
@@ -987,7 +981,7 @@ __global__ void split_kernel(const float* __restrict__ src, TV t) {
     for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? __ldg(src + px * t.C + c + j) : 0.0f;
     store8(t.hi, t.lo, gid * 8, v);
 }
-// u8 image (dense pitch C) -> (x - mean[c]) * norm[c] -> split-bf16: the reference's convertToRGBA32FAndNormalize
+// u8 image (dense pitch C) -> (x - mean[c]) * norm[c] -> split-fp16: the reference's convertToRGBA32FAndNormalize
 // (core/inc/snn/imageTexture.h:114) done on the device, so only a quarter of the fp32 bytes cross PCIe.
 struct U8Norm {
     float mean[4], norm[4];

@@ -1,17 +1,18 @@
 // Conv2D (1x1 and k x k, stride 1 and 2) as an implicit GEMM on Blackwell's 5th-generation tensor
 // cores, hand-written for sm_100a: TMA (cp.async.bulk.tensor) stages NHWC activation tiles and packed weights from HBM
 // into 128B-swizzled shared memory, one elected thread issues tcgen05.mma, accumulators live in TMEM and are read back
-// with tcgen05.ld by the epilogue warps (bias + residual + activation + split-bf16 store).
+// with tcgen05.ld by the epilogue warps (bias + residual + activation + split-fp16 store).
 //
 //   D[M = 128 output pixels, N = n_blk <= 128 output channels] += A[M, K] * B[N, K]^T,   K = (tap, 64-channel block)
 //
-// fp32-faithful arithmetic out of bf16 tensor cores: activations and weights are stored as hi + lo bf16 pairs
-// (snnb_internal.h); every K block accumulates into fp32 TMEM
-//       A_hi*B_hi  +  A_lo*B_hi  +  A_hi*B_lo                      (the dropped A_lo*B_lo term is ~2^-18 relative),
-// which keeps ~16 mantissa bits per operand — far inside the 1e-3 per-layer parity budget — at 3 bf16 MMA-units per
-// product, i.e. 1.5x the cost of one TF32 pass but with fp32-class accuracy (TF32's 10-bit mantissa would not hold 1e-3).
-// The three terms are issued as TWO instructions per K=16 step: A_hi x [B_hi ; B_lo] (N = 2 n_blk, two accumulator column
-// blocks) and A_lo x B_hi (onto the first block); the epilogue adds the blocks.
+// fp32-faithful arithmetic out of fp16 tensor cores: activations and weights are stored as hi + lo fp16 pairs
+// (snnb_internal.h); every K block accumulates into fp32 TMEM, template parameter TERMS:
+//   3:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (the dropped A_lo*B_lo term is ~2^-24 relative): ~22 mantissa bits per operand. Issued
+//       as TWO instructions per K=16 step: A_hi x [B_hi ; B_lo] (N = 2 n_blk, two accumulator column blocks) and A_lo x B_hi
+//       (onto the first block); the epilogue adds the blocks. n_blk <= 128.
+//   2:  (A_hi + A_lo) * B_hi: the weights rounded ONCE to fp16 (<= 2^-12 relative per weight, measured per-layer error vs the
+//       oracle ~1e-4 of the tensor's range - inside the 1e-3 budget), two instructions, ONE accumulator block, n_blk <= 256.
+//   1:  A_hi * B_hi: the half-precision storage mode (the reference's RGBA16F), no lo planes anywhere.
 //
 // A tile = a (tw x th x tn)-pixel box of the OUTPUT grid (tw*th*tn <= 128): for filter tap (ky,kx) the producer issues
 // ONE 4-D TMA box load at input coordinate (ox0*s + kx - pad_x, oy0*s + ky - pad_y); out-of-range rows/columns are
@@ -37,12 +38,13 @@
 namespace snnb {
 
 constexpr int UM_BLOCK_M     = 128;
-constexpr int UM_BLOCK_K     = 64; // bf16 elements: 128 bytes = one SWIZZLE_128B row
-constexpr int UM_MAX_N       = 128;
+constexpr int UM_BLOCK_K     = 64; // fp16 elements: 128 bytes = one SWIZZLE_128B row
+constexpr int UM_MAX_N       = 128; // 3-term product: the accumulator holds two column blocks of n_blk
+constexpr int UM_MAX_N2      = 256; // 2-term (fp16 weights) and 1-term (fp16 storage) products: one column block
 constexpr int UM_STAGES      = 3;
 constexpr int UM_A_BYTES     = UM_BLOCK_M * 128;
 constexpr int UM_B_BYTES     = UM_MAX_N * 128;
-constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES; // A_hi, A_lo, B_hi, B_lo = 64 KB
+constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES; // A_hi, A_lo, then [B_hi ; B_lo] (3-term) or one B plane of up to 256 rows = 64 KB
 constexpr int UM_EPI_WARPS   = 8;                       // two warps per TMEM lane quarter, interleaved over 16-column chunks
 constexpr int UM_THREADS     = 64 + 32 * UM_EPI_WARPS; // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int UM_ACC_COLS    = 2 * UM_MAX_N; // one accumulator buffer: [A_hi.B_hi + A_lo.B_hi | A_hi.B_lo], up to 2 x 128 fp32 columns
@@ -52,11 +54,26 @@ constexpr int UM_SCHED_SLOTS = 8;                        // ring of work-item id
 constexpr int UM_SMEM_BYTES  = UM_STAGES * UM_STAGE_BYTES + UM_STG_BYTES + 1024 /*alignment slack*/ + 320 /*barriers + scheduler ring*/;
 constexpr int UM_SMEM_BYTES_SPLIT = (UM_STAGES - 1) * UM_STAGE_BYTES + 2 * UM_STG_BYTES + 1024 + 320; // two epilogue groups, one ring stage less
 
+// ---- halo mode (3x3, stride 1): the A operand of all nine taps comes from ONE (8+2) x (16+2)-pixel halo tile per 64-channel
+// block, loaded once by TMA; tap (ky,kx) is the same shared memory read through a descriptor whose start address is shifted
+// by (ky * 10 + kx) pixels and whose 8-row group stride (SBO) is the halo's row pitch, 10 pixels = 1280 B. Legal because both
+// the TMA unit and the tensor core apply SWIZZLE_128B to absolute shared-memory address bits (tools/umma_desc_probe.cu), so a
+// pixel row is found where TMA put it whatever the descriptor's phase. L2 -> SM traffic of A drops from 9 x 32 KB to 46 KB per
+// tile and channel block (the r01 kernel moved 363-389 MB per 56x56x64 launch against 51.5 MB algorithmic: it was bound by
+// the ~72 B/clk/SM the SM can ingest, not by the tensor pipe). The weights (one K block per tap) keep their own ring.
+constexpr int HL_TW = 8, HL_TH = 16, HL_W = HL_TW + 2, HL_H = HL_TH + 2;
+constexpr int HL_PLANE         = (HL_W * HL_H * 128 + 1023) / 1024 * 1024; // 23 552 B: one plane of the halo tile, 1024-aligned
+constexpr int HL_A_STAGES      = 2;
+constexpr int HL_A_STAGE_BYTES = 2 * HL_PLANE;
+constexpr int HL_B_STAGES      = 3;              // == the STAGES template argument of the halo instantiations
+constexpr int HL_B_STAGE_BYTES = 2 * UM_B_BYTES; // [B_hi ; B_lo] of 128 rows or one plane of up to 256 rows
+constexpr int HL_SMEM_BYTES    = HL_A_STAGES * HL_A_STAGE_BYTES + HL_B_STAGES * HL_B_STAGE_BYTES + UM_STG_BYTES + 1024 + 384;
+
 struct UmmaParams {
-    __nv_bfloat16* out_hi;
-    __nv_bfloat16* out_lo;
-    const __nv_bfloat16* res_hi;
-    const __nv_bfloat16* res_lo;
+    __half* out_hi;
+    __half* out_lo;
+    const __half* res_hi;
+    const __half* res_lo;
     const float* bias;
     int N, OH, OW, OC, OCp;
     int tw, th, tn, rows_used;
@@ -75,6 +92,7 @@ struct UmmaParams {
     int* counters;   // [tile], zero between launches (the last arriver resets it)
     long long* trace; // profiling aid (env SNNB_UMMA_TRACE): CTA 0 writes clock64 stamps per role, [6][256]
     int ablate; // profiling aid (env SNNB_UMMA_ABLATE, results are WRONG when set): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs
+    int has_lo; // the output tensor has a lo plane (0 in the fp16 storage mode)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -151,8 +169,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; issued by ONE thread for the whole CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate; issued by ONE thread for the whole CTA.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -188,10 +206,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// Same with an arbitrary stride between 8-row groups (halo mode: the halo tile's row pitch, not a multiple of 1024 B)
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t) (sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format at bits 7 / 10,
 // both operands K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+// a_format / b_format (bits [7,10) / [10,13)): 0 = F16 for both operands. (kind::f16 refuses a BF16 A with an F16 B operand:
+// "illegal instruction", tools/umma_desc_probe.cu - which is why the storage format is an fp16 pair, not round 1's bf16 pair.)
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
 }
 
 // transcendental activations only (tanh / sigmoid / SiLU): rare, kept out of line so the hot epilogue stays small
@@ -206,18 +230,22 @@ __device__ __noinline__ float umma_act(float v, int act, float alpha) {
     default: return v;
     }
 }
+// split-fp16 (snnb_internal.h): packed pair conversions, round to nearest, saturated to +-65504
+__device__ __forceinline__ float2 um_h2f(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ uint32_t um_f2h(float a, float b) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+    return h;
+}
 __device__ __forceinline__ void um_split2(float a, float b, uint32_t& h, uint32_t& l) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-    h                 = *reinterpret_cast<uint32_t*>(&hh);
-    const float ra    = a - __uint_as_float(h << 16);
-    const float rb    = b - __uint_as_float(h & 0xffff0000u);
-    __nv_bfloat162 ll = __floats2bfloat162_rn(ra, rb);
-    l                 = *reinterpret_cast<uint32_t*>(&ll);
+    h               = um_f2h(a, b);
+    const float2 hf = um_h2f(h);
+    l               = um_f2h(a - hf.x, b - hf.y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue of one output tile, shared by both tensor-core kernels: TMEM -> registers -> +bias (+residual) -> activation
-// -> split-bf16 -> SHARED MEMORY (128B-swizzled, bank-conflict-free) -> ONE TMA bulk store per plane and 64-channel slab.
+// -> split-fp16 -> SHARED MEMORY (128B-swizzled, bank-conflict-free) -> ONE TMA bulk store per plane and 64-channel slab.
 //
 // Why through smem + TMA: each thread owns one output pixel (TMEM lane), so direct global stores are 32 scattered
 // 16-byte pieces per warp instruction = 32 L1 wavefronts each; at 128 rows x n_blk channels that is 8-16 k wavefronts
@@ -230,7 +258,8 @@ struct EpiArgs {
     const CUtensorMap *o_hi64, *o_lo64, *o_hiT, *o_loT; // output maps: 64-channel slab (SWIZZLE_128B) and tail slab (dense)
     const CUtensorMap *r_hi64, *r_lo64, *r_hiT, *r_loT; // residual maps, same geometry
     const float* bias;
-    int n_blk, OC, act, has_res, rows_box; // the A_hi.B_lo partial sums sit n_blk columns after the main block
+    int n_blk, OC, act, has_res, rows_box; // 3-term: the A_hi.B_lo partial sums sit n_blk columns after the main block
+    int has_lo;                            // write (and read, for the residual) the lo plane; 0 in the fp16 storage mode
     float alpha;
     uint32_t stg;       // staging smem (hi plane; lo plane at + UM_BLOCK_M * 128)
     uint32_t res_bar;   // mbarrier for the residual TMA load
@@ -254,14 +283,14 @@ __device__ __forceinline__ void epilogue_residual_load(const EpiArgs& e, int sl,
     const uint32_t pitch = sw ? 128u : (uint32_t) w * 2u;
     if (elect_one()) {
         bulk_wait_read0();
-        mbar_expect_tx(e.res_bar, 2u * (uint32_t) e.rows_box * pitch); // the box has rows_box rows (<= 128)
+        mbar_expect_tx(e.res_bar, (e.has_lo ? 2u : 1u) * (uint32_t) e.rows_box * pitch); // the box has rows_box rows (<= 128)
         tma_load_4d(e.stg, sw ? e.r_hi64 : e.r_hiT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
-        tma_load_4d(e.stg + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
+        if (e.has_lo) tma_load_4d(e.stg + UM_BLOCK_M * 128, sw ? e.r_lo64 : e.r_loT, e.res_bar, oc0 + sl * 64, c1, c2, c3);
     }
     __syncwarp();
 }
 
-template <int NWARPS>
+template <int NWARPS, int TERMS>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, int oc0, int c1, int c2, int c3, int row, int half, bool leader, int lane,
                                               uint32_t& res_phase) {
     constexpr int MAXC  = NWARPS == 8 ? 2 : 4; // 16-column chunks of one 64-column slab owned by this warp
@@ -283,7 +312,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
         const uint32_t xr    = sw ? (uint32_t) (row & 7) : 0u;
         const int slab_oc    = oc0 + sl * 64;
         if (e.has_res && sl > 0) epilogue_residual_load(e, sl, oc0, c1, c2, c3, leader); // slab 0's was issued before the accumulator wait
-        // ---- phase 1: TMEM -> registers -> bias (+ residual) -> activation -> packed split-bf16, nothing written yet ----
+        // ---- phase 1: TMEM -> registers -> bias (+ residual) -> activation -> packed split-fp16, nothing written yet ----
         bool res_ready = false;
 #pragma unroll
         for (int k0 = 0; k0 < MAXC; k0 += 2) { // two chunks at a time: their four TMEM loads are in flight together
@@ -318,7 +347,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                         for (int j = 0; j < 16; ++j) r[kk][j] = __float_as_uint(a16[j]), r2[kk][j] = 0u;
                     } else {
                         tmem_ld16(taddr + (uint32_t) c, r[kk]);
-                        tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2[kk]);
+                        if (TERMS == 3) {
+                            tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2[kk]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r2[kk][j] = 0u; // one column block: folded away by the compiler
+                        }
                     }
                 }
             }
@@ -347,11 +381,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                             const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
                             uint32_t hh[4], ll[4];
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]) : "r"(a));
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(a + UM_BLOCK_M * 128));
+                            if (e.has_lo) {
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(a + UM_BLOCK_M * 128));
+                            } else {
+                                ll[0] = ll[1] = ll[2] = ll[3] = 0u;
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                v[g * 8 + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-                                v[g * 8 + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+                                const float2 rh = um_h2f(hh[j]), rl = um_h2f(ll[j]);
+                                v[g * 8 + 2 * j] += rh.x + rl.x;
+                                v[g * 8 + 2 * j + 1] += rh.y + rl.y;
                             }
                         }
                     }
@@ -398,9 +437,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                         const uint32_t a = srow + ((((uint32_t) (ci * 2 + g)) ^ xr) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[kk][4 * g]), "r"(oh[kk][4 * g + 1]), "r"(oh[kk][4 * g + 2]), "r"(oh[kk][4 * g + 3])
                                      : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[kk][4 * g]), "r"(ol[kk][4 * g + 1]), "r"(ol[kk][4 * g + 2]),
-                                     "r"(ol[kk][4 * g + 3])
-                                     : "memory");
+                        if (e.has_lo)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + UM_BLOCK_M * 128), "r"(ol[kk][4 * g]), "r"(ol[kk][4 * g + 1]), "r"(ol[kk][4 * g + 2]),
+                                         "r"(ol[kk][4 * g + 3])
+                                         : "memory");
                     }
                 }
             }
@@ -413,7 +453,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
         if (leader) {
             if (elect_one()) {
                 tma_store_4d(sw ? e.o_hi64 : e.o_hiT, e.stg, slab_oc, c1, c2, c3);
-                tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
+                if (e.has_lo) tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
                 bulk_commit();
             }
             __syncwarp();
@@ -424,12 +464,17 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
 }
 // Split-K: write this work item's raw fp32 accumulator tile (both column blocks added) to global memory, laid out
 // [16-column chunk][float4 index][row][4 floats] so that every warp access is 512 contiguous bytes.
-template <int NWARPS>
+template <int NWARPS, int TERMS>
 __device__ __forceinline__ void epilogue_dump_partial(const EpiArgs& e, uint32_t taddr, float* dst, int row, int half, int lane) {
     for (int c = (NWARPS == 8 ? half : 0) * 16; c < e.n_blk; c += (NWARPS == 8 ? 32 : 16)) {
         uint32_t r[16], r2[16];
         tmem_ld16(taddr + (uint32_t) c, r);
-        tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2);
+        if (TERMS == 3) {
+            tmem_ld16(taddr + (uint32_t) (e.n_blk + c), r2);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r2[j] = 0u;
+        }
         tmem_ld_wait();
         float4* d = reinterpret_cast<float4*>(dst) + (size_t) (c >> 4) * 4 * UM_BLOCK_M + row; // [chunk][j4][row][4 floats]
 #pragma unroll
@@ -463,7 +508,10 @@ __device__ __forceinline__ void epilogue_drain(bool leader) {
 // barrier and bulk-store queue, so one group's barrier / TMA-store latencies overlap the other group's arithmetic. Used for
 // layers with a short K loop (1x1 convolutions), which run at the speed of the epilogue; pays for the second staging buffer
 // with one ring stage (2 instead of 3).
-template <int STAGES, bool SPLIT_EPI>
+// TERMS: how the fp32-faithful product is formed. 3 = A_hi x [B_hi ; B_lo] + A_lo x B_hi (fp16 weight pair, accumulator of two
+// column blocks, n_blk <= 128); 2 = (A_hi + A_lo) x B16 with ONE fp16 weight plane (one column block, n_blk <= 256);
+// 1 = A_hi x B_hi only (fp16 storage mode: no lo planes anywhere).
+template <int STAGES, bool SPLIT_EPI, int TERMS, bool HALO>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO_hi64, const __grid_constant__ CUtensorMap tmO_lo64,
@@ -472,7 +520,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t stg       = smem_base + STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned), one buffer per epilogue group
+    // HALO: [A ring: HL_A_STAGES x (hi plane, lo plane)] [B ring: STAGES x 32 KB] [staging]; else [ring: STAGES x 64 KB] [staging]
+    const uint32_t b_ring    = smem_base + (HALO ? HL_A_STAGES * HL_A_STAGE_BYTES : 0);
+    const uint32_t stg       = HALO ? b_ring + STAGES * HL_B_STAGE_BYTES : smem_base + STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned), one buffer per epilogue group
     const uint32_t bar_base  = stg + (SPLIT_EPI ? 2 : 1) * UM_STG_BYTES;
     // barrier slots (8 bytes each): full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), TMEM base slot, residual barrier
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
@@ -487,6 +537,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     auto sched_full  = [&](int s) { return bar_base + 128u + 8u * s; };
     auto sched_empty = [&](int s) { return bar_base + 192u + 8u * s; };
     auto sched_id    = [&](int s) { return bar_base + 256u + 4u * s; };
+    auto a_full_bar  = [&](int s) { return bar_base + 288u + 8u * s; }; // HALO: the halo-tile ring
+    auto a_empty_bar = [&](int s) { return bar_base + 320u + 8u * s; };
     // consumer side: wait for sequence number `seq`, read its work id, release the slot (one arrive per consuming warp)
     auto sched_take = [&](int seq, bool arrive) {
         const int slot = seq & (UM_SCHED_SLOTS - 1);
@@ -512,6 +564,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
+        if (HALO)
+            for (int s = 0; s < HL_A_STAGES; ++s) {
+                mbar_init(a_full_bar(s), 1);
+                mbar_init(a_empty_bar(s), 1);
+            }
         for (int s = 0; s < UM_SCHED_SLOTS; ++s) {
             mbar_init(sched_full(s), 1);
             mbar_init(sched_empty(s), 1 + UM_EPI_WARPS); // the MMA thread + one lane of every epilogue warp
@@ -547,9 +604,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer =====================
         {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = 2u * (uint32_t) p.rows_used * 128u + 2u * (uint32_t) p.n_blk * 128u;
+            int stage = 0, hstage = 0;
+            uint32_t phase = 0, hphase = 0;
+            (void) hstage, (void) hphase;
+            const uint32_t tx_bytes = (TERMS == 1 ? 1u : 2u) * (uint32_t) p.rows_used * 128u + (TERMS == 3 ? 2u : 1u) * (uint32_t) p.n_blk * 128u;
             const int ks = p.ksize, cbs = p.cblocks, icp = p.ICp;
             const bool skip_tma = (p.ablate & 2) != 0;
             const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u; // B_lo rows follow B_hi's: one [2 n_blk x 64] operand
@@ -581,6 +639,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 // Keep this loop lean: it runs once per K block and every stall here delays the whole pipeline (no divisions,
                 // no parameter loads: ncu r01 showed ~60 dependent scalar instructions/iteration bounding the kernel).
                 // K block kb = (ky * ks + kx) * cbs + cb; the counters are decoded once per work item and then stepped.
+                if constexpr (HALO) {
+                    // one halo tile per channel block, then the nine taps' weights: K order (cb, tap)
+                    for (int cb = 0; cb < cbs; ++cb) {
+                        mbar_wait(a_empty_bar(hstage), hphase ^ 1u);
+                        if (elect_one()) {
+                            const uint32_t sA = smem_base + hstage * HL_A_STAGE_BYTES, fb = a_full_bar(hstage);
+                            if (skip_tma) {
+                                mbar_arrive(fb);
+                            } else {
+                                mbar_expect_tx(fb, (TERMS == 1 ? 1u : 2u) * (uint32_t) (HL_W * HL_H * 128));
+                                tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0, iy0, n0);
+                                if (TERMS >= 2) tma_load_4d(sA + HL_PLANE, &tmA_lo, fb, cb * UM_BLOCK_K, ix0, iy0, n0);
+                            }
+                        }
+                        if (++hstage == HL_A_STAGES) hstage = 0, hphase ^= 1u;
+                        int wk = cb * UM_BLOCK_K;
+                        for (int tap = 0; tap < 9; ++tap, wk += icp) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            UM_TRACE(0, tr);
+                            ++tr;
+                            if (elect_one()) {
+                                const uint32_t sB = b_ring + stage * HL_B_STAGE_BYTES, fb = full_bar(stage);
+                                if (skip_tma) {
+                                    mbar_arrive(fb);
+                                } else {
+                                    mbar_expect_tx(fb, (TERMS == 3 ? 2u : 1u) * (uint32_t) p.n_blk * 128u);
+                                    tma_load_2d(sB, &tmB_hi, fb, wk, oc0);
+                                    if (TERMS == 3) tma_load_2d(sB + b_lo_off, &tmB_lo, fb, wk, oc0);
+                                }
+                            }
+                            if (++stage == STAGES) stage = 0, phase ^= 1u;
+                        }
+                    }
+                    work = __shfl_sync(0xffffffffu, next, 0);
+                    continue;
+                }
                 int cb = kb0 % cbs, tap0 = kb0 / cbs;
                 int kx = tap0 % ks, ky = tap0 / ks;
                 int wk = tap0 * icp; // K coordinate into the packed weights = tap * ICp + cb * 64
@@ -595,9 +689,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         } else {
                             mbar_expect_tx(fb, tx_bytes);
                             tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
-                            tma_load_4d(sA + UM_A_BYTES, &tmA_lo, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
+                            if (TERMS >= 2) tma_load_4d(sA + UM_A_BYTES, &tmA_lo, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
                             tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, fb, wk + cb * UM_BLOCK_K, oc0);
-                            tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
+                            if (TERMS == 3) tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
                         }
                     }
                     if (++stage == STAGES) stage = 0, phase ^= 1u;
@@ -616,7 +710,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // 3-term split product with TWO MMAs per K step: A_hi x [B_hi ; B_lo] (N = 2 n_blk, two column blocks) and
         // A_lo x B_hi (N = n_blk, onto the first block); the epilogue adds the blocks. Same math as three N = n_blk MMAs, but
         // A_hi is fetched from shared memory once instead of twice and there are 8 instead of 12 issues per K block.
-        const uint32_t idesc_cat = make_idesc(UM_BLOCK_M, 2 * p.n_blk), idesc = make_idesc(UM_BLOCK_M, p.n_blk);
+        const uint32_t idesc_cat = TERMS == 3 ? make_idesc(UM_BLOCK_M, 2 * p.n_blk) : 0u;
+        const uint32_t idesc     = make_idesc(UM_BLOCK_M, p.n_blk);
         // Descriptor of stage 0's A_hi tile; every other operand is this plus a constant in the 16-byte address field (all of
         // shared memory is < 256 KB, so the 14-bit field never carries). Keeps the per-K-block preamble to a couple of adds:
         // the issue of tcgen05.mma does not run ahead of the tensor pipe, so every scalar clock here is a lost MMA clock.
@@ -625,7 +720,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // full, so scalar work placed BETWEEN the MMAs of a K block overlaps with them, while work between K blocks is lost
         // tensor time: the look-ahead test of the next stage's barrier and the bookkeeping sit before the last two MMAs.
         if (elect_one()) {
-            int it = 0, tr = 0;
+            int it = 0, tr = 0, hstage = 0;
+            uint32_t hphase = 0;
+            (void) hstage, (void) hphase;
             bool ready = false; // full_bar(stage) already observed complete by the look-ahead
             const bool no_mma = (p.ablate & 4) != 0;
             for (;; ++it) {
@@ -636,6 +733,65 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t) (acc * UM_ACC_COLS);
+                if constexpr (HALO) {
+                    const uint64_t bdesc0 = make_smem_desc(b_ring);
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        mbar_wait(a_full_bar(hstage), hphase); // this channel block's halo tile has landed
+                        // SBO = the halo's row pitch (10 pixels): 8-row group g of tap (ky,kx) starts (g + ky) * 10 + kx pixels into the tile
+                        const uint64_t halo = make_smem_desc_sbo(smem_base + hstage * HL_A_STAGE_BYTES, HL_W * 128);
+                        int tap_off = 0; // (ky * HL_W + kx) * 128 B, in 16-byte units
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!ready) mbar_wait(full_bar(stage), phase); // this tap's weights have landed
+                            tc_fence_after();
+                            UM_TRACE(1, tr);
+                            const uint64_t a_hi = halo + (uint64_t) (uint32_t) tap_off, a_lo = a_hi + (HL_PLANE >> 4);
+                            const uint64_t b_cat = bdesc0 + (uint64_t) (uint32_t) (stage * (HL_B_STAGE_BYTES >> 4));
+                            const uint32_t first = (cb > 0 || tap > 0) ? 1u : 0u;
+                            if (!no_mma) {
+                                if (TERMS == 3) {
+#pragma unroll
+                                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (first || j > 0) ? 1u : 0u);
+                                    umma_f16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
+                                    umma_f16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
+                                } else if (TERMS == 2) {
+#pragma unroll
+                                    for (int j = 0; j < 3; ++j) {
+                                        umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, (first || j > 0) ? 1u : 0u);
+                                        umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
+                                    }
+                                } else {
+                                    umma_f16(d_tmem, a_hi + 0u, b_cat + 0u, idesc, first);
+                                    umma_f16(d_tmem, a_hi + 2u, b_cat + 2u, idesc, 1u);
+                                }
+                            }
+                            const int cur         = stage;
+                            const uint32_t nphase = phase ^ (stage == STAGES - 1 ? 1u : 0u);
+                            stage                 = stage == STAGES - 1 ? 0 : stage + 1;
+                            phase                 = nphase;
+                            ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking look-ahead
+                            if (!no_mma) {
+                                if (TERMS == 3) {
+                                    umma_f16(d_tmem, a_lo + 4u, b_cat + 4u, idesc, 1u);
+                                    umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+                                } else if (TERMS == 2) {
+                                    umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
+                                    umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+                                } else {
+                                    umma_f16(d_tmem, a_hi + 4u, b_cat + 4u, idesc, 1u);
+                                    umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
+                                }
+                            }
+                            umma_commit(empty_bar(cur)); // weight slot free once these MMAs retire
+                            UM_TRACE(2, tr);
+                            ++tr;
+                            tap_off += (tap % 3 == 2) ? ((HL_W - 2) * 128 >> 4) : (128 >> 4); // next tap: +1 pixel, or to the next halo row
+                        }
+                        umma_commit(a_empty_bar(hstage)); // halo tile free once all nine taps have retired
+                        if (++hstage == HL_A_STAGES) hstage = 0, hphase ^= 1u;
+                    }
+                    umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
+                    continue;
+                }
                 const int kb0 = (work / total_tiles) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!ready) mbar_wait(full_bar(stage), phase); // TMA bytes have landed
@@ -643,12 +799,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     UM_TRACE(1, tr);
                     const uint64_t a_hi = desc0 + (uint64_t) (uint32_t) (stage * (UM_STAGE_BYTES >> 4)), a_lo = a_hi + (UM_A_BYTES >> 4);
                     const uint64_t b_cat = a_hi + (2 * UM_A_BYTES >> 4); // rows [0, n_blk) = B_hi, [n_blk, 2 n_blk) = B_lo
-                    // UMMA_K = 16 bf16 = 32 bytes: K step j advances the start address by 2 (x16 B)
+                    // UMMA_K = 16 fp16 = 32 bytes: K step j advances the start address by 2 (x16 B)
                     if (!no_mma) {
+                        if (TERMS == 3) {
 #pragma unroll
-                        for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_bf16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (kb > kb0 || j > 0) ? 1u : 0u);
-                        umma_bf16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
-                        umma_bf16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
+                            for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (kb > kb0 || j > 0) ? 1u : 0u);
+                            umma_f16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
+                            umma_f16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
+                        } else if (TERMS == 2) { // (A_hi + A_lo) x B16, K step by K step
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                                umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
+                            }
+                        } else {
+                            umma_f16(d_tmem, a_hi + 0u, b_cat + 0u, idesc, kb > kb0 ? 1u : 0u);
+                            umma_f16(d_tmem, a_hi + 2u, b_cat + 2u, idesc, 1u);
+                        }
                     }
                     const int cur         = stage;
                     const uint32_t nphase = phase ^ (stage == STAGES - 1 ? 1u : 0u);
@@ -656,8 +823,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     phase                 = nphase;
                     ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking
                     if (!no_mma) {
-                        umma_bf16(d_tmem, a_lo + 4u, b_cat + 4u, idesc, 1u);
-                        umma_bf16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+                        if (TERMS == 3) {
+                            umma_f16(d_tmem, a_lo + 4u, b_cat + 4u, idesc, 1u);
+                            umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+                        } else if (TERMS == 2) {
+                            umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
+                            umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+                        } else {
+                            umma_f16(d_tmem, a_hi + 4u, b_cat + 4u, idesc, 1u);
+                            umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
+                        }
                     }
                     umma_commit(empty_bar(cur));                           // smem slot free once these MMAs retire
                     if (kb == kb1 - 1) umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
@@ -676,6 +851,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         e.o_hi64 = &tmO_hi64, e.o_lo64 = &tmO_lo64, e.o_hiT = &tmO_hiT, e.o_loT = &tmO_loT;
         e.r_hi64 = &tmR_hi64, e.r_lo64 = &tmR_lo64, e.r_hiT = &tmR_hiT, e.r_loT = &tmR_loT;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = p.has_res, e.rows_box = p.rows_used, e.alpha = p.alpha;
+        e.has_lo = p.has_lo;
         const int grp = SPLIT_EPI ? half : 0;                 // epilogue group of this warp
         const bool leader = warp == (SPLIT_EPI ? 2 + 4 * grp : 2); // the group's TMA-issuing warp
         e.stg = stg + grp * UM_STG_BYTES, e.res_bar = res_bar + 16u * grp, e.bar_id = 1 + grp;
@@ -707,7 +883,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
             if (p.ksplit > 1) {
                 float* tile_parts = p.partials + (size_t) tile * p.ksplit * (UM_BLOCK_M * p.n_blk);
-                epilogue_dump_partial<UM_EPI_WARPS>(e, taddr, tile_parts + (size_t) split * (UM_BLOCK_M * p.n_blk), row, half, lane);
+                epilogue_dump_partial<UM_EPI_WARPS, TERMS>(e, taddr, tile_parts + (size_t) split * (UM_BLOCK_M * p.n_blk), row, half, lane);
                 __threadfence(); // partial tile visible device-wide before the arrival is counted
                 named_bar_sync(1, UM_EPI_WARPS * 32);
                 if (warp == 2 && lane == 0) {
@@ -725,9 +901,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             }
             if (SPLIT_EPI)
-                epilogue_tile<UM_EPI_WARPS / 2>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, 0, leader, lane, res_phase);
+                epilogue_tile<UM_EPI_WARPS / 2, TERMS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, 0, leader, lane, res_phase);
             else
-                epilogue_tile<UM_EPI_WARPS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, leader, lane, res_phase);
+                epilogue_tile<UM_EPI_WARPS, TERMS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, leader, lane, res_phase);
             e.part_src = nullptr;
             if (leader) UM_TRACE(4, it);
         }
@@ -754,7 +930,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // Small-input-channel convolution (IC <= 8: the 7x7 / 3x3 RGB stems, ESPCN's 1-channel 5x5) on the same tensor cores,
 // with a ZERO-COPY sliding-window A operand.
 //
-// With C padded to 8 bf16 one pixel is ONE 16-byte vector per plane = exactly one K "chunk" of a tcgen05 K-major
+// With C padded to 8 fp16 one pixel is ONE 16-byte vector per plane = exactly one K "chunk" of a tcgen05 K-major
 // operand. In the un-swizzled (SWIZZLE_NONE) canonical layout row m / chunk c of A is read from
 //        start + (m/8)*SBO + (m%8)*16 B + c*LBO,
 // and nothing stops LBO from being 16 B: chunk c of row m is then simply pixel m + c of a dense pixel row in shared
@@ -777,8 +953,8 @@ constexpr int RW_B_BYTES       = 144 * 1024;                   // resident weigh
 constexpr int RW_SMEM_BYTES    = RW_B_BYTES + RW_STAGES * RW_STAGE_BYTES + UM_STG_BYTES + 1024 + 256;
 
 struct RowWinParams {
-    __nv_bfloat16* out_hi;
-    __nv_bfloat16* out_lo;
+    __half* out_hi;
+    __half* out_lo;
     const float* bias;
     int N, OH, OW, OC, OCp, n_blk, ocr;
     int kh, stride, pad_y;
@@ -794,6 +970,7 @@ struct RowWinParams {
 // (8 rows x 16 B), version 1, layout type 0.
 __device__ __forceinline__ uint64_t make_window_desc(uint32_t saddr) { return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (8ull << 32) | (1ull << 46); }
 
+template <int TERMS> // see conv_umma_kernel
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_constant__ CUtensorMap tmA_hi1, const __grid_constant__ CUtensorMap tmA_lo0,
                    const __grid_constant__ CUtensorMap tmA_lo1, const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -851,17 +1028,21 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             // weight panel: once per CTA
             if (elect_one()) {
                 const int vrows = p.kh * p.panels; // (filter row, panel)
-                mbar_expect_tx(b_bar, 2u * (uint32_t) vrows * (uint32_t) p.n_blk * 128u);
+                mbar_expect_tx(b_bar, (TERMS == 3 ? 2u : 1u) * (uint32_t) vrows * (uint32_t) p.n_blk * 128u);
                 for (int v = 0; v < vrows; ++v) {
-                    tma_load_2d(sB + (2 * v) * p.n_blk * 128, &tmB_hi, b_bar, 0, v * p.ocr);
-                    tma_load_2d(sB + (2 * v + 1) * p.n_blk * 128, &tmB_lo, b_bar, 0, v * p.ocr);
+                    if (TERMS == 3) {
+                        tma_load_2d(sB + (2 * v) * p.n_blk * 128, &tmB_hi, b_bar, 0, v * p.ocr);
+                        tma_load_2d(sB + (2 * v + 1) * p.n_blk * 128, &tmB_lo, b_bar, 0, v * p.ocr);
+                    } else {
+                        tma_load_2d(sB + v * p.n_blk * 128, &tmB_hi, b_bar, 0, v * p.ocr); // one plane
+                    }
                 }
             }
             __syncwarp();
             // activation row segments
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = 2u * (uint32_t) p.parities * RW_ARR_BYTES;
+            const uint32_t tx_bytes = (TERMS == 1 ? 1u : 2u) * (uint32_t) p.parities * RW_ARR_BYTES;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int xt = tile % p.tiles_x, oy = (tile / p.tiles_x) % p.OH, n = tile / (p.tiles_x * p.OH);
                 const int ox0 = xt * UM_BLOCK_M;
@@ -872,10 +1053,10 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                         const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
                         mbar_expect_tx(full_bar(stage), tx_bytes);
                         tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
-                        tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                        if (TERMS >= 2) tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
                         if (p.parities == 2) {
                             tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
-                            tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                            if (TERMS >= 2) tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
                         }
                     }
                     __syncwarp();
@@ -885,14 +1066,16 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         }
     } else if (warp == 1) {
         mbar_wait(b_bar, 0);
-        const uint32_t idesc_cat = make_idesc(UM_BLOCK_M, 2 * p.n_blk), idesc = make_idesc(UM_BLOCK_M, p.n_blk); // see conv_umma_kernel
+        // see conv_umma_kernel: 3-term = A_hi x [B_hi ; B_lo] + A_lo x B_hi; 2-term = (A_hi + A_lo) x B16; 1-term = A_hi x B_hi
+        const uint32_t idesc_cat = TERMS == 3 ? make_idesc(UM_BLOCK_M, 2 * p.n_blk) : make_idesc(UM_BLOCK_M, p.n_blk);
+        const uint32_t idesc     = make_idesc(UM_BLOCK_M, p.n_blk);
         if (elect_one()) { // one thread owns the issue loop (see conv_umma_kernel)
             // window descriptor (16-byte address field) offsets of the K steps, relative to the stage's hi plane
             uint32_t koff[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) koff[q] = q < p.ksteps ? (((uint32_t) p.ks_parity[q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[q] * 16u) >> 4) : 0u;
             const uint64_t wdesc0 = make_window_desc(sA0), bdesc0 = make_smem_desc(sB);
-            const uint32_t b_panel = (uint32_t) (2 * p.n_blk * 128) >> 4;  // one [B_hi ; B_lo] panel (64 K columns)
+            const uint32_t b_panel = (uint32_t) ((TERMS == 3 ? 2 : 1) * p.n_blk * 128) >> 4;  // one [B_hi ; B_lo] (or single-plane) panel (64 K columns)
             const uint32_t b_ky    = b_panel * (uint32_t) p.panels;         // one filter row
             const int last_q      = p.ksteps - 1;
             const uint32_t koff_last = ((uint32_t) p.ks_parity[last_q] * RW_ARR_BYTES + (uint32_t) p.ks_erel[last_q] * 16u) >> 4;
@@ -915,8 +1098,8 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     for (int q = 0; q < 8; ++q) { // K step q lives in weight panel q / 4, columns 16 (q % 4) ..
                         if (q < last_q) {
                             const uint64_t bq = b_cat + (uint64_t) ((q >> 2) * b_panel + 2u * (q & 3));
-                            umma_bf16(d_tmem, a0 + koff[q], bq, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u);           // -> [hi.hi | hi.lo]
-                            umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff[q], bq, idesc, 1u);             // lo.hi onto the first block
+                            umma_f16(d_tmem, a0 + koff[q], bq, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u);           // -> [hi.hi | hi.lo]
+                            if (TERMS >= 2) umma_f16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff[q], bq, idesc, 1u); // lo.hi onto the first block
                         }
                     }
                     const uint64_t b_last = b_cat + (uint64_t) ((last_q >> 2) * b_panel + 2u * (last_q & 3));
@@ -924,8 +1107,8 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     phase ^= (stage == RW_STAGES - 1) ? 1u : 0u;
                     stage = stage == RW_STAGES - 1 ? 0 : stage + 1;
                     ready = mbar_test_wait(full_bar(stage), phase); // look-ahead, overlaps with the MMAs already queued
-                    umma_bf16(d_tmem, a0 + koff_last, b_last, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
-                    umma_bf16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff_last, b_last, idesc, 1u);
+                    umma_f16(d_tmem, a0 + koff_last, b_last, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
+                    if (TERMS >= 2) umma_f16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff_last, b_last, idesc, 1u);
                     umma_commit(empty_bar(cur));
                     if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
                     UM_TRACE(2, tr);
@@ -944,6 +1127,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         e.o_hi64 = &tmO_hi, e.o_lo64 = &tmO_lo, e.o_hiT = &tmO_hi, e.o_loT = &tmO_lo;
         e.r_hi64 = e.r_lo64 = e.r_hiT = e.r_loT = &tmO_hi;
         e.bias = p.bias, e.n_blk = p.n_blk, e.OC = p.OC, e.act = p.act, e.has_res = 0, e.rows_box = UM_BLOCK_M, e.alpha = p.alpha;
+        e.has_lo = TERMS >= 2;
         e.stg = stg, e.res_bar = 0, e.bar_id = 1;
         e.part_src = nullptr, e.part_splits = 0;
         uint32_t res_phase = 0;
@@ -958,7 +1142,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             e.tmem_empty = tmem_empty_bar(acc);
             e.trace = p.trace, e.trace_seq = it;
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * 2 * RW_MAX_N);
-            epilogue_tile<RW_EPI_WARPS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, half, warp == 2, lane, res_phase);
+            epilogue_tile<RW_EPI_WARPS, TERMS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, half, warp == 2, lane, res_phase);
             if (warp == 2) UM_TRACE(4, it);
         }
         epilogue_drain(warp == 2);
@@ -1036,15 +1220,15 @@ static EncodeTiledFn get_encode(snnb_context* ctx) {
     return reinterpret_cast<EncodeTiledFn>(ctx->tmap_encode_fn);
 }
 
-// Tensor maps of an NHWC split-bf16 tensor for the epilogue's TMA stores / residual loads: box = (width channels, tw, th, tn).
+// Tensor maps of an NHWC split-fp16 tensor for the epilogue's TMA stores / residual loads: box = (width channels, tw, th, tn).
 static int encode_nhwc_box_maps(EncodeTiledFn encode, const snnb_tensor* t, int width, int tw, int th, int tn, bool swizzle128, CUtensorMap (&maps)[2]) {
     const cuuint64_t dims[4]    = {(cuuint64_t) t->cp, (cuuint64_t) t->w, (cuuint64_t) t->h, (cuuint64_t) t->n};
     const cuuint64_t strides[3] = {(cuuint64_t) t->cp * 2, (cuuint64_t) t->w * t->cp * 2, (cuuint64_t) t->h * t->w * t->cp * 2};
     const cuuint32_t box[4]     = {(cuuint32_t) width, (cuuint32_t) tw, (cuuint32_t) th, (cuuint32_t) tn};
     const cuuint32_t estr[4]    = {1, 1, 1, 1};
-    __nv_bfloat16* planes[2]    = {t->hi, t->lo};
+    __half* planes[2]    = {t->hi, t->lo ? t->lo : t->hi}; // fp16 storage mode: the lo map is encoded but never used
     for (int i = 0; i < 2; ++i) {
-        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out/residual) failed: %d (cp %d w %d h %d n %d box %d %d %d %d)", (int) r, t->cp, t->w, t->h, t->n,
@@ -1086,19 +1270,27 @@ static TilePlan plan_tiles(int N, int OH, int OW, int stride) {
 // the last arriver, +~9 k clk) fills the GPU when a layer has few tiles and a long K (7x7x512: 128 tiles x 72 K blocks).
 struct OcPlan {
     int n_blk = 0, tiles_oc = 0, ksplit = 1, kb_per_split = 0;
+    double cost = 1e300; // modelled clocks of the launch
 };
-static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int num_kb, int sm_count) {
+// Tensor-pipe time of one M = 128 tcgen05.mma with N columns (tools/umma_microbench.cu: operand fetch from shared memory, A 4 KB +
+// B N x 32 B at 128 B/clk, bounds the narrow shapes): N <= 64: 48 clk, N = 128: 64, N = 256: 128.
+static double mma_clk(int n) { return std::max(48.0, n * 0.5); }
+static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int num_kb, int sm_count, int terms, bool halo = false) {
     OcPlan best;
     double best_cost = 1e300;
     static const int no_split = getenv("SNNB_NO_SPLITK") != nullptr;
-    const int t_min = (OC + UM_MAX_N - 1) / UM_MAX_N, t_max = (OC + 15) / 16;
+    const int max_n = terms == 3 ? UM_MAX_N : UM_MAX_N2;
+    const int t_min = (OC + max_n - 1) / max_n, t_max = (OC + 15) / 16;
     for (int t = t_min; t <= t_max; ++t) {
-        const int blk = std::min(UM_MAX_N, round_up((OC + t - 1) / t, 16));
+        const int blk = std::min(max_n, round_up((OC + t - 1) / t, 16));
         if (blk * t < OC) continue;
         // boxes narrower than 8 pixels (7x7 maps) move ~20 % fewer bytes per clock through the TMA unit (measured 59 vs 74-77 B/clk)
         const double ingest  = tile_w < 8 ? 58.0 : 72.0;
-        const double kb_cost = std::max((2.0 * rows_used * 128 + 2.0 * blk * 128) / ingest, blk <= 64 ? 310.0 : 420.0) + 60.0;
-        for (int sp = 1; sp <= (no_split ? 1 : 4); ++sp) {
+        // halo mode: one (8+2) x (16+2) halo tile per channel block serves all nine taps
+        const double a_bytes = (terms == 1 ? 1.0 : 2.0) * (halo ? HL_W * HL_H * 128 / 9.0 : rows_used * 128.0), b_bytes = (terms == 3 ? 2.0 : 1.0) * blk * 128;
+        const double mma     = terms == 3 ? 4.0 * (mma_clk(2 * blk) + mma_clk(blk)) : 4.0 * terms * mma_clk(blk); // per 64-wide K block
+        const double kb_cost = std::max((a_bytes + b_bytes) / ingest, mma) + 60.0;
+        for (int sp = 1; sp <= ((no_split || halo) ? 1 : 4); ++sp) {
             if (sp > 1 && (num_kb < 8 * sp)) break; // not worth a reduction for short K
             const int kbps          = (num_kb + sp - 1) / sp;
             if ((sp - 1) * kbps >= num_kb) continue; // an empty split
@@ -1106,7 +1298,7 @@ static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int
             const long long rounds = (items + sm_count - 1) / sm_count;
             const double cost      = (double) rounds * (kbps * kb_cost + 7000.0 + (sp > 1 ? 9000.0 : 0.0));
             if (cost < best_cost * (sp > 1 ? 0.93 : 1.0) - 1e-9) // split only for a clear win
-                best_cost = cost, best.n_blk = blk, best.tiles_oc = t, best.ksplit = sp, best.kb_per_split = kbps;
+                best_cost = cost, best.cost = cost, best.n_blk = blk, best.tiles_oc = t, best.ksplit = sp, best.kb_per_split = kbps;
         }
         if (blk <= 16) break;
     }
@@ -1130,6 +1322,14 @@ static int ensure_splitk_scratch(snnb_context* ctx, size_t partial_bytes, size_t
         ctx->splitk_counters = static_cast<int*>(pnew), ctx->splitk_counter_n = n_counters;
     }
     return 0;
+}
+
+// How the product is formed (template parameter TERMS of the kernels): the launch's own precision, else the context's default;
+// tensors without a lo plane (fp16 storage mode) can only take the 1-term product.
+static int conv_terms(const snnb_context* ctx, const ConvArgs& a) {
+    if (!a.in->lo || !a.out->lo) return 1;
+    const int prec = a.precision >= 0 ? a.precision : ctx->precision;
+    return prec == SNNB_PRECISION_FP16W ? 2 : (prec == SNNB_PRECISION_FP16 ? 1 : 3);
 }
 
 static bool rowwin_supported(const ConvArgs& a) {
@@ -1175,43 +1375,47 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     for (int plane = 0; plane < 2; ++plane)
         for (int par = 0; par < 2; ++par) {
             const int pp = par < rp.parities ? par : 0; // unused maps alias parity 0 (kernel never issues them)
-            __nv_bfloat16* base = (plane ? in->lo : in->hi) + (size_t) pp * 8;
+            __half* base = (plane ? in->lo : in->hi) + (size_t) pp * 8;
             const int wp        = (in->w - pp + a.stride - 1) / a.stride; // pixels of this parity per row
             const cuuint64_t dims[4]    = {8, (cuuint64_t) (wp > 0 ? wp : 1), (cuuint64_t) in->h, (cuuint64_t) in->n};
             const cuuint64_t strides[3] = {(cuuint64_t) a.stride * 16, (cuuint64_t) in->w * 16, (cuuint64_t) in->h * in->w * 16};
             const cuuint32_t box[4]     = {8, (cuuint32_t) RW_BOXW, 1, 1};
             const cuuint32_t estr[4]    = {1, 1, 1, 1};
-            CUresult r = encode(&tmA[plane * 2 + par], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CUresult r = encode(&tmA[plane * 2 + par], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, rowwin) failed: %d", (int) r);
         }
+    const int terms = conv_terms(ctx, a);
     {
         const cuuint64_t dims[2]    = {64, (cuuint64_t) a.k * p.panels * a.w->ocr}; // [ky][panel][OCr] rows of 64 K columns
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2]     = {64, (cuuint32_t) p.n_blk};
         const cuuint32_t estr[2]    = {1, 1};
-        __nv_bfloat16* planes[2]    = {a.w->w_row_hi, a.w->w_row_lo};
+        void* planes[2]             = {(void*) a.w->w_row_hi, (void*) a.w->w_row_lo}; // the 2-term product uses the hi plane alone: fp16_rn(w)
         for (int i = 0; i < 2; ++i) {
-            CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, planes[i], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, rowwin) failed: %d", (int) r);
         }
     }
     CUtensorMap tmO[2];
     if (encode_nhwc_box_maps(encode, out, p.n_blk, UM_BLOCK_M, 1, 1, p.n_blk == 64, tmO)) return 2;
     if (!(ctx->func_attr_mask & ATTR_ROWWIN)) {
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
         ctx->func_attr_mask |= ATTR_ROWWIN;
     }
     const int total_tiles = p.N * p.OH * p.tiles_x;
     const int grid        = std::min(total_tiles, ctx->sm_count);
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
-    const cudaError_t le = launch_k_pdl(conv_rowwin_kernel, dim3(grid), dim3(RW_THREADS), RW_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], tmO[0], tmO[1], p);
+    auto* kern = terms == 3 ? conv_rowwin_kernel<3> : (terms == 2 ? conv_rowwin_kernel<2> : conv_rowwin_kernel<1>);
+    const cudaError_t le = launch_k_pdl(kern, dim3(grid), dim3(RW_THREADS), RW_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], tmO[0], tmO[1], p);
     if (p.trace) {
         char hdr[256];
-        snprintf(hdr, sizeof hdr, "rowwin k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d kh %d ksteps %d", a.k, a.stride, a.in->c, a.out->c, a.out->n, a.out->h, a.out->w,
-                 p.n_blk, total_tiles, grid, p.kh, p.ksteps);
+        snprintf(hdr, sizeof hdr, "rowwin k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d kh %d ksteps %d terms %d", a.k, a.stride, a.in->c, a.out->c, a.out->n, a.out->h, a.out->w,
+                 p.n_blk, total_tiles, grid, p.kh, p.ksteps, terms);
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
@@ -1241,7 +1445,22 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     p.tiles_x = tp.tiles_x, p.tiles_y = tp.tiles_y, p.tiles_n = tp.tiles_n;
     p.ksize = a.k, p.stride = a.stride, p.pad_x = a.pad_x, p.pad_y = a.pad_y;
     p.cblocks = (in->c + UM_BLOCK_K - 1) / UM_BLOCK_K;
-    const OcPlan op = plan_oc_ksplit(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, tp.tw, a.k * a.k * p.cblocks, ctx->sm_count);
+    const int terms = conv_terms(ctx, a);
+    p.has_lo        = out->lo != nullptr;
+    OcPlan op       = plan_oc_ksplit(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, tp.tw, a.k * a.k * p.cblocks, ctx->sm_count, terms);
+    // halo mode (3x3, stride 1): 8 x 16-pixel tiles whose nine taps share one halo load; taken when the cost model prefers it
+    // (fewer bytes per K block against the MMA rows lost where 8 / 16 do not divide the feature map)
+    static const bool no_halo = getenv("SNNB_NO_HALO") != nullptr;
+    bool halo                 = false;
+    if (!no_halo && a.k == 3 && a.stride == 1 && a.pad_x <= 1 && a.pad_y <= 1) {
+        const int hx = (out->w + HL_TW - 1) / HL_TW, hy = (out->h + HL_TH - 1) / HL_TH;
+        const OcPlan hp = plan_oc_ksplit(out->c, hx * hy * out->n, UM_BLOCK_M, HL_TW, 9 * p.cblocks, ctx->sm_count, terms, true);
+        if (hp.n_blk > 0 && hp.cost < op.cost) {
+            halo = true, op = hp;
+            p.tw = HL_TW, p.th = HL_TH, p.tn = 1, p.rows_used = UM_BLOCK_M;
+            p.tiles_x = hx, p.tiles_y = hy, p.tiles_n = out->n;
+        }
+    }
     SNNB_REQUIRE(op.n_blk > 0, "launch_conv2d_umma: no output-channel plan");
     p.n_blk = op.n_blk, p.tiles_oc = op.tiles_oc, p.ksplit = op.ksplit, p.kb_per_split = op.kb_per_split;
     p.partials = nullptr, p.counters = nullptr;
@@ -1257,7 +1476,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     }
     p.sched_counter = ctx->sched_counter;
     if (p.ksplit > 1) {
-        const size_t tiles = (size_t) tp.tiles_x * tp.tiles_y * tp.tiles_n * p.tiles_oc;
+        const size_t tiles = (size_t) p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         SNNB_CUDA_OK(cudaStreamIsCapturing(ctx->stream, &cap));
         const size_t need = tiles * p.ksplit * UM_BLOCK_M * p.n_blk * sizeof(float);
@@ -1276,11 +1495,11 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     {
         const cuuint64_t dims[4]    = {(cuuint64_t) in->c, (cuuint64_t) in->w, (cuuint64_t) in->h, (cuuint64_t) in->n};
         const cuuint64_t strides[3] = {(cuuint64_t) in->cp * 2, (cuuint64_t) in->w * in->cp * 2, (cuuint64_t) in->h * in->w * in->cp * 2};
-        const cuuint32_t box[4]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) (p.tw * a.stride), (cuuint32_t) (p.th * a.stride), (cuuint32_t) p.tn};
+        const cuuint32_t box[4]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) (halo ? HL_W : p.tw * a.stride), (cuuint32_t) (halo ? HL_H : p.th * a.stride), (cuuint32_t) p.tn};
         const cuuint32_t estr[4]    = {1, (cuuint32_t) a.stride, (cuuint32_t) a.stride, 1};
-        __nv_bfloat16* planes[2]    = {in->hi, in->lo};
+        __half* planes[2]    = {in->hi, in->lo ? in->lo : in->hi}; // fp16 storage mode: the lo map is never issued
         for (int i = 0; i < 2; ++i) {
-            CUresult r = encode(&tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CUresult r = encode(&tmA[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d box %u %u %u %u)", (int) r, in->c, in->w, in->h, in->n, box[0],
                          box[1], box[2], box[3]);
@@ -1291,10 +1510,10 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         const cuuint64_t strides[1] = {(cuuint64_t) a.w->kp * 2};
         const cuuint32_t box[2]     = {(cuuint32_t) UM_BLOCK_K, (cuuint32_t) p.n_blk};
         const cuuint32_t estr[2]    = {1, 1};
-        __nv_bfloat16* planes[2]    = {a.w->w_hi, a.w->w_lo};
+        void* planes[2]             = {(void*) a.w->w_hi, (void*) a.w->w_lo}; // the 2-term product uses the hi plane alone: fp16_rn(w)
         for (int i = 0; i < 2; ++i) {
-            CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, planes[i], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (kp %d ocr %d n_blk %d)", (int) r, a.w->kp, a.w->ocr, p.n_blk);
         }
     }
@@ -1309,26 +1528,38 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         if (encode_nhwc_box_maps(encode, res, wT ? wT : 64, p.tw, p.th, p.tn, wT == 0, tmRT)) return 2;
     }
     if (!(ctx->func_attr_mask & ATTR_UMMA)) {
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES - 1, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES_SPLIT));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<HL_B_STAGES, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<HL_B_STAGES, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<HL_B_STAGES, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
         ctx->func_attr_mask |= ATTR_UMMA;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int grid        = std::min(total_tiles * p.ksplit, ctx->sm_count);
     // short K loop (1x1 convolutions): the layer runs at the speed of the epilogue -> two independent epilogue groups
     static const bool no_split_epi = getenv("SNNB_NO_SPLIT_EPI") != nullptr;
-    const bool split_epi           = !no_split_epi && p.ksplit == 1 && p.ksize * p.ksize * p.cblocks <= 3 && total_tiles >= 2 * grid;
+    const bool split_epi           = !halo && !no_split_epi && p.ksplit == 1 && p.ksize * p.ksize * p.cblocks <= 3 && total_tiles >= 2 * grid;
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
+    auto* k_split = terms == 3 ? conv_umma_kernel<UM_STAGES - 1, true, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES - 1, true, 2, false> : conv_umma_kernel<UM_STAGES - 1, true, 1, false>);
+    auto* k_plain = terms == 3 ? conv_umma_kernel<UM_STAGES, false, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES, false, 2, false> : conv_umma_kernel<UM_STAGES, false, 1, false>);
+    auto* k_halo  = terms == 3 ? conv_umma_kernel<HL_B_STAGES, false, 3, true> : (terms == 2 ? conv_umma_kernel<HL_B_STAGES, false, 2, true> : conv_umma_kernel<HL_B_STAGES, false, 1, true>);
     const cudaError_t le =
-        split_epi ? launch_k_pdl(conv_umma_kernel<UM_STAGES - 1, true>, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES_SPLIT, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0],
-                                 tmO64[1], tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0], tmRT[1], p)
-                  : launch_k_pdl(conv_umma_kernel<UM_STAGES, false>, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1],
-                                 tmOT[0], tmOT[1], tmR64[0], tmR64[1], tmRT[0], tmRT[1], p);
+        halo      ? launch_k_pdl(k_halo, dim3(grid), dim3(UM_THREADS), HL_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1], tmR64[0],
+                                 tmR64[1], tmRT[0], tmRT[1], p)
+        : split_epi ? launch_k_pdl(k_split, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES_SPLIT, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1],
+                                 tmR64[0], tmR64[1], tmRT[0], tmRT[1], p)
+                  : launch_k_pdl(k_plain, dim3(grid), dim3(UM_THREADS), UM_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1], tmR64[0],
+                                 tmR64[1], tmRT[0], tmRT[1], p);
     if (p.trace) {
         char hdr[256];
-        snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d ksplit %d", a.k, a.stride, in->c, out->c, out->n, out->h, out->w,
-                 p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -1 : p.ksplit); // ksplit -1 = split-epilogue variant
+        snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d ksplit %d terms %d halo %d", a.k, a.stride, in->c, out->c, out->n,
+                 out->h, out->w, p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -1 : p.ksplit, terms, (int) halo); // ksplit -1 = split-epilogue variant
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
@@ -1363,8 +1594,8 @@ template <int S> struct DwTile {
     static constexpr int SMEM_BYTES  = DW_STAGES * STAGE_BYTES + 128 /*alignment*/ + 64 /*barriers*/;
 };
 struct DwTmaParams {
-    __nv_bfloat16* out_hi;
-    __nv_bfloat16* out_lo;
+    __half* out_hi;
+    __half* out_lo;
     const float* w;    // [9][Cp]
     const float* bias; // [Cp + padding]
     int N, OH, OW, C, Cp;
@@ -1460,8 +1691,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) depthwise_tma_kernel(const __gr
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    v[2 * j]     = __uint_as_float(h[j] << 16) + __uint_as_float(l[j] << 16);
-                    v[2 * j + 1] = __uint_as_float(h[j] & 0xffff0000u) + __uint_as_float(l[j] & 0xffff0000u);
+                    const float2 vh = um_h2f(h[j]), vl = um_h2f(l[j]);
+                    v[2 * j]     = vh.x + vl.x;
+                    v[2 * j + 1] = vh.y + vl.y;
                 }
 #pragma unroll
                 for (int t = 0; t < T::TXT; ++t) {
@@ -1538,9 +1770,9 @@ template <int S> static int launch_depthwise_tma_s(snnb_context* ctx, const Conv
         const cuuint64_t strides[3] = {(cuuint64_t) in->cp * 2, (cuuint64_t) in->w * in->cp * 2, (cuuint64_t) in->h * in->w * in->cp * 2};
         const cuuint32_t box[4]     = {64, (cuuint32_t) T::IW, (cuuint32_t) T::IH, 1};
         const cuuint32_t estr[4]    = {1, 1, 1, 1};
-        __nv_bfloat16* planes[2]    = {in->hi, in->lo};
+        __half* planes[2]    = {in->hi, in->lo};
         for (int i = 0; i < 2; ++i) {
-            CUresult r = encode(&tmI[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CUresult r = encode(&tmI[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(depthwise input) failed: %d", (int) r);
         }

@@ -16,10 +16,10 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 size_t PackedHost::device_bytes() const {
     size_t b = 0;
     b += align256(w_f32.size() * sizeof(float));
-    b += align256(w_hi.size() * sizeof(__nv_bfloat16));
-    b += align256(w_lo.size() * sizeof(__nv_bfloat16));
-    b += align256(w_row_hi.size() * sizeof(__nv_bfloat16));
-    b += align256(w_row_lo.size() * sizeof(__nv_bfloat16));
+    b += align256(w_hi.size() * sizeof(__half));
+    b += align256(w_lo.size() * sizeof(__half));
+    b += align256(w_row_hi.size() * sizeof(__half));
+    b += align256(w_row_lo.size() * sizeof(__half));
     b += align256(bias.size() * sizeof(float));
     b += align256(gamma.size() * sizeof(float));
     b += align256(beta.size() * sizeof(float));
@@ -60,9 +60,9 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
     out.kp      = k * k * ICp;
     out.ocr     = round_up(OC, 16);
     out.w_f32.assign((size_t) K * out.ocw, 0.0f);
-    out.w_hi.assign((size_t) out.ocr * out.kp, __float2bfloat16_rn(0.0f));
-    out.w_lo.assign((size_t) out.ocr * out.kp, __float2bfloat16_rn(0.0f));
-    out.bias.assign(out.ocw + 192, 0.0f); // zero tail: the tcgen05 epilogue reads float4s up to tiles_oc * n_blk
+    out.w_hi.assign((size_t) out.ocr * out.kp, __float2half_rn(0.0f));
+    out.w_lo.assign((size_t) out.ocr * out.kp, __float2half_rn(0.0f));
+    out.bias.assign(out.ocw + 320, 0.0f); // zero tail: the tcgen05 epilogue reads float4s up to tiles_oc * n_blk (n_blk <= 256)
     for (int o = 0; o < OC; ++o) {
         out.bias[o] = shift[o];
         for (int i = 0; i < IC; ++i)
@@ -72,9 +72,9 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
                     const int kidx  = (ky * k + kx) * IC + i;
                     out.w_f32[(size_t) kidx * out.ocw + o] = wv;
                     const int kcol                         = (ky * k + kx) * ICp + i;
-                    const __nv_bfloat16 h                  = __float2bfloat16_rn(wv);
+                    const __half h                  = __float2half_rn(wv);
                     out.w_hi[(size_t) o * out.kp + kcol]   = h;
-                    out.w_lo[(size_t) o * out.kp + kcol]   = __float2bfloat16_rn(wv - __bfloat162float(h));
+                    out.w_lo[(size_t) o * out.kp + kcol]   = __float2half_rn(wv - __half2float(h));
                 }
     }
 }
@@ -85,8 +85,8 @@ void pack_rowwin_host(PackedHost& p, int stride, int pad_x) {
     const int k = p.kernel, IC = p.in_ch, OC = p.out_ch;
     p.row_stride = stride, p.row_pad = pad_x;
     const int panels = (rp.ksteps + 3) / 4; // 64 K columns (4 K steps) per panel: [ky][panel][OCr][64]
-    p.w_row_hi.assign((size_t) k * panels * p.ocr * 64, __float2bfloat16_rn(0.0f));
-    p.w_row_lo.assign((size_t) k * panels * p.ocr * 64, __float2bfloat16_rn(0.0f));
+    p.w_row_hi.assign((size_t) k * panels * p.ocr * 64, __float2half_rn(0.0f));
+    p.w_row_lo.assign((size_t) k * panels * p.ocr * 64, __float2half_rn(0.0f));
     for (int ky = 0; ky < k; ++ky)
         for (int o = 0; o < OC; ++o)
             for (int q = 0; q < rp.ksteps; ++q)
@@ -96,9 +96,9 @@ void pack_rowwin_host(PackedHost& p, int stride, int pad_x) {
                     for (int c = 0; c < IC; ++c) {
                         const float wv        = p.w_f32[(size_t) ((ky * k + j) * IC + c) * p.ocw + o]; // BN already folded in
                         const size_t idx      = (((size_t) ky * panels + q / 4) * p.ocr + o) * 64 + (q % 4) * 16 + h * 8 + c;
-                        const __nv_bfloat16 hh = __float2bfloat16_rn(wv);
+                        const __half hh = __float2half_rn(wv);
                         p.w_row_hi[idx]       = hh;
-                        p.w_row_lo[idx]       = __float2bfloat16_rn(wv - __bfloat162float(hh));
+                        p.w_row_lo[idx]       = __float2half_rn(wv - __half2float(hh));
                     }
                 }
 }

@@ -3,7 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -79,15 +79,21 @@ inline cudaError_t launch_k_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block,
 } // namespace snnb
 
 // ---- device storage -----------------------------------------------------------------------------------------
-// Activations: NHWC, channel pitch Cp = round_up(C, 8), stored as TWO bf16 planes:
-//     hi = bf16_rn(v),  lo = bf16_rn(v - hi)          (v ~ hi + lo to 2^-17 relative: "fp32-faithful")
-// Same 4 bytes/element of HBM traffic as fp32, but each plane is a K-major bf16 operand that TMA can
-// drop into shared memory for tcgen05.mma unmodified; the 3-term product hi*Whi + lo*Whi + hi*Wlo
-// restores ~16 bits of mantissa in the fp32 TMEM accumulator. Channels [C, Cp) are kept at zero.
+// Activations: NHWC, channel pitch Cp = round_up(C, 8), stored as TWO fp16 planes ("split-fp16"):
+//     hi = fp16_rn(v),  lo = fp16_rn(v - hi)          (v = hi + lo to 2^-22 relative for |v| >= 2^-3; absolute 3e-8 below)
+// Same 4 bytes/element of HBM traffic as fp32, but each plane is a K-major fp16 operand that TMA can drop into shared
+// memory for tcgen05.mma (kind::f16) unmodified. Products accumulate in fp32 TMEM as
+//     3-term  hi*Whi + lo*Whi + hi*Wlo   (weights as fp16 pairs too: ~22 bits per operand)          SNNB_PRECISION_FP32X3
+//     2-term  hi*Whi + lo*Whi            (weights rounded once to fp16: <= 2^-12 relative per weight)  SNNB_PRECISION_FP16W
+//     1-term  hi*Whi                     (half-precision storage mode: no lo planes at all)           SNNB_PRECISION_FP16->FP16
+// Round 1 stored bf16 pairs (8+8 bits); tcgen05's kind::f16 refuses a bf16 A with an fp16 B operand ("illegal instruction",
+// tools/umma_desc_probe.cu), so the pair format itself moved to fp16 to make the 2-term product possible. Range: values are
+// saturated to +-65504 on store (cvt.rn.satfinite), the same range as the reference's own RGBA16F mode.
+// Channels [C, Cp) are kept at zero.
 struct snnb_tensor {
     snnb_context* ctx = nullptr;
-    __nv_bfloat16* hi = nullptr; // plane 0; plane 1 (lo) = hi + plane_elems
-    __nv_bfloat16* lo = nullptr;
+    __half* hi = nullptr; // plane 0; plane 1 (lo) = hi + plane_elems
+    __half* lo = nullptr;
     int n = 0, h = 0, w = 0, c = 0, cp = 0;
     size_t plane_elems = 0;      // n*h*w*cp rounded up to 64 elements (128 B)
     bool owns = true;
@@ -102,13 +108,13 @@ struct snnb_weights {
     // SIMT path: fp32 [K = k*k*IC][OCw], OCw = round_up(OC, 64); BN folded in.
     float* w_f32 = nullptr;
     int ocw = 0;
-    // tcgen05 path: bf16 hi/lo [OCr][Kp] K-major (k index = (ky*k+kx)*IC + ic), Kp = round_up(K, 8), OCr = round_up(OC, 16).
-    __nv_bfloat16* w_hi = nullptr;
-    __nv_bfloat16* w_lo = nullptr;
+    // tcgen05 path: fp16 hi/lo [OCr][Kp] K-major (k index = (ky*k+kx)*IC + ic), Kp = round_up(K, 8), OCr = round_up(OC, 16).
+    __half* w_hi = nullptr;
+    __half* w_lo = nullptr;
     int kp = 0, ocr = 0;
-    // small-input-channel "row window" variant (IC <= 8): bf16 hi/lo [kh][OCr][64], columns in RowPlan K order
-    __nv_bfloat16* w_row_hi = nullptr;
-    __nv_bfloat16* w_row_lo = nullptr;
+    // small-input-channel "row window" variant (IC <= 8): fp16 hi/lo [kh][OCr][64], columns in RowPlan K order
+    __half* w_row_hi = nullptr;
+    __half* w_row_lo = nullptr;
     int row_stride = 0, row_pad = 0;
     // depthwise: fp32 [k*k][Cp]
     // folded bias: fp32 [round_up(OC, 64)]
@@ -139,6 +145,7 @@ struct snnb_context {
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: one bit per kernel, per context
     // (= per device), not a process-wide flag
     uint32_t func_attr_mask = 0;
+    int precision = SNNB_PRECISION_FP32X3; // default product form of per-operator convolution launches (snnb_context_set_precision)
     std::vector<void*> scratch_blocks;
 };
 
@@ -165,6 +172,7 @@ struct ConvArgs {
     const snnb_weights* w;
     int k, stride, pad_x, pad_y, pad_mode, act;
     float alpha;
+    int precision = -1; // SNNB_PRECISION_* of this launch; -1 = the context's default
 };
 int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a);
 int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a); // kernels_umma.cu (tcgen05 + TMA)
@@ -197,7 +205,7 @@ int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc); 
 // ---- host-side weight folding/packing (pack.cpp) -----------------------------------------------------------
 // K ordering of the row-window convolution kernel (kernels_umma.cu): for stride s the taps of one filter row fall
 // into s column parities; within a parity consecutive taps read consecutive pixels of the de-interleaved row, so one
-// tcgen05.mma K step (16 bf16 = 2 pixels x 8 channels) covers two taps of the same parity.
+// tcgen05.mma K step (16 fp16 = 2 pixels x 8 channels) covers two taps of the same parity.
 struct RowPlan {
     int parities = 0;
     int dmin[2]  = {0, 0}; // pixel offset (in de-interleaved index) of the first tap of each parity, relative to the output index
@@ -233,8 +241,8 @@ static inline bool make_row_plan(int k, int stride, int pad_x, RowPlan& rp) {
 
 struct PackedHost {
     std::vector<float> w_f32;           // [K][OCw]
-    std::vector<__nv_bfloat16> w_hi, w_lo; // [OCr][Kp]
-    std::vector<__nv_bfloat16> w_row_hi, w_row_lo; // [kh][OCr][64] (row-window kernel), empty unless IC <= 8
+    std::vector<__half> w_hi, w_lo; // [OCr][Kp]
+    std::vector<__half> w_row_hi, w_row_lo; // [kh][OCr][64] (row-window kernel), empty unless IC <= 8
     int row_stride = 0, row_pad = 0;
     std::vector<float> bias;            // [round_up(OC,64)]
     std::vector<float> gamma, beta, mean, var;

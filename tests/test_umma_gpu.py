@@ -44,6 +44,56 @@ def run_case(ctx, n, h, w, ic, oc, k, s=1, padding="same", act="", alpha=0.1, bi
     return err
 
 
+def run_case_fp16w(ctx, n, h, w, ic, oc, k, s=1, padding="same", act="relu", seed=0, residual=False):
+    """The 2-term product (SNNB_PRECISION_FP16W): split-bf16 activations x ONE fp16 weight plane. Two checks: (a) against the
+    oracle fed with the SAME fp16-rounded folded weights the difference is fp32-accumulation noise (the kernel computes exactly
+    (A_hi + A_lo) * fp16(W)); (b) against the oracle with the original weights the error is the weight rounding (2^-12 relative
+    per weight), inside the 1e-3 per-layer budget."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, (n, h, w, ic)).astype(np.float32)
+    wt = (rng.standard_normal((oc, ic, k, k)) * np.sqrt(2.0 / (k * k * ic))).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, oc).astype(np.float32)
+    bnd = {"gamma": rng.uniform(0.5, 1.5, oc).astype(np.float32), "beta": rng.uniform(-0.1, 0.1, oc).astype(np.float32),
+           "mean": rng.uniform(-0.1, 0.1, oc).astype(np.float32), "var": rng.uniform(0.5, 1.5, oc).astype(np.float32)}
+    o = oracle.same_padding(k, padding == "same") if isinstance(padding, str) else list(padding)
+    oh, ow = oracle.conv_out_dim(h, k, s, o[0], o[1]), oracle.conv_out_dim(w, k, s, o[0], o[1])
+    px, py = (0, 0) if k == 1 else (o[0], o[2])
+    res = rng.uniform(-1, 1, (n, oh, ow, oc)).astype(np.float32) if residual else None
+    # BN folded the way csrc/pack.cpp does it, then the weights rounded to fp16
+    sc = bnd["gamma"] / np.maximum(np.sqrt(bnd["var"] + np.float32(0.001)), np.float32(0.0001))
+    w16 = (wt * sc[:, None, None, None]).astype(np.float16).astype(np.float32)
+    shift = ((b - bnd["mean"]) * sc + bnd["beta"]).astype(np.float32)
+    want16 = oracle.conv2d(x, w16, shift, None, s, px, py, "constant", "" if residual else act, 0.1, (oh, ow))
+    want = oracle.conv2d(x, wt, b, bnd, s, px, py, "constant", "" if residual else act, 0.1, (oh, ow))
+    if residual:
+        want16, want = oracle.add(want16, res, act, 0.1), oracle.add(want, res, act, 0.1)
+    ctx.set_precision("fp16w")
+    try:
+        got = core.conv2d(ctx, x, wt, b, bnd, s, px, py, "constant", act, 0.1, (oh, ow), residual=res, algo="tcgen05")
+    finally:
+        ctx.set_precision("fp32x3")
+    scale = float(np.abs(want).max())
+    e_exact = float(np.abs(got - want16).max()) / scale
+    e_round = float(np.abs(got - want).max()) / scale
+    what = "fp16w conv n%d %dx%d ic%d oc%d k%d s%d" % (n, h, w, ic, oc, k, s)
+    assert e_exact < 3e-5, (what, "kernel vs oracle on fp16-rounded weights", e_exact)
+    assert e_round < 1e-3, (what, "weight rounding error relative to the tensor's range", e_round)
+    return e_exact, e_round
+
+
+@pytest.mark.parametrize("n,h,w,ic,oc,k,s", [(2, 56, 56, 64, 64, 3, 1), (2, 28, 28, 128, 128, 3, 1), (3, 14, 14, 256, 256, 3, 1), (5, 7, 7, 512, 512, 3, 1),
+                                             (2, 56, 56, 64, 128, 3, 2), (2, 28, 28, 144, 24, 1, 1), (2, 7, 7, 320, 1280, 1, 1), (1, 13, 13, 512, 1024, 3, 1),
+                                             (2, 224, 224, 3, 64, 7, 2), (1, 15, 13, 32, 48, 3, 1), (4, 1, 1, 1280, 1000, 1, 1)])
+def test_fp16w_two_term_product(ctx, n, h, w, ic, oc, k, s):
+    run_case_fp16w(ctx, n, h, w, ic, oc, k, s, padding="same" if k > 1 else "valid", seed=ic + oc + k)
+
+
+def test_fp16w_residual_and_wide_tiles(ctx):
+    run_case_fp16w(ctx, 2, 14, 14, 128, 80, 3, residual=True, seed=5)
+    run_case_fp16w(ctx, 8, 14, 14, 256, 512, 3, seed=6)    # n_blk = 256: one accumulator block of 256 columns
+    run_case_fp16w(ctx, 8, 28, 28, 64, 200, 1, padding="valid", seed=7)  # channel tail in a wide tile
+
+
 def test_first_light_1x1(ctx):
     # the smallest complete case: one M tile, one K block, one N tile
     run_case(ctx, 1, 8, 16, 64, 64, 1, padding="valid", bias=False, bn=False)

@@ -120,7 +120,6 @@ int main() {
     float* d;
     cudaMalloc(&d, 512 * sizeof(float));
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
-    run_mixed(d);
     const uint64_t SW128 = (1ull << 16) | (1ull << 46) | (2ull << 61);
     // (1) SWIZZLE_128B: aligned reference, then start shifted by r0 rows with and without base_offset, SBO = 1024 and 2048
     run("SW128 start+0 rows, SBO 1024, base_offset 0 (reference: row m chunk c -> piece m*8 + (c ^ (m&7)))", SW128 | (64ull << 32), 0, d);
@@ -139,5 +138,12 @@ int main() {
     run("NOSW LBO 2048 B, SBO 128 B (chunk-major planes of 128 rows x 16 B): expect piece m + 128*c", NOSW | (128ull << 16) | (8ull << 32), 0, d);
     run("NOSW LBO 16 B, SBO 128 B (OVERLAPPING sliding window): expect piece m + c", NOSW | (1ull << 16) | (8ull << 32), 0, d);
     run("NOSW LBO 16 B, SBO 256 B (stride-2 rows?): expect piece 2*(m/8)*8.. ", NOSW | (1ull << 16) | (16ull << 32), 0, d);
+    // halo mode of conv_umma_kernel: start shifted by (ky * 10 + kx) pixel rows, SBO = 10 rows; expect piece (m/8*10 + m%8 + r0)*8 + (c ^ (row & 7))
+    for (int r0 : {1, 2, 10, 11, 12, 21, 22}) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "HALO SW128 start+%d rows, SBO 1280, base_offset 0: row m -> smem row %d + (m/8)*10 + m%%8", r0, r0);
+        run(buf, SW128 | (80ull << 32), r0 * 128, d);
+    }
+    run_mixed(d); // LAST: a refused operand-format combination is a sticky 'illegal instruction' error
     return 0;
 }
