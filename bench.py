@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames per step of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer roofline table to stderr")
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "fp16w", "fp16"],
+                    help="product form of the tensor-core path (snnb.h SNNB_PRECISION_*); the headline is fp32x3")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's batch per GPU (the metric's config is the default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -232,7 +234,7 @@ def main():
     d = tempfile.mkdtemp(prefix="snnb_bench_r%d_" % rank)
     path, layers = modelzoo.build(key, d)
     ctx = core.GpuContext(local_rank)
-    model = core.MixedInferenceCore(ctx, path, batch=batch, conv_algo=args.algo, use_cuda_graph=not args.no_graph, fuse=not args.no_fuse)
+    model = core.MixedInferenceCore(ctx, path, batch=batch, conv_algo=args.algo, use_cuda_graph=not args.no_graph, fuse=not args.no_fuse, precision=args.precision)
     arena_bytes = parallel.broadcast_model_weights(model, dev, src=0) if world > 1 else model.weight_arena()[1]
 
     x = modelzoo.synthetic_input(key, batch, seed=7767517 + rank)

@@ -65,9 +65,9 @@ constexpr int HL_TW = 8, HL_TH = 16, HL_W = HL_TW + 2, HL_H = HL_TH + 2;
 constexpr int HL_PLANE         = (HL_W * HL_H * 128 + 1023) / 1024 * 1024; // 23 552 B: one plane of the halo tile, 1024-aligned
 constexpr int HL_A_STAGES      = 2;
 constexpr int HL_A_STAGE_BYTES = 2 * HL_PLANE;
-constexpr int HL_B_STAGES      = 3;              // == the STAGES template argument of the halo instantiations
-constexpr int HL_B_STAGE_BYTES = 2 * UM_B_BYTES; // [B_hi ; B_lo] of 128 rows or one plane of up to 256 rows
-constexpr int HL_SMEM_BYTES    = HL_A_STAGES * HL_A_STAGE_BYTES + HL_B_STAGES * HL_B_STAGE_BYTES + UM_STG_BYTES + 1024 + 384;
+constexpr int HL_B_STAGES      = 6;              // == the STAGES template argument of the halo instantiations (barrier slots)
+constexpr int HL_B_RING_BYTES  = 6 * UM_B_BYTES; // 96 KB of weight stages: 3 x 32 KB ([B_hi ; B_lo] of 128 rows / one plane of 256 rows) or 6 x 16 KB
+constexpr int HL_SMEM_BYTES    = HL_A_STAGES * HL_A_STAGE_BYTES + HL_B_RING_BYTES + UM_STG_BYTES + 1024 + 384;
 
 struct UmmaParams {
     __half* out_hi;
@@ -93,6 +93,7 @@ struct UmmaParams {
     long long* trace; // profiling aid (env SNNB_UMMA_TRACE): CTA 0 writes clock64 stamps per role, [6][256]
     int ablate; // profiling aid (env SNNB_UMMA_ABLATE, results are WRONG when set): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs
     int has_lo; // the output tensor has a lo plane (0 in the fp16 storage mode)
+    int b_stages, b_stage_bytes; // halo mode: depth and stage size of the weight ring (3 x 32 KB, or 6 x 16 KB when a stage fits)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -522,7 +523,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
     // HALO: [A ring: HL_A_STAGES x (hi plane, lo plane)] [B ring: STAGES x 32 KB] [staging]; else [ring: STAGES x 64 KB] [staging]
     const uint32_t b_ring    = smem_base + (HALO ? HL_A_STAGES * HL_A_STAGE_BYTES : 0);
-    const uint32_t stg       = HALO ? b_ring + STAGES * HL_B_STAGE_BYTES : smem_base + STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned), one buffer per epilogue group
+    const uint32_t stg       = HALO ? b_ring + HL_B_RING_BYTES : smem_base + STAGES * UM_STAGE_BYTES; // epilogue staging (1024-aligned), one buffer per epilogue group
     const uint32_t bar_base  = stg + (SPLIT_EPI ? 2 : 1) * UM_STG_BYTES;
     // barrier slots (8 bytes each): full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), TMEM base slot, residual barrier
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
@@ -534,11 +535,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // Dynamic work distribution. CTA b starts with work item b; every further item is drawn from a global counter by the
     // producer warp (persistent CTAs on a statically striped grid finished up to 17 % apart on store-heavy layers) and handed
     // to the MMA thread and the epilogue warps through this ring: id in sched_id[slot], full/empty mbarriers per slot.
-    auto sched_full  = [&](int s) { return bar_base + 128u + 8u * s; };
-    auto sched_empty = [&](int s) { return bar_base + 192u + 8u * s; };
-    auto sched_id    = [&](int s) { return bar_base + 256u + 4u * s; };
-    auto a_full_bar  = [&](int s) { return bar_base + 288u + 8u * s; }; // HALO: the halo-tile ring
-    auto a_empty_bar = [&](int s) { return bar_base + 320u + 8u * s; };
+    const uint32_t sched_base = bar_base + 8u * (2 * STAGES + 8); // behind the slots above (2 * STAGES + 8 of them)
+    auto sched_full  = [&](int s) { return sched_base + 8u * s; };
+    auto sched_empty = [&](int s) { return sched_base + 64u + 8u * s; };
+    auto sched_id    = [&](int s) { return sched_base + 128u + 4u * s; };
+    auto a_full_bar  = [&](int s) { return sched_base + 160u + 8u * s; }; // HALO: the halo-tile ring
+    auto a_empty_bar = [&](int s) { return sched_base + 176u + 8u * s; };
     // consumer side: wait for sequence number `seq`, read its work id, release the slot (one arrive per consuming warp)
     auto sched_take = [&](int seq, bool arrive) {
         const int slot = seq & (UM_SCHED_SLOTS - 1);
@@ -640,8 +642,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 // no parameter loads: ncu r01 showed ~60 dependent scalar instructions/iteration bounding the kernel).
                 // K block kb = (ky * ks + kx) * cbs + cb; the counters are decoded once per work item and then stepped.
                 if constexpr (HALO) {
-                    // one halo tile per channel block, then the nine taps' weights: K order (cb, tap)
-                    for (int cb = 0; cb < cbs; ++cb) {
+                    // K order (cb, tap): one halo tile per channel block, then the nine taps' weights. The halo tile of the NEXT
+                    // unit (next channel block, or the next work item's first) is requested one unit ahead, after this unit's first
+                    // weight stages are in flight: its ~1 us latency used to sit exposed at every tile boundary (r02 trace: ~2 k clk
+                    // of 7.5 k per 56x56x64 tile).
+                    auto issue_halo = [&](int w, int cb) {
+                        const int tile_ = w % total_tiles, m_ = tile_ % m_tiles;
+                        const int bx_ = m_ % p.tiles_x, by_ = (m_ / p.tiles_x) % p.tiles_y, bn_ = m_ / (p.tiles_x * p.tiles_y);
                         mbar_wait(a_empty_bar(hstage), hphase ^ 1u);
                         if (elect_one()) {
                             const uint32_t sA = smem_base + hstage * HL_A_STAGE_BYTES, fb = a_full_bar(hstage);
@@ -649,18 +656,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                 mbar_arrive(fb);
                             } else {
                                 mbar_expect_tx(fb, (TERMS == 1 ? 1u : 2u) * (uint32_t) (HL_W * HL_H * 128));
-                                tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0, iy0, n0);
-                                if (TERMS >= 2) tma_load_4d(sA + HL_PLANE, &tmA_lo, fb, cb * UM_BLOCK_K, ix0, iy0, n0);
+                                tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, bx_ * HL_TW - p.pad_x, by_ * HL_TH - p.pad_y, bn_);
+                                if (TERMS >= 2) tma_load_4d(sA + HL_PLANE, &tmA_lo, fb, cb * UM_BLOCK_K, bx_ * HL_TW - p.pad_x, by_ * HL_TH - p.pad_y, bn_);
                             }
                         }
+                        __syncwarp();
                         if (++hstage == HL_A_STAGES) hstage = 0, hphase ^= 1u;
+                    };
+                    if (seq == 0) issue_halo(work, 0); // prologue: every later unit's tile is requested by its predecessor
+                    int nwork = total_work;           // next work item, known once the atomic draw above has returned
+                    for (int cb = 0; cb < cbs; ++cb) {
                         int wk = cb * UM_BLOCK_K;
                         for (int tap = 0; tap < 9; ++tap, wk += icp) {
+                            if (tap == 3) { // three weight stages are in flight: now the next unit's halo tile
+                                if (cb + 1 < cbs) {
+                                    issue_halo(work, cb + 1);
+                                } else {
+                                    nwork = __shfl_sync(0xffffffffu, next, 0);
+                                    if (nwork < total_work) issue_halo(nwork, 0);
+                                }
+                            }
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             UM_TRACE(0, tr);
                             ++tr;
                             if (elect_one()) {
-                                const uint32_t sB = b_ring + stage * HL_B_STAGE_BYTES, fb = full_bar(stage);
+                                const uint32_t sB = b_ring + stage * p.b_stage_bytes, fb = full_bar(stage);
                                 if (skip_tma) {
                                     mbar_arrive(fb);
                                 } else {
@@ -669,10 +689,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                     if (TERMS == 3) tma_load_2d(sB + b_lo_off, &tmB_lo, fb, wk, oc0);
                                 }
                             }
-                            if (++stage == STAGES) stage = 0, phase ^= 1u;
+                            if (++stage == p.b_stages) stage = 0, phase ^= 1u;
                         }
                     }
-                    work = __shfl_sync(0xffffffffu, next, 0);
+                    work = nwork;
                     continue;
                 }
                 int cb = kb0 % cbs, tap0 = kb0 / cbs;
@@ -745,40 +765,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             tc_fence_after();
                             UM_TRACE(1, tr);
                             const uint64_t a_hi = halo + (uint64_t) (uint32_t) tap_off, a_lo = a_hi + (HL_PLANE >> 4);
-                            const uint64_t b_cat = bdesc0 + (uint64_t) (uint32_t) (stage * (HL_B_STAGE_BYTES >> 4));
+                            const uint64_t b_cat = bdesc0 + (uint64_t) (uint32_t) (stage * (p.b_stage_bytes >> 4));
                             const uint32_t first = (cb > 0 || tap > 0) ? 1u : 0u;
+                            // First K step, then the look-ahead test of the next stage's barrier (its ~150 clk latency hides behind
+                            // the six MMAs still to be issued: behind only two, as in r01, the pipe ran dry ~180 clk per K block),
+                            // then the rest.
                             if (!no_mma) {
-                                if (TERMS == 3) {
-#pragma unroll
-                                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (first || j > 0) ? 1u : 0u);
-                                    umma_f16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
-                                    umma_f16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
-                                } else if (TERMS == 2) {
-#pragma unroll
-                                    for (int j = 0; j < 3; ++j) {
-                                        umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, (first || j > 0) ? 1u : 0u);
-                                        umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
-                                    }
-                                } else {
-                                    umma_f16(d_tmem, a_hi + 0u, b_cat + 0u, idesc, first);
-                                    umma_f16(d_tmem, a_hi + 2u, b_cat + 2u, idesc, 1u);
-                                }
+                                umma_f16(d_tmem, a_hi, b_cat, TERMS == 3 ? idesc_cat : idesc, first);
+                                if (TERMS == 2) umma_f16(d_tmem, a_lo, b_cat, idesc, 1u);
                             }
                             const int cur         = stage;
-                            const uint32_t nphase = phase ^ (stage == STAGES - 1 ? 1u : 0u);
-                            stage                 = stage == STAGES - 1 ? 0 : stage + 1;
+                            const uint32_t nphase = phase ^ (stage == p.b_stages - 1 ? 1u : 0u);
+                            stage                 = stage == p.b_stages - 1 ? 0 : stage + 1;
                             phase                 = nphase;
                             ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking look-ahead
                             if (!no_mma) {
                                 if (TERMS == 3) {
-                                    umma_f16(d_tmem, a_lo + 4u, b_cat + 4u, idesc, 1u);
-                                    umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+#pragma unroll
+                                    for (int j = 1; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, 1u);
+#pragma unroll
+                                    for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
                                 } else if (TERMS == 2) {
-                                    umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
-                                    umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+#pragma unroll
+                                    for (int j = 1; j < UM_BLOCK_K / 16; ++j) {
+                                        umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, 1u);
+                                        umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
+                                    }
                                 } else {
-                                    umma_f16(d_tmem, a_hi + 4u, b_cat + 4u, idesc, 1u);
-                                    umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
+#pragma unroll
+                                    for (int j = 1; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, 1u);
                                 }
                             }
                             umma_commit(empty_bar(cur)); // weight slot free once these MMAs retire
@@ -800,22 +815,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const uint64_t a_hi = desc0 + (uint64_t) (uint32_t) (stage * (UM_STAGE_BYTES >> 4)), a_lo = a_hi + (UM_A_BYTES >> 4);
                     const uint64_t b_cat = a_hi + (2 * UM_A_BYTES >> 4); // rows [0, n_blk) = B_hi, [n_blk, 2 n_blk) = B_lo
                     // UMMA_K = 16 fp16 = 32 bytes: K step j advances the start address by 2 (x16 B)
+                    const uint32_t first = kb > kb0 ? 1u : 0u;
+                    // first K step | look-ahead test of the next stage (latency hidden behind the remaining MMAs) | the rest
                     if (!no_mma) {
-                        if (TERMS == 3) {
-#pragma unroll
-                            for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, (kb > kb0 || j > 0) ? 1u : 0u);
-                            umma_f16(d_tmem, a_lo + 0u, b_cat + 0u, idesc, 1u);
-                            umma_f16(d_tmem, a_lo + 2u, b_cat + 2u, idesc, 1u);
-                        } else if (TERMS == 2) { // (A_hi + A_lo) x B16, K step by K step
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
-                                umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
-                            }
-                        } else {
-                            umma_f16(d_tmem, a_hi + 0u, b_cat + 0u, idesc, kb > kb0 ? 1u : 0u);
-                            umma_f16(d_tmem, a_hi + 2u, b_cat + 2u, idesc, 1u);
-                        }
+                        umma_f16(d_tmem, a_hi, b_cat, TERMS == 3 ? idesc_cat : idesc, first);
+                        if (TERMS == 2) umma_f16(d_tmem, a_lo, b_cat, idesc, 1u);
                     }
                     const int cur         = stage;
                     const uint32_t nphase = phase ^ (stage == STAGES - 1 ? 1u : 0u);
@@ -824,14 +828,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking
                     if (!no_mma) {
                         if (TERMS == 3) {
-                            umma_f16(d_tmem, a_lo + 4u, b_cat + 4u, idesc, 1u);
-                            umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+#pragma unroll
+                            for (int j = 1; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, 1u);
+#pragma unroll
+                            for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
                         } else if (TERMS == 2) {
-                            umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
-                            umma_f16(d_tmem, a_lo + 6u, b_cat + 6u, idesc, 1u);
+#pragma unroll
+                            for (int j = 1; j < UM_BLOCK_K / 16; ++j) {
+                                umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, 1u);
+                                umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
+                            }
                         } else {
-                            umma_f16(d_tmem, a_hi + 4u, b_cat + 4u, idesc, 1u);
-                            umma_f16(d_tmem, a_hi + 6u, b_cat + 6u, idesc, 1u);
+#pragma unroll
+                            for (int j = 1; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, 1u);
                         }
                     }
                     umma_commit(empty_bar(cur));                           // smem slot free once these MMAs retire
@@ -1447,6 +1456,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     p.cblocks = (in->c + UM_BLOCK_K - 1) / UM_BLOCK_K;
     const int terms = conv_terms(ctx, a);
     p.has_lo        = out->lo != nullptr;
+    p.b_stages = 0, p.b_stage_bytes = 0;
     OcPlan op       = plan_oc_ksplit(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, tp.tw, a.k * a.k * p.cblocks, ctx->sm_count, terms);
     // halo mode (3x3, stride 1): 8 x 16-pixel tiles whose nine taps share one halo load; taken when the cost model prefers it
     // (fewer bytes per K block against the MMA rows lost where 8 / 16 do not divide the feature map)
@@ -1457,6 +1467,8 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         const OcPlan hp = plan_oc_ksplit(out->c, hx * hy * out->n, UM_BLOCK_M, HL_TW, 9 * p.cblocks, ctx->sm_count, terms, true);
         if (hp.n_blk > 0 && hp.cost < op.cost) {
             halo = true, op = hp;
+            p.b_stage_bytes = (terms == 3 ? 2 : 1) * op.n_blk * 128 <= UM_B_BYTES ? UM_B_BYTES : 2 * UM_B_BYTES; // 16 KB when a stage fits, else 32 KB
+            p.b_stages      = HL_B_RING_BYTES / p.b_stage_bytes;
             p.tw = HL_TW, p.th = HL_TH, p.tn = 1, p.rows_used = UM_BLOCK_M;
             p.tiles_x = hx, p.tiles_y = hy, p.tiles_n = out->n;
         }
