@@ -45,7 +45,7 @@ static int ensure_stage_host(snnb_context* ctx, size_t bytes) {
     return 0;
 }
 
-int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** out) {
+int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** out, bool lo_plane) {
     SNNB_REQUIRE(ctx && out, "tensor_alloc: null argument");
     SNNB_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0, "tensor_alloc: bad dims %d %d %d %d", n, h, w, c);
     auto t   = std::make_unique<snnb_tensor>();
@@ -53,9 +53,10 @@ int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** ou
     t->n = n, t->h = h, t->w = w, t->c = c, t->cp = round_up(c, 8);
     size_t elems   = (size_t) n * h * w * t->cp;
     t->plane_elems = (elems + 63) / 64 * 64;
-    SNNB_CUDA_OK(cudaMalloc(&t->hi, t->plane_elems * 2 * sizeof(__half)));
-    t->lo = t->hi + t->plane_elems;
-    SNNB_CUDA_OK(cudaMemsetAsync(t->hi, 0, t->plane_elems * 2 * sizeof(__half), ctx->stream));
+    const size_t planes = lo_plane ? 2 : 1; // half-precision storage mode: the hi plane alone
+    SNNB_CUDA_OK(cudaMalloc(&t->hi, t->plane_elems * planes * sizeof(__half)));
+    t->lo = lo_plane ? t->hi + t->plane_elems : nullptr;
+    SNNB_CUDA_OK(cudaMemsetAsync(t->hi, 0, t->plane_elems * planes * sizeof(__half), ctx->stream));
     *out = t.release();
     return 0;
 }

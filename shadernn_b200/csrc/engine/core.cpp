@@ -60,6 +60,8 @@ static bool allZeroPadding(const PaddingSpec& p) {
 
 bool MixedInferenceCore::init(std::string& err) {
     const int N = (int) options.batch;
+    // ShaderGenOptions::preferrHalfPrecision (layeroption.h:43 -> RGBA16F textures): every tensor is ONE fp16 plane
+    const bool twoPlanes = options.precision != SNNB_PRECISION_FP16;
     std::unordered_map<GenericModelLayer*, int> order;
     for (size_t i = 0; i < graph.sorted.size(); ++i) order[graph.sorted[i]] = (int) i;
 
@@ -167,7 +169,7 @@ bool MixedInferenceCore::init(std::string& err) {
         // dims of the tensor = dims of `owner` (for conv->add fusion both agree)
         const Dims& d = graph.outputDims[order[owner]];
         snnb_tensor* t = nullptr;
-        if (tensor_alloc(ctx, N, (int) d.height, (int) d.width, (int) d.depth, &t)) {
+        if (tensor_alloc(ctx, N, (int) d.height, (int) d.width, (int) d.depth, &t, twoPlanes)) {
             err = get_error();
             return false;
         }
@@ -202,7 +204,7 @@ bool MixedInferenceCore::init(std::string& err) {
             const bool prepad = cl->wantsPrepad(L->inputs[0], L->output, options.convAlgo, ph, pw);
             std::swap(cl->weights, probe_w);
             if (prepad) {
-                if (tensor_alloc(ctx, N, ph, pw, L->inputs[0]->c, &cl->prepadded)) {
+                if (tensor_alloc(ctx, N, ph, pw, L->inputs[0]->c, &cl->prepadded, twoPlanes)) {
                     err = get_error();
                     return false;
                 }
@@ -212,7 +214,7 @@ bool MixedInferenceCore::init(std::string& err) {
         if (L->typeName == "Dense") {
             auto* dl = static_cast<DenseLayer*>(L);
             if (L->inputs[0]->h * L->inputs[0]->w != 1) {
-                if (tensor_alloc(ctx, N, 1, 1, (int) dl->numInputPlanes, &dl->flat)) {
+                if (tensor_alloc(ctx, N, 1, 1, (int) dl->numInputPlanes, &dl->flat, twoPlanes)) {
                     err = get_error();
                     return false;
                 }

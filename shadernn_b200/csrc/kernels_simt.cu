@@ -35,9 +35,11 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float v[
         v[2 * j] = a.x + b.x, v[2 * j + 1] = a.y + b.y;
     }
 }
+// lo == nullptr: the tensor lives in the half-precision storage mode (SNNB_PRECISION_FP16, one plane). The test is uniform
+// over the grid.
 __device__ __forceinline__ void load8(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off, float v[8]) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
-    const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    const uint4 l = lo ? __ldg(reinterpret_cast<const uint4*>(lo + off)) : make_uint4(0u, 0u, 0u, 0u);
     unpack8(h, l, v);
 }
 
@@ -54,17 +56,17 @@ __device__ __forceinline__ void store8(__half* __restrict__ hi, __half* __restri
     split2(v[4], v[5], h.z, l.z);
     split2(v[6], v[7], h.w, l.w);
     *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
 }
 
 __device__ __forceinline__ float load1(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off) {
-    return __half2float(hi[off]) + __half2float(lo[off]);
+    return __half2float(hi[off]) + (lo ? __half2float(lo[off]) : 0.0f);
 }
 __device__ __forceinline__ void store1(__half* __restrict__ hi, __half* __restrict__ lo, size_t off, float v) {
     uint32_t h, l;
     split2(v, 0.0f, h, l);
     hi[off] = __ushort_as_half((unsigned short) (h & 0xffffu));
-    lo[off] = __ushort_as_half((unsigned short) (l & 0xffffu));
+    if (lo) lo[off] = __ushort_as_half((unsigned short) (l & 0xffffu));
 }
 
 // Activations: ids of conv2dVulkan.cpp:57-71; math of shadertemplate_vk_conv2d.comp:290-340 (SiLU computed
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(256) pool_kernel(TV in, TV out, int k, int str
                 const bool ok  = oky && fx < efx;
                 const size_t o = (((size_t) n * in.H + sy + (ok ? fy : 0)) * in.W + sx + (ok ? fx : 0)) * in.Cp + c;
                 th[fx] = __ldg(reinterpret_cast<const uint4*>(in.hi + o));
-                tl[fx] = __ldg(reinterpret_cast<const uint4*>(in.lo + o));
+                tl[fx] = in.lo ? __ldg(reinterpret_cast<const uint4*>(in.lo + o)) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
             for (int fx = 0; fx < KW; ++fx) {

@@ -1384,7 +1384,7 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     for (int plane = 0; plane < 2; ++plane)
         for (int par = 0; par < 2; ++par) {
             const int pp = par < rp.parities ? par : 0; // unused maps alias parity 0 (kernel never issues them)
-            __half* base = (plane ? in->lo : in->hi) + (size_t) pp * 8;
+            __half* base = ((plane && in->lo) ? in->lo : in->hi) + (size_t) pp * 8; // half-precision storage mode: the lo maps are never issued
             const int wp        = (in->w - pp + a.stride - 1) / a.stride; // pixels of this parity per row
             const cuuint64_t dims[4]    = {8, (cuuint64_t) (wp > 0 ? wp : 1), (cuuint64_t) in->h, (cuuint64_t) in->n};
             const cuuint64_t strides[3] = {(cuuint64_t) a.stride * 16, (cuuint64_t) in->w * 16, (cuuint64_t) in->h * in->w * 16};
@@ -1757,6 +1757,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) depthwise_tma_kernel(const __gr
 }
 
 bool depthwise_tma_supported(const ConvArgs& a) {
+    if (!a.in->lo || !a.out->lo) return false; // half-precision storage mode: the CUDA-core kernel (one plane)
     // tiles are 8x16 (stride 1) / 4x8 (stride 2) output pixels: tiny feature maps (7x7) would leave most of a tile empty
     const int tw = a.stride == 1 ? 16 : 8, th = a.stride == 1 ? 8 : 4;
     const int tx = (a.out->w + tw - 1) / tw, ty = (a.out->h + th - 1) / th;

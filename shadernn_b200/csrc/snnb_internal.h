@@ -259,6 +259,6 @@ void pack_channels_host(int C, const float* g, const float* b, const float* m, c
 // Copy a PackedHost into device memory at `base` (device, 256-B aligned) and point `w` at it. Returns bytes used.
 int place_weights(snnb_context* ctx, const PackedHost& p, char* base, snnb_weights* w);
 
-int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** out);
+int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** out, bool lo_plane = true);
 
 } // namespace snnb

@@ -383,7 +383,7 @@ def convert(onnx_path, out_dir, input_hw=None, split=True, fold_pads=True):
 def torch_eval(g, x_nhwc):
     import torch
     import torch.nn.functional as F
-    init = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in g["init"].items() if v.dtype.kind == "f"}
+    init = {k: torch.from_numpy(np.array(v)) for k, v in g["init"].items() if v.dtype.kind == "f"}
     vals = {g["inputs"][0][0]: torch.from_numpy(np.ascontiguousarray(x_nhwc, dtype=np.float32)).permute(0, 3, 1, 2).contiguous()}
     with torch.no_grad():
         for nd in g["nodes"]:

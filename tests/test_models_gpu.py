@@ -226,6 +226,69 @@ def test_fused_graph_equals_unfused_and_graph_replay(ctx, model_dir, name, hw, k
         assert np.array_equal(c0, c1) and np.array_equal(c1, c2)
 
 
+# ---- half-precision storage mode (SURVEY §8 f-N4): the reference's preferrHalfPrecision / RGBA16F textures ------------------
+HALF_TOL = 0.1  # the reference's own half-precision threshold (demo/common/testutil.h:1195), relative to each tensor's range
+
+
+@pytest.mark.parametrize("name,hw,batch,sample", [("resnet18", (224, 224), 32, 2), ("mobilenetv2", (224, 224), 16, 2), ("yolov3tiny", (416, 416), 2, 1),
+                                                  ("candy", (256, 256), 1, 1), ("espcn", (224, 224), 1, 1)])
+def test_fp16_storage_mode_every_layer(ctx, model_dir, name, hw, batch, sample):
+    # one fp16 plane per tensor and per weight, one MMA per product, half the bytes: every layer within the reference's
+    # half-precision tolerance, and for the classifiers the same top-1 as the fp32-class oracle
+    m, x, want, worst = baseline_size_check(ctx, name, hw, batch, sample, model_dir, True, eps=HALF_TOL, precision="fp16")
+    if name in ("resnet18", "mobilenetv2"):
+        out, cls = m.run(x)
+        assert np.array_equal(cls[:sample], oracle.argmax1(want[-1]))
+    assert worst < 0.02, worst  # measured: ~1e-3 .. 1e-2, an order of magnitude inside the reference's 0.1
+
+
+def _real_candy_head(tmp_dir):
+    from _candy_fixture import head_graph as _head_graph
+    from shadernn_b200 import onnx2snn
+    g, x, want = _head_graph()
+    layers = onnx2snn.convert_graph(g, input_hw=(64, 64))
+    return modelzoo.write_model(layers, os.path.join(tmp_dir, "candy_head_layers.json"), split=True), x, want
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "fp16w"])
+def test_real_candy_weights_head_vs_torch_golden(ctx, tmp_path, precision):
+    # REFERENCE-HELD WEIGHTS (the first two stages of modelzoo/StyleTransfer/candy-9_simplified.onnx, frozen in
+    # tests/golden/candy_head_golden.npz) against what torch computed for those ONNX nodes: 9x9 and 3x3-stride-2 convolutions
+    # with reflect padding, InstanceNorm, ReLU - on the CUDA engine, through the converter's JSON
+    path, x, want = _real_candy_head(str(tmp_path))
+    m = core.MixedInferenceCore(ctx, path, batch=1, input_hw=(64, 64), fuse=True, precision=precision)
+    out, _ = m.run(x, want_classes=False)
+    rel = assert_layer_close(out, want, EPS, "real Candy head")
+    print("real Candy weights, first two stages, %s: max|err|/range %.3g" % (precision, rel))
+    assert rel < LIMIT[precision]
+
+
+REF_MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "_ref_models")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_MODELS, "candy-9_simplified_layers.json")),
+                    reason="tests/golden/_ref_models/ is generated by __graft_entry__.build() where /root/reference exists (and travels with the snapshot)")
+@pytest.mark.parametrize("precision", ["fp32x3", "fp16w"])
+def test_real_candy_whole_model_vs_torch_and_oracle(ctx, precision):
+    # the WHOLE real-weight model (converted from the reference's ONNX file by build()): final image against torch's evaluation
+    # of the ONNX graph (golden, generated with it) and every layer against the oracle
+    path = os.path.join(REF_MODELS, "candy-9_simplified_layers.json")
+    z = np.load(os.path.join(REF_MODELS, "candy_full_golden.npz"))
+    x, want = z["x"], z["y"]
+    layers_want = oracle.Model(path).run(x, return_all=True)
+    m = core.MixedInferenceCore(ctx, path, batch=1, fuse=False, precision=precision)
+    m.set_input(x)
+    m.forward()
+    ctx.sync()
+    worst = 0.0
+    for i in range(m.num_layers):
+        worst = max(worst, assert_layer_close(m.layer_output(i), layers_want[i], EPS, m.layer_info(i)[0]))
+    out, _ = m.run(x, want_classes=False)
+    rel = assert_layer_close(out, want, EPS, "real Candy output vs torch(ONNX)")
+    print("real Candy 224x224, %s: per-layer worst vs oracle %.3g, output vs torch(ONNX) %.3g" % (precision, worst, rel))
+    assert max(worst, rel) < LIMIT[precision]
+
+
 def test_batch_consistency_at_baseline_size(ctx, model_dir):
     # size-independent property at BASELINE.json's full ResNet-18 config (224x224x3, batch 32): every image's logits
     # equal what the same image yields in a batch of 1. No kernel reduces across images; the only difference allowed is
