@@ -213,6 +213,9 @@ int snnb_model_layer_output(snnb_model* m, int layer, float* host_nhwc, size_t c
 int snnb_model_dump_outputs(snnb_model* m, const char* dir);
 /* Per-layer device time of one forward pass, ms, via event pairs (writeTimeStat, core.cpp:437-442). times[num_layers]. */
 int snnb_model_time_layers(snnb_model* m, float* times_ms, int capacity);
+/* Name of the CUDA kernel layer `layer` launched in the last snnb_model_time_layers() pass ("" for a layer that launched none:
+ * inputs, fused-away layers). What bench.py attributes the per-kernel roofline to. */
+int snnb_model_layer_kernel(const snnb_model* m, int layer, char* name, int name_cap);
 /* Kernels launched by one forward pass. */
 int snnb_model_launches_per_forward(const snnb_model* m);
 /* YOLO detection output of the last run (yololayer.cpp:177-226): rows {class, score, x, y, w, h}; returns the

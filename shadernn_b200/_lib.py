@@ -110,6 +110,7 @@ SIGNATURES = {
     "snnb_model_dump_outputs": (C.c_int, [vp, C.c_char_p]),
     "snnb_model_time_layers": (C.c_int, [vp, c_float_p, C.c_int]),
     "snnb_model_launches_per_forward": (C.c_int, [vp]),
+    "snnb_model_layer_kernel": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int]),
     "snnb_model_get_boxes": (C.c_int, [vp, C.c_int, c_float_p, C.c_int, c_int_p]),
     "snnb_model_weight_arena": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
 }

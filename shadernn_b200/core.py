@@ -422,6 +422,12 @@ class MixedInferenceCore:
         check(lib().snnb_model_time_layers(self.h, arr, n), "snnb_model_time_layers")
         return np.array(list(arr), dtype=np.float32)
 
+    def layer_kernel(self, layer):
+        """Kernel launched by `layer` in the last time_layers() pass ("" if none)."""
+        buf = C.create_string_buffer(128)
+        check(lib().snnb_model_layer_kernel(self.h, int(layer), buf, 128), "snnb_model_layer_kernel")
+        return buf.value.decode()
+
     def dump_outputs(self, directory):
         check(lib().snnb_model_dump_outputs(self.h, directory.encode()), "snnb_model_dump_outputs")
 

@@ -24,7 +24,11 @@ MixedInferenceCore::~MixedInferenceCore() {
     if (scratchArena) cudaFree(scratchArena);
     if (ioStage) cudaFree(ioStage);
     if (argmaxDev) cudaFree(argmaxDev);
+    if (yoloDev) cudaFree(yoloDev);
+    if (yoloHost) cudaFreeHost(yoloHost);
     for (auto& sl : slots) {
+        if (sl.yoloDev) cudaFree(sl.yoloDev);
+        if (sl.yoloHost) cudaFreeHost(sl.yoloHost);
         if (sl.stageIn) cudaFree(sl.stageIn);
         if (sl.stageOut) cudaFree(sl.stageOut);
         if (sl.argmax) cudaFree(sl.argmax);
@@ -327,6 +331,13 @@ bool MixedInferenceCore::init(std::string& err) {
         err = "cudaMalloc(io staging) failed";
         return false;
     }
+    if (yolo) {
+        const size_t yb = YOLOLayer::candidateBytes(N);
+        if (cudaMalloc(&yoloDev, yb) != cudaSuccess || cudaMallocHost(&yoloHost, yb) != cudaSuccess) {
+            err = "cudaMalloc(YOLO candidate lists) failed";
+            return false;
+        }
+    }
     {
         GenericModelLayer* last = nullptr;
         for (auto* L : outputLayers)
@@ -415,10 +426,7 @@ int MixedInferenceCore::getOutput(int idx, float* host, size_t capacityFloats) {
 int MixedInferenceCore::run(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1) {
     if (setInput(0, hostInput)) return 1;
     if (forward()) return 1;
-    if (yolo) {
-        SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-        if (yolo->decode(ctx, boxes)) return 1;
-    }
+    if (yolo && decodeYolo(yoloDev, yoloHost, true)) return 1;
     int outIdx = -1;
     for (size_t i = 0; i < outputLayers.size(); ++i)
         if (outputLayers[i]->typeName != "YOLO") {
@@ -439,6 +447,18 @@ int MixedInferenceCore::run(const float* hostInput, float* hostOutput, size_t ca
     return 0;
 }
 
+// YOLO decode: threshold + compaction on the device (yololayer.cpp:115-164 up to the confidence test), a few KB of candidates
+// to the host, then the exact score formula, score sort and NMS there (identical lists, identical order: finishDecode).
+int MixedInferenceCore::decodeYolo(void* dev, void* host, bool sync) {
+    if (yolo->enqueueCandidates(ctx, dev)) return 1;
+    SNNB_CUDA_OK(cudaMemcpyAsync(host, dev, YOLOLayer::candidateBytes((int) options.batch), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!sync) return 0;
+    SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const int rc = yolo->finishDecode(host, boxes);
+    if (rc < 0) return yolo->decode(ctx, boxes); // an image overflowed its candidate list: all-host decode of the (still resident) heads
+    return rc;
+}
+
 // ---- streaming (additive to the reference's synchronous run) ---------------------------------------------------------
 int MixedInferenceCore::ensureStreaming() {
     if (copyStream) return 0;
@@ -450,6 +470,10 @@ int MixedInferenceCore::ensureStreaming() {
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.h2dDone, cudaEventDisableTiming));
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.stageFree, cudaEventDisableTiming));
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.resultReady, cudaEventDisableTiming));
+        if (yolo) {
+            SNNB_CUDA_OK(cudaMalloc(&sl.yoloDev, YOLOLayer::candidateBytes((int) options.batch)));
+            SNNB_CUDA_OK(cudaMallocHost(&sl.yoloHost, YOLOLayer::candidateBytes((int) options.batch)));
+        }
     }
     return 0;
 }
@@ -464,14 +488,14 @@ int MixedInferenceCore::submitU8(const uint8_t* hostInput, const float mean[4], 
 int MixedInferenceCore::submitImpl(const void* hostInput, bool u8, const float* mean, const float* norm, float* hostOutput, size_t capacityFloats, int* classes1,
                                    int* ticket) {
     SNNB_REQUIRE(hostInput && ticket, "submit: null argument");
-    SNNB_REQUIRE(!yolo, "submit: detection models decode on the host; use run()");
     if (ensureStreaming()) return 1;
     Slot& sl = slots[nextTicket & 1];
     SNNB_REQUIRE(!sl.busy, "submit: two submissions are already in flight; wait() on ticket %d first", nextTicket - 2);
     int outIdx = 0;
     snnb_tensor* in  = inputLayers[0]->output;
-    snnb_tensor* out = outputLayers[outIdx]->output;
-    const size_t inBytes = in->pixels() * in->c * (u8 ? sizeof(uint8_t) : sizeof(float)), outFloats = out->pixels() * out->c;
+    snnb_tensor* out = outputLayers[outIdx]->output; // nullptr for a detection model: its output is the box list (snnb_model_get_boxes)
+    if (!out) hostOutput = nullptr, classes1 = nullptr;
+    const size_t inBytes = in->pixels() * in->c * (u8 ? sizeof(uint8_t) : sizeof(float)), outFloats = out ? out->pixels() * out->c : 0;
     SNNB_REQUIRE(!hostOutput || capacityFloats >= outFloats, "submit: output buffer too small (%zu < %zu floats)", capacityFloats, outFloats);
     // copy stream: wait until the split kernel of the submission that last used this slot has consumed the staging
     if (sl.everUsed) SNNB_CUDA_OK(cudaStreamWaitEvent(copyStream, sl.stageFree, 0));
@@ -492,6 +516,7 @@ int MixedInferenceCore::submitImpl(const void* hostInput, bool u8, const float* 
         SNNB_CUDA_OK(cudaMemcpyAsync(classes1, sl.argmax, sizeof(int) * options.batch, cudaMemcpyDeviceToHost, ctx->stream));
         sl.classesHost = classes1;
     }
+    if (yolo && decodeYolo(sl.yoloDev, sl.yoloHost, false)) return 1; // candidates -> pinned host, asynchronously; NMS in wait()
     SNNB_CUDA_OK(cudaEventRecord(sl.resultReady, ctx->stream));
     sl.busy = sl.everUsed = true;
     *ticket = nextTicket++;
@@ -506,6 +531,11 @@ int MixedInferenceCore::wait(int ticket) {
     if (sl.classesHost)
         for (uint32_t i = 0; i < options.batch; ++i) sl.classesHost[i] += 1; // core.cpp:228-233: argmax + 1
     sl.busy = false;
+    if (yolo) {
+        const int rc = yolo->finishDecode(sl.yoloHost, boxes);
+        SNNB_REQUIRE(rc >= 0, "wait: an image produced more than %d detection candidates; use snnb_model_run() for this input", YOLOLayer::YOLO_MAX_CAND);
+        return rc;
+    }
     return 0;
 }
 
@@ -530,10 +560,14 @@ int MixedInferenceCore::timeLayers(std::vector<float>& ms) {
     ExecOptions eo;
     eo.convAlgo = options.convAlgo, eo.precision = options.precision;
     SNNB_CUDA_OK(cudaEventRecord(ev[0], ctx->stream));
+    layerKernels.assign(layers.size(), std::string());
     for (size_t i = 0; i < graph.sorted.size(); ++i) {
         GenericModelLayer* L = graph.sorted[i];
-        if (!(L->fusedAway || L->isInputLayer || L->typeName == "YOLO"))
+        if (!(L->fusedAway || L->isInputLayer || L->typeName == "YOLO")) {
+            ctx->last_kernel = nullptr;
             if (int rc = L->run(ctx, eo)) return rc;
+            layerKernels[L->layerId] = ctx->last_kernel ? ctx->last_kernel : (L->typeName + " kernels");
+        }
         SNNB_CUDA_OK(cudaEventRecord(ev[i + 1], ctx->stream));
     }
     SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));

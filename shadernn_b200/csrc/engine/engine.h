@@ -266,8 +266,16 @@ public:
 class YOLOLayer : public GenericModelLayer { // yololayer.{h,cpp}: host decode + NMS of two heads
 public:
     void getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const override;
-    int run(snnb_context*, const ExecOptions&) override { return 0; } // host op: executed by the core after the device pass
+    int run(snnb_context*, const ExecOptions&) override { return 0; } // executed by the core after the device pass (candidates + host NMS)
+    // all-host decode (downloads both heads): the fallback when an image has more candidates than the device list holds
     int decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perImage);
+    // device threshold + compaction into `devCounts` / `devCand` ([N] ints, [N][YOLO_MAX_CAND][8] floats), asynchronous
+    static constexpr int YOLO_MAX_CAND = 1024;
+    static size_t candidateBytes(int n) { return (size_t) n * (sizeof(int) + (size_t) YOLO_MAX_CAND * 8 * sizeof(float)); }
+    int enqueueCandidates(snnb_context* ctx, void* devBuf);
+    // host part on the downloaded buffer: exact score formula, confidence threshold, score sort, NMS (yololayer.cpp:56-164).
+    // Returns 0, or -1 when some image overflowed the candidate list (caller falls back to decode()).
+    int finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes>& perImage) const;
 };
 
 // -------------------------------------------------------------------------------------------------------------
@@ -332,6 +340,7 @@ public:
     size_t arenaBytes = 0;
     int launchesPerForward = 0;
     bool isClassifier = false;
+    std::vector<std::string> layerKernels; // per layer (JSON order): the kernel its last timeLayers() pass launched
 
 private:
     bool init(std::string& err);
@@ -344,6 +353,9 @@ private:
     size_t ioStageBytes = 0;
     int* argmaxDev   = nullptr;
     dp::YOLOLayer* yolo = nullptr;
+    void* yoloDev  = nullptr; // device candidate lists of the YOLO decode (counts + [N][YOLO_MAX_CAND][8])
+    void* yoloHost = nullptr; // pinned host mirror
+    int decodeYolo(void* dev, void* host, bool sync); // candidates kernel + D2H (+ sync + host NMS into `boxes`)
     // streaming state
     struct Slot {
         float* stageIn = nullptr;   // device fp32 staging for this slot's input batch
@@ -351,6 +363,8 @@ private:
         int* argmax = nullptr;
         cudaEvent_t h2dDone = nullptr, stageFree = nullptr, resultReady = nullptr;
         int* classesHost = nullptr;
+        void* yoloDev = nullptr;
+        void* yoloHost = nullptr;
         bool busy = false, everUsed = false;
     } slots[2];
     cudaStream_t copyStream = nullptr;

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstring>
 #include <thread>
 
 #include "engine.h"
@@ -284,13 +285,47 @@ float iou(const Box& a, const Box& b) { // yololayer.cpp:56-70
 }
 } // namespace
 
+namespace {
+// yololayer.cpp:31-38
+const int kGridScale[2] = {32, 16};
+const float kAnchors[]  = {10, 14, 23, 27, 37, 58, 81, 82, 135, 169, 344, 319};
+const float kMasks[]    = {3, 4, 5, 1, 2, 3};
+const int GC = 3, NFIX = 5, ONUM = 6;
+const float kConfThresh = 0.35f, kIouThresh = 0.45f; // yololayer.cpp:182-183
+
+// one box from the six raw values of a (cell, anchor): yololayer.cpp:115-164. Returns false below the confidence threshold.
+bool decodeCell(const float* d, int yi, int gx, int gy, int gc, int gw, int gh, Box& out) {
+    int cls        = 0;
+    float maxLogit = -3.402823466e+38f;
+    for (int i = NFIX; i < ONUM; ++i)
+        if (d[i] > maxLogit) maxLogit = d[i], cls = i - NFIX;
+    const int ai   = (int) kMasks[gc + yi * GC];
+    const float bw = kAnchors[ai * 2], bh = kAnchors[ai * 2 + 1];
+    const int netW = kGridScale[yi] * gw, netH = kGridScale[yi] * gh;
+    const float prob = 1.f / ((1.f + std::exp(-d[4]) * (1.f + std::exp(-maxLogit)))); // yololayer.cpp:136, as parenthesised
+    if (!(prob > kConfThresh)) return false;
+    const float cx = (gx + 1.0f / (1.0f + std::exp(-d[0]))) / gw;
+    const float cy = (gy + 1.0f / (1.0f + std::exp(-d[1]))) / gh;
+    const float w_ = std::exp(d[2]) * bw / netW, h_ = std::exp(d[3]) * bh / netH;
+    out = Box {cls, prob, cx - w_ / 2, cy - h_ / 2, w_, h_};
+    return true;
+}
+// NMS, yololayer.cpp:72-110: stable sort by score, greedy suppression within a class
+void nms(std::vector<Box>& list, SNNModelOutputBoxes& out) {
+    std::stable_sort(list.begin(), list.end(), [](const Box& l, const Box& r) { return l.score > r.score; });
+    std::vector<char> merged(list.size(), 0);
+    for (size_t i = 0; i < list.size(); ++i) {
+        if (merged[i]) continue;
+        for (size_t j = i + 1; j < list.size(); ++j) {
+            if (merged[j] || list[i].cls != list[j].cls) continue;
+            if (iou(list[i], list[j]) > kIouThresh) merged[j] = 1;
+        }
+        out.rows.push_back({(float) list[i].cls, list[i].score, list[i].x, list[i].y, list[i].w, list[i].h});
+    }
+}
+} // namespace
+
 int YOLOLayer::decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perImage) {
-    // yololayer.cpp:31-38
-    static const int gridScale[2] = {32, 16};
-    static const float anchors[]  = {10, 14, 23, 27, 37, 58, 81, 82, 135, 169, 344, 319};
-    static const float masks[]    = {3, 4, 5, 1, 2, 3};
-    const int GC = 3, NFIX = 5, ONUM = 6;
-    const float confThresh = 0.35f, iouThresh = 0.45f; // yololayer.cpp:182-183
     if (inputs.size() < 2) {
         set_error("%s: YOLO expects two heads", name.c_str());
         return 2;
@@ -315,38 +350,15 @@ int YOLOLayer::decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perIm
             // the reference derives the grid from a fixed 416 input (yololayer.cpp:178-191); we use the head's own dims,
             // which coincide for 416x416.
             const int gw = t->w, gh = t->h, C = t->c;
-            const int netW = gridScale[yi] * gw, netH = gridScale[yi] * gh;
             const float* data = heads[yi].data() + (size_t) n * gw * gh * C;
             for (int gy = 0; gy < gh; ++gy)
                 for (int gx = 0; gx < gw; ++gx)
                     for (int gc = 0; gc < GC; ++gc) {
-                        const float* d = data + ((size_t) gy * gw + gx) * C + gc * ONUM;
-                        int cls        = 0;
-                        float maxLogit = -3.402823466e+38f;
-                        for (int i = NFIX; i < ONUM; ++i)
-                            if (d[i] > maxLogit) maxLogit = d[i], cls = i - NFIX;
-                        const int ai   = (int) masks[gc + yi * GC];
-                        const float bw = anchors[ai * 2], bh = anchors[ai * 2 + 1];
-                        const float prob = 1.f / ((1.f + std::exp(-d[4]) * (1.f + std::exp(-maxLogit)))); // yololayer.cpp:136, as parenthesised
-                        if (prob > confThresh) {
-                            const float cx = (gx + 1.0f / (1.0f + std::exp(-d[0]))) / gw;
-                            const float cy = (gy + 1.0f / (1.0f + std::exp(-d[1]))) / gh;
-                            const float w_ = std::exp(d[2]) * bw / netW, h_ = std::exp(d[3]) * bh / netH;
-                            list.push_back(Box {cls, prob, cx - w_ / 2, cy - h_ / 2, w_, h_});
-                        }
+                        Box b;
+                        if (decodeCell(data + ((size_t) gy * gw + gx) * C + gc * ONUM, yi, gx, gy, gc, gw, gh, b)) list.push_back(b);
                     }
         }
-        // NMS, yololayer.cpp:72-110
-        std::stable_sort(list.begin(), list.end(), [](const Box& l, const Box& r) { return l.score > r.score; });
-        std::vector<char> merged(list.size(), 0);
-        for (size_t i = 0; i < list.size(); ++i) {
-            if (merged[i]) continue;
-            for (size_t j = i + 1; j < list.size(); ++j) {
-                if (merged[j] || list[i].cls != list[j].cls) continue;
-                if (iou(list[i], list[j]) > iouThresh) merged[j] = 1;
-            }
-            perImage[n].rows.push_back({(float) list[i].cls, list[i].score, list[i].x, list[i].y, list[i].w, list[i].h});
-        }
+        nms(list, perImage[n]);
     };
     const int nthreads = std::max(1, std::min(N, (int) std::min(32u, std::max(1u, std::thread::hardware_concurrency()))));
     if (nthreads == 1) {
@@ -358,6 +370,51 @@ int YOLOLayer::decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perIm
                 for (int n = t; n < N; n += nthreads) decodeImage(n);
             });
         for (auto& th : pool) th.join();
+    }
+    return 0;
+}
+
+int YOLOLayer::enqueueCandidates(snnb_context* ctx, void* devBuf) {
+    if (inputs.size() < 2 || inputs[0]->c < GC * ONUM || inputs[1]->c < GC * ONUM) {
+        set_error("%s: YOLO expects two heads of >= %d channels", name.c_str(), GC * ONUM);
+        return 2;
+    }
+    const int N = inputs[0]->n;
+    int* counts = static_cast<int*>(devBuf);
+    float* cand = reinterpret_cast<float*>(counts + N);
+    // margin below the threshold: the device's expf may differ from the host's std::exp in the last bits; the host decides
+    return launch_yolo_candidates(ctx, inputs[0], inputs[1], kConfThresh - 1e-3f, YOLO_MAX_CAND, counts, cand);
+}
+
+int YOLOLayer::finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes>& perImage) const {
+    const int N       = inputs[0]->n;
+    const int* counts = static_cast<const int*>(hostBuf);
+    const float* cand = reinterpret_cast<const float*>(counts + N);
+    for (int n = 0; n < N; ++n)
+        if (counts[n] > YOLO_MAX_CAND) return -1;
+    perImage.assign(N, SNNModelOutputBoxes());
+    const int cells0 = inputs[0]->h * inputs[0]->w * GC;
+    for (int n = 0; n < N; ++n) {
+        std::vector<const float*> rows(counts[n]);
+        for (int i = 0; i < counts[n]; ++i) rows[i] = cand + ((size_t) n * YOLO_MAX_CAND + i) * 8;
+        auto scan = [](const float* r) {
+            int v;
+            memcpy(&v, r, sizeof v);
+            return v;
+        };
+        // the device appended in arbitrary order: back to the order the reference's loops visit the cells
+        std::sort(rows.begin(), rows.end(), [&](const float* a, const float* b) { return scan(a) < scan(b); });
+        std::vector<Box> list;
+        for (const float* r : rows) {
+            int s        = scan(r);
+            const int yi = s >= cells0 ? 1 : 0;
+            if (yi) s -= cells0;
+            const int gw = inputs[yi]->w, gh = inputs[yi]->h;
+            const int gc = s % GC, cell = s / GC, gx = cell % gw, gy = cell / gw;
+            Box b;
+            if (decodeCell(r + 1, yi, gx, gy, gc, gw, gh, b)) list.push_back(b);
+        }
+        nms(list, perImage[n]);
     }
     return 0;
 }

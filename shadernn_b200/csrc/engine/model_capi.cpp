@@ -150,6 +150,11 @@ int snnb_model_time_layers(snnb_model* m, float* times_ms, int capacity) {
     return 0;
 }
 int snnb_model_launches_per_forward(const snnb_model* m) { return m ? m->core->launchesPerForward : -1; }
+int snnb_model_layer_kernel(const snnb_model* m, int layer, char* name, int name_cap) {
+    SNNB_REQUIRE(m && name && layer >= 0 && layer < (int) m->core->layers.size(), "snnb_model_layer_kernel: bad argument");
+    copyStr(name, name_cap, layer < (int) m->core->layerKernels.size() ? m->core->layerKernels[layer] : std::string());
+    return 0;
+}
 
 int snnb_model_get_boxes(snnb_model* m, int n, float* rows6, int max_rows, int* count) {
     SNNB_REQUIRE(m && count, "snnb_model_get_boxes: null argument");

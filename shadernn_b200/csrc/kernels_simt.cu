@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(128) conv2d_simt_kernel(const ConvKParams p) {
 }
 
 int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a) {
+    ctx->last_kernel = "conv2d_simt_kernel";
     ConvKParams p;
     p.in      = view(a.in);
     p.out     = view(a.out);
@@ -393,6 +394,7 @@ __global__ void __launch_bounds__(128) depthwise_generic_kernel(const DwParams p
 int launch_depthwise(snnb_context* ctx, const ConvArgs& a) {
     static const bool no_tma = getenv("SNNB_DW_SIMT") != nullptr; // A/B switch: the CUDA-core kernels below
     if (!no_tma && depthwise_tma_supported(a)) return launch_depthwise_tma(ctx, a);
+    ctx->last_kernel = "depthwise_kernel";
     DwParams p;
     p.in = view(a.in), p.out = view(a.out);
     p.w = a.w->w_f32, p.bias = a.w->bias;
@@ -586,6 +588,7 @@ bool gap_dense_supported(const snnb_tensor* in, const snnb_tensor* out, const sn
     return w && w->w_f32 && in->h * in->w >= 4 && in->cp <= 4096 && out->c <= 256 && out->h * out->w == 1 && in->n == out->n;
 }
 int launch_gap_dense(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, bool softmax) {
+    ctx->last_kernel = "gap_dense_kernel";
     const int parts   = std::max(1, std::min(256 / (in->cp >> 3), 8));
     const size_t smem = (size_t) (parts * in->cp + out->cp) * sizeof(float);
     launch_k(gap_dense_kernel, dim3((unsigned) in->n), dim3(256), smem, ctx->stream, view(in), view(out), (const float*) w->w_f32, w->ocw, (const float*) w->bias, act, alpha,
@@ -595,6 +598,7 @@ int launch_gap_dense(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out,
 }
 
 int launch_pool(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int k, int stride, bool avg) {
+    ctx->last_kernel = "pool_kernel";
     TV vi = view(in), vo = view(out);
     if (avg && out->h == 1 && out->w == 1 && k >= in->h && k >= in->w && in->h * in->w >= 16) {
         const long long warps = (long long) in->n * (out->cp >> 3);
@@ -657,6 +661,7 @@ static unsigned vec_blocks(const snnb_tensor* t, int threads) {
 }
 
 int launch_add(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out, int act, float alpha) {
+    ctx->last_kernel = "add_kernel";
     launch_k(add_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(a), view(b), view(out), act, alpha);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
@@ -721,6 +726,48 @@ __global__ void __launch_bounds__(128) argmax_kernel(TV in, int* __restrict__ id
 }
 int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx) {
     launch_k(argmax_kernel, dim3((unsigned) (((long long) in->n * 32 + 127) / 128)), dim3(128), 0, ctx->stream, view(in), dev_idx);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// YOLO decode, device part (yololayer.cpp:115-164): threshold + compaction. One thread per (image, head, cell, anchor) reads the
+// six values of its box and evaluates the reference's score formula; cells that could pass the confidence threshold (0.35,
+// tested with a safety margin: the HOST re-evaluates the exact std::exp formula and applies the real threshold) append
+// {scan index, d0..d5} to the image's candidate list. The host then sorts the few survivors by scan index - the order the
+// reference's loops visit them - and runs score-sort + NMS exactly as before: the detection list is bit-identical to the
+// all-host decode while 16 images x 2535 cells x 18 floats no longer cross PCIe.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void yolo_candidates_kernel(TV h0, TV h1, float thresh, int maxc, int* counts, float* cand) {
+    pdl_wait();
+    const int cells0 = h0.H * h0.W * 3, cells1 = h1.H * h1.W * 3;
+    const long long total = (long long) h0.N * (cells0 + cells1);
+    const long long gid   = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int n = (int) (gid / (cells0 + cells1)), r = (int) (gid % (cells0 + cells1));
+    const bool second = r >= cells0;
+    const TV& t       = second ? h1 : h0;
+    const int rr = second ? r - cells0 : r, gc = rr % 3, cell = rr / 3;
+    const size_t base = ((size_t) n * t.H * t.W + cell) * t.Cp + gc * 6;
+    float d[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[i] = load1(t.hi, t.lo, base + i);
+    const float prob = 1.f / ((1.f + expf(-d[4]) * (1.f + expf(-d[5])))); // yololayer.cpp:136, as parenthesised; one class: maxLogit = d[5]
+    if (prob > thresh) {
+        const int slot = atomicAdd(counts + n, 1);
+        if (slot < maxc) {
+            float* o = cand + ((size_t) n * maxc + slot) * 8;
+            o[0]     = __int_as_float(r); // scan index: (head, gy, gx, gc) in the reference's loop order
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o[1 + i] = d[i];
+            o[7] = prob;
+        }
+    }
+}
+int launch_yolo_candidates(snnb_context* ctx, const snnb_tensor* h0, const snnb_tensor* h1, float thresh, int maxc, int* counts, float* cand) {
+    SNNB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * h0->n, ctx->stream));
+    const long long total = (long long) h0->n * ((long long) h0->h * h0->w + (long long) h1->h * h1->w) * 3;
+    launch_k(yolo_candidates_kernel, dim3((unsigned) ((total + 255) / 256)), dim3(256), 0, ctx->stream, view(h0), view(h1), thresh, maxc, counts, cand);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -813,6 +860,7 @@ __global__ void upsample_kernel(TV in, TV out, float inv, int bilinear) {
     store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
 }
 int launch_upsample(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, float scale, bool bilinear) {
+    ctx->last_kernel = "upsample_kernel";
     launch_k(upsample_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), 1.0f / scale, bilinear ? 1 : 0);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
@@ -839,6 +887,7 @@ __global__ void pad_kernel(TV in, TV out, int pad_x, int pad_y, int mode) {
     store8(out.hi, out.lo, (((size_t) n * out.H + oy) * out.W + ox) * out.Cp + c, v);
 }
 int launch_pad(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int pad_x, int pad_y, int mode) {
+    ctx->last_kernel = "pad_kernel";
     launch_k(pad_kernel, dim3(vec_blocks(out, 256)), dim3(256), 0, ctx->stream, view(in), view(out), pad_x, pad_y, mode);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
@@ -920,6 +969,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(TV in, TV out, cons
     store8(out.hi, out.lo, (size_t) gid * 8, v);
 }
 int launch_instancenorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, float* scratch) {
+    ctx->last_kernel = "instnorm_kernels";
     // scratch: instnorm_scratch_floats(n, cp) floats = (mean, rstd) per (n, c) + the chunk partials; the engine passes a
     // model-owned buffer (stable under CUDA graphs)
     float* stats = scratch;

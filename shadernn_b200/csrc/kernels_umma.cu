@@ -1364,6 +1364,7 @@ bool conv2d_umma_supported(const ConvArgs& a) {
 enum { ATTR_UMMA = 1u, ATTR_ROWWIN = 2u, ATTR_DW1 = 4u, ATTR_DW2 = 8u }; // bits of snnb_context::func_attr_mask
 
 static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
+    ctx->last_kernel = "conv_rowwin_kernel";
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;
     RowPlan rp;
@@ -1556,6 +1557,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     // short K loop (1x1 convolutions): the layer runs at the speed of the epilogue -> two independent epilogue groups
     static const bool no_split_epi = getenv("SNNB_NO_SPLIT_EPI") != nullptr;
     const bool split_epi           = !halo && !no_split_epi && p.ksplit == 1 && p.ksize * p.ksize * p.cblocks <= 3 && total_tiles >= 2 * grid;
+    ctx->last_kernel = halo ? "conv_umma_kernel<halo>" : (split_epi ? "conv_umma_kernel<short-K>" : (p.ksplit > 1 ? "conv_umma_kernel<split-K>" : "conv_umma_kernel"));
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
     auto* k_split = terms == 3 ? conv_umma_kernel<UM_STAGES - 1, true, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES - 1, true, 2, false> : conv_umma_kernel<UM_STAGES - 1, true, 1, false>);
@@ -1767,6 +1769,7 @@ bool depthwise_tma_supported(const ConvArgs& a) {
 }
 
 template <int S> static int launch_depthwise_tma_s(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
+    ctx->last_kernel = "depthwise_tma_kernel";
     using T = DwTile<S>;
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;

@@ -145,6 +145,7 @@ struct snnb_context {
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: one bit per kernel, per context
     // (= per device), not a process-wide flag
     uint32_t func_attr_mask = 0;
+    const char* last_kernel = nullptr; // name of the kernel the most recent launcher chose (snnb_model_layer_kernel, bench.py's roofline)
     int precision = SNNB_PRECISION_FP32X3; // default product form of per-operator convolution launches (snnb_context_set_precision)
     std::vector<void*> scratch_blocks;
 };
@@ -189,6 +190,8 @@ int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out,
 int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int act, float alpha);
 int launch_softmax(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
 int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx);
+// YOLO decode, device part: cells whose score can pass `thresh` -> per-image candidate lists [N][maxc][8] = {scan index, d0..d5, score}
+int launch_yolo_candidates(snnb_context* ctx, const snnb_tensor* h0, const snnb_tensor* h1, float thresh, int maxc, int* counts, float* cand);
 int launch_flatten(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
 int launch_concat(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out);
 int launch_upsample(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, float scale, bool bilinear);

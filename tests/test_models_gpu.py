@@ -202,6 +202,41 @@ def test_yolo_decode_with_planted_detection(ctx, model_dir):
     assert_same_boxes(got, ref)
 
 
+def test_yolo_device_compaction_streaming_and_batch(ctx, model_dir):
+    # decode = threshold + compaction on the device, exact formula + NMS on the host (yololayer.cpp:56-164): the lists must be
+    # those of the oracle (which decodes everything on the CPU), image by image, through run() AND through submit()/wait()
+    import ctypes as C
+    path, layers = modelzoo.build("yolov3tiny", model_dir + "/planted", input_hw=(416, 416), seed=21)
+    for head in [l for l in layers if l["type"] == "Conv2D" and l["outputPlanes"] == 18]:
+        head["_w"]["bias"][:] = 0
+        head["_w"]["bias"][[4, 5, 10, 11]] = [-1.0, 0.0, -1.0, 0.0]  # scores scattered around the 0.35 threshold
+    modelzoo.write_model(layers, path, split=True)
+    xs = [modelzoo.synthetic_input("yolov3tiny", 4, (416, 416), seed=s) for s in (1, 2, 3)]
+    om = oracle.Model(path)
+    m = core.MixedInferenceCore(ctx, path, batch=4, fuse=True, use_cuda_graph=True)
+    refs = []
+    for x in xs:
+        om.run(x)
+        refs.append([b.copy() for b in om.boxes])
+        m.run(x, want_classes=False)
+        for n in range(4):
+            assert_same_boxes(m.boxes(n), refs[-1][n])
+    assert sum(len(b) for r in refs for b in r) > 20, "the planted heads should produce detections"
+    assert any(len(b) != len(refs[0][0]) for r in refs for b in r), "images should differ in their detection count"
+    ins = [np.ascontiguousarray(x) for x in xs]
+    pending = None
+    for i, x in enumerate(ins):
+        t = m.submit_raw(x.ctypes.data_as(C.c_void_p), None, 0, None)
+        if pending is not None:
+            m.wait(pending[0])  # boxes of the PREVIOUS submission
+            for n in range(4):
+                assert_same_boxes(m.boxes(n), refs[pending[1]][n])
+        pending = (t, i)
+    m.wait(pending[0])
+    for n in range(4):
+        assert_same_boxes(m.boxes(n), refs[pending[1]][n])
+
+
 def test_candy_layerwise(ctx, model_dir):
     # reflect padding, instance norm, nearest upsample, residual adds; inputs in [0,255]
     layerwise_check(ctx, "candy", (64, 64), 1, model_dir)
