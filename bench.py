@@ -139,9 +139,15 @@ class ClockSampler:
 
 
 def fixed_oracle_threads(oracle_mod):
-    """ONE thread team for every CPU measurement: all logical CPUs of the box (round 1 re-tuned the team per run and the reference
-    arm wandered 17.6 .. 78 frames/s between runs). torchrun exports OMP_NUM_THREADS=1, so the count is always set explicitly."""
-    n = os.cpu_count() or 1
+    """ONE thread team for every CPU measurement, fixed by rule: half the physical cores. (Round 1 re-tuned the team in every run
+    and the reference arm wandered 17.6 .. 78 frames/s between runs; all 128 logical CPUs of the GPU box run the memory-bound
+    operators 4x slower than 32 threads.) torchrun exports OMP_NUM_THREADS=1, so the count is always set explicitly."""
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or (os.cpu_count() or 2) // 2
+    except Exception:
+        phys = max(1, (os.cpu_count() or 2) // 2)
+    n = max(1, phys // 2)
     oracle_mod.lib().orc_set_num_threads(n)
     return n
 
@@ -217,6 +223,10 @@ class Workload:
         self.model = core.MixedInferenceCore(self.ctx, self.path, batch=batch, conv_algo=args.algo, use_cuda_graph=not args.no_graph, fuse=not args.no_fuse,
                                              precision=precision)
         self.detector = any(l["type"] == "YOLO" for l in self.layers)
+        self.head_dims = []
+        if self.detector:
+            yi = [i for i, l in enumerate(self.layers) if l["type"] == "YOLO"][0]
+            self.head_dims = [self.model.layer_info(j)[2][1:3] for j in self.layers[yi]["inputId"]]
         self.in_shape = self.model.input_shape(0)
         self.out_shape = None if self.detector else self.model.output_shape(0)
         n_out = 1 if self.detector else int(np.prod(self.out_shape))
@@ -298,7 +308,8 @@ class Workload:
 
     def d2h_bytes(self):
         if self.detector:
-            return self.batch * (4 + 1024 * 8 * 4)  # candidate lists of the device-side YOLO threshold + compaction
+            cells = sum(l_h * l_w for (l_h, l_w) in self.head_dims) * 3
+            return self.batch * (4 + cells * 8 * 4)  # candidate lists of the device-side YOLO threshold + compaction (one slot per cell and anchor)
         return int(np.prod(self.out_shape)) * 4 + self.batch * 4
 
 
@@ -360,8 +371,8 @@ def kernel_roofline(wl, work, pk, terms, step_ms, reps=5):
     # whole-graph lower bounds: every reference layer's bytes (fused-away Add / Pad included) and the launched kernels' only
     t_unf = sum(max(by / (pk["hbm_gbs"] * 1e9), fl / (peak_t * 1e12)) for (_, fl, by) in work)
     t_fus = 0.0
-    for i, ((t, fl, by), ms_l) in enumerate(zip(work, lt)):
-        if ms_l > 0:
+    for i, ((t, fl, by), kn) in enumerate(zip(work, kernels)):
+        if kn:
             t_fus += max(by / (pk["hbm_gbs"] * 1e9), fl / (peak_t * 1e12))
         elif t == "Add":
             t_fus += by / 3.0 / (pk["hbm_gbs"] * 1e9)  # fused into the producing conv: only the residual operand is still read
@@ -378,7 +389,7 @@ def layer_table(desc, batch, work, lt, kernels, pk, terms, step_ms, out):
               % (desc, batch, terms, terms))
     out.write("# %-3s %-18s %-26s %8s %8s %8s %8s %8s %6s %9s %9s\n" % ("id", "layer", "kernel", "ms", "GFLOP", "MB", "TF/s", "GB/s", "bound", "roofline%", "ceiling%"))
     for i, ((t, fl, by), ms_l, kn) in enumerate(zip(work, lt, kernels)):
-        if ms_l <= 0:
+        if ms_l <= 0 or not kn:
             continue
         t_h, t_t = by / (pk["hbm_gbs"] * 1e9), fl / (pk["bf16_tflops_sustained"] * 1e12)
         out.write("[%02d] %-18s %-26s %8.3f %8.2f %8.2f %8.1f %8.0f %6s %8.1f%% %8.1f%%\n" %

@@ -225,6 +225,44 @@ int snnb_model_get_boxes(snnb_model* m, int n, float* rows6, int max_rows, int* 
  * (torch.distributed) and no collective ever runs on the forward path. */
 int snnb_model_weight_arena(snnb_model* m, void** device_ptr, size_t* bytes);
 
+/* ---- multi-GPU: the ONE collective of the engine, in C++ --------------------------------------------
+ * One process per GPU. Rank `root` packs the weights; every other rank receives the packed arena with a single ncclBroadcast
+ * on the context's stream. NCCL is resolved at run time (the process's already-loaded libnccl.so.2 - e.g. PyTorch's - else
+ * dlopen): the library has no link-time dependency on it. Bootstrap: rank 0 calls snnb_nccl_unique_id and ships the 128
+ * bytes to the others by whatever means the host has (MPI, a file, torch.distributed), then every rank creates its
+ * communicator. No collective ever runs on the forward path. (The reference is single-device: new surface, kept thin.) */
+typedef struct snnb_comm snnb_comm;
+int snnb_nccl_unique_id(unsigned char id128[128]);
+int snnb_nccl_comm_create(snnb_context* ctx, int rank, int world_size, const unsigned char id128[128], snnb_comm** out);
+int snnb_nccl_comm_destroy(snnb_comm* comm);
+int snnb_bcast_weights(snnb_model* m, snnb_comm* comm, int root); /* asynchronous on the context's stream */
+
+/* ---- layer registration: snn::dp::registerLayer(name, LayerCreator) (core/src/ic2/layerFactory.h:116-122) ------------
+ * A host registers a creator for a layer `type` string; when a model file names that type, the creator is called with a
+ * read-only view of the "Layer_<i>" JSON object (the accessors below = what ModelParser hands the reference's creators,
+ * modelparser.h:60-157) and fills in the implementation: how the output dims follow from the inputs' and what to launch.
+ * `run` works on the context's stream with this header's own operator launches (or its own kernels on the tensors' planes).
+ * Registering an existing name replaces it, as registerLayer() does (built-in types included). */
+typedef struct snnb_layer_json snnb_layer_json;
+int snnb_layer_json_number(const snnb_layer_json* layer, const char* key, double* out);             /* 0 = present and numeric */
+int snnb_layer_json_string(const snnb_layer_json* layer, const char* key, char* buf, int cap);      /* 0 = present and a string */
+/* numeric array at a dotted path ("weights.kernel"); the pointer stays valid during the creator call only */
+int snnb_layer_json_numbers(const snnb_layer_json* layer, const char* path, const double** data, size_t* count);
+typedef struct {
+    void* user;
+    /* hwc triples: in_hwc[3*i .. 3*i+2] = (height, width, channels) of input i; write the output's into out_hwc[3]. 0 = ok. */
+    int (*output_dims)(void* user, int num_inputs, const int* in_hwc, int* out_hwc);
+    /* enqueue the layer's work on snnb_context_stream(ctx). 0 = ok. */
+    int (*run)(void* user, snnb_context* ctx, int num_inputs, const snnb_tensor* const* inputs, snnb_tensor* output);
+    void (*destroy)(void* user); /* may be NULL */
+} snnb_layer_impl;
+typedef int (*snnb_layer_creator)(void* registry_user, const snnb_layer_json* layer, snnb_layer_impl* out);
+int snnb_register_layer(const char* type_name, snnb_layer_creator creator, void* registry_user);
+int snnb_unregister_layer(const char* type_name);
+/* Raw device planes of a tensor for custom kernels: NHWC, channel pitch `cp` (a multiple of 8), fp16 hi plane and lo plane
+ * (value = hi + lo; lo is NULL in the half-precision storage mode). */
+int snnb_tensor_planes(const snnb_tensor* t, void** hi, void** lo, int* cp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ SOURCES = [
     "engine/core.cpp",
     "engine/model_capi.cpp",
 ]
-HEADERS = ["snnb_internal.h", "engine/engine.h", "engine/json.h", "../../include/snnb.h", "umma_utils.cuh"]
+HEADERS = ["snnb_internal.h", "engine/engine.h", "engine/json.h", "../../include/snnb.h"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xcompiler", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -80,7 +80,7 @@ def build(verbose=False, force=False):
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile_one(nvcc, s, hdr, verbose), SOURCES))
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [nvcc, "-ccbin", _host_cxx()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda", "-lpthread"]
+        cmd = [nvcc, "-ccbin", _host_cxx()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda", "-lpthread", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout[-4000:], r.stderr[-8000:]))

@@ -113,6 +113,16 @@ SIGNATURES = {
     "snnb_model_layer_kernel": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int]),
     "snnb_model_get_boxes": (C.c_int, [vp, C.c_int, c_float_p, C.c_int, c_int_p]),
     "snnb_model_weight_arena": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "snnb_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "snnb_nccl_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]),
+    "snnb_nccl_comm_destroy": (C.c_int, [vp]),
+    "snnb_bcast_weights": (C.c_int, [vp, vp, C.c_int]),
+    "snnb_register_layer": (C.c_int, [C.c_char_p, vp, vp]),
+    "snnb_unregister_layer": (C.c_int, [C.c_char_p]),
+    "snnb_layer_json_number": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double)]),
+    "snnb_layer_json_string": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_int]),
+    "snnb_layer_json_numbers": (C.c_int, [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_size_t)]),
+    "snnb_tensor_planes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), c_int_p]),
 }
 
 _lib = None

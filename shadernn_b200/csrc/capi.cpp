@@ -126,6 +126,11 @@ int snnb_tensor_free(snnb_tensor* t) {
     delete t;
     return 0;
 }
+int snnb_tensor_planes(const snnb_tensor* t, void** hi, void** lo, int* cp) {
+    SNNB_REQUIRE(t && hi && lo && cp, "snnb_tensor_planes: null argument");
+    *hi = t->hi, *lo = t->lo, *cp = t->cp;
+    return 0;
+}
 int snnb_tensor_dims(const snnb_tensor* t, int* n, int* h, int* w, int* c) {
     SNNB_REQUIRE(t, "snnb_tensor_dims: null tensor");
     if (n) *n = t->n;

@@ -332,7 +332,7 @@ bool MixedInferenceCore::init(std::string& err) {
         return false;
     }
     if (yolo) {
-        const size_t yb = YOLOLayer::candidateBytes(N);
+        const size_t yb = yolo->candidateBytes();
         if (cudaMalloc(&yoloDev, yb) != cudaSuccess || cudaMallocHost(&yoloHost, yb) != cudaSuccess) {
             err = "cudaMalloc(YOLO candidate lists) failed";
             return false;
@@ -451,7 +451,7 @@ int MixedInferenceCore::run(const float* hostInput, float* hostOutput, size_t ca
 // to the host, then the exact score formula, score sort and NMS there (identical lists, identical order: finishDecode).
 int MixedInferenceCore::decodeYolo(void* dev, void* host, bool sync) {
     if (yolo->enqueueCandidates(ctx, dev)) return 1;
-    SNNB_CUDA_OK(cudaMemcpyAsync(host, dev, YOLOLayer::candidateBytes((int) options.batch), cudaMemcpyDeviceToHost, ctx->stream));
+    SNNB_CUDA_OK(cudaMemcpyAsync(host, dev, yolo->candidateBytes(), cudaMemcpyDeviceToHost, ctx->stream));
     if (!sync) return 0;
     SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     const int rc = yolo->finishDecode(host, boxes);
@@ -471,8 +471,8 @@ int MixedInferenceCore::ensureStreaming() {
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.stageFree, cudaEventDisableTiming));
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.resultReady, cudaEventDisableTiming));
         if (yolo) {
-            SNNB_CUDA_OK(cudaMalloc(&sl.yoloDev, YOLOLayer::candidateBytes((int) options.batch)));
-            SNNB_CUDA_OK(cudaMallocHost(&sl.yoloHost, YOLOLayer::candidateBytes((int) options.batch)));
+            SNNB_CUDA_OK(cudaMalloc(&sl.yoloDev, yolo->candidateBytes()));
+            SNNB_CUDA_OK(cudaMallocHost(&sl.yoloHost, yolo->candidateBytes()));
         }
     }
     return 0;
@@ -533,7 +533,7 @@ int MixedInferenceCore::wait(int ticket) {
     sl.busy = false;
     if (yolo) {
         const int rc = yolo->finishDecode(sl.yoloHost, boxes);
-        SNNB_REQUIRE(rc >= 0, "wait: an image produced more than %d detection candidates; use snnb_model_run() for this input", YOLOLayer::YOLO_MAX_CAND);
+        SNNB_REQUIRE(rc >= 0, "wait: corrupt detection candidate list");
         return rc;
     }
     return 0;

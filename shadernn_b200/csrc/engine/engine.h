@@ -120,6 +120,17 @@ protected:
     size_t _scratchBytes = 0;
 };
 
+// A layer supplied through the C-ABI (snnb_register_layer): dims and launches are the host's callbacks.
+class PluginLayer : public GenericModelLayer {
+public:
+    snnb_layer_impl impl {};
+    ~PluginLayer() override {
+        if (impl.destroy) impl.destroy(impl.user);
+    }
+    void getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const override;
+    int run(snnb_context* ctx, const ExecOptions& opt) override;
+};
+
 typedef GenericModelLayer* (*LayerCreator)(ModelParser&, int);
 void initLayerRegisty();
 void registerLayer(const std::string& layerName, LayerCreator creator);
@@ -270,8 +281,9 @@ public:
     // all-host decode (downloads both heads): the fallback when an image has more candidates than the device list holds
     int decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perImage);
     // device threshold + compaction into `devCounts` / `devCand` ([N] ints, [N][YOLO_MAX_CAND][8] floats), asynchronous
-    static constexpr int YOLO_MAX_CAND = 1024;
-    static size_t candidateBytes(int n) { return (size_t) n * (sizeof(int) + (size_t) YOLO_MAX_CAND * 8 * sizeof(float)); }
+    // one slot per (cell, anchor) of both heads: the list can never overflow, whatever the scores
+    int maxCand() const { return inputs.size() < 2 ? 0 : (inputs[0]->h * inputs[0]->w + inputs[1]->h * inputs[1]->w) * 3; }
+    size_t candidateBytes() const { return inputs.size() < 2 ? 0 : (size_t) inputs[0]->n * (sizeof(int) + (size_t) maxCand() * 8 * sizeof(float)); }
     int enqueueCandidates(snnb_context* ctx, void* devBuf);
     // host part on the downloaded buffer: exact score formula, confidence threshold, score sort, NMS (yololayer.cpp:56-164).
     // Returns 0, or -1 when some image overflowed the candidate list (caller falls back to decode()).

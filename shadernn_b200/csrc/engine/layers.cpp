@@ -383,20 +383,21 @@ int YOLOLayer::enqueueCandidates(snnb_context* ctx, void* devBuf) {
     int* counts = static_cast<int*>(devBuf);
     float* cand = reinterpret_cast<float*>(counts + N);
     // margin below the threshold: the device's expf may differ from the host's std::exp in the last bits; the host decides
-    return launch_yolo_candidates(ctx, inputs[0], inputs[1], kConfThresh - 1e-3f, YOLO_MAX_CAND, counts, cand);
+    return launch_yolo_candidates(ctx, inputs[0], inputs[1], kConfThresh - 1e-3f, maxCand(), counts, cand);
 }
 
 int YOLOLayer::finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes>& perImage) const {
     const int N       = inputs[0]->n;
     const int* counts = static_cast<const int*>(hostBuf);
     const float* cand = reinterpret_cast<const float*>(counts + N);
+    const int maxc = maxCand();
     for (int n = 0; n < N; ++n)
-        if (counts[n] > YOLO_MAX_CAND) return -1;
+        if (counts[n] > maxc) return -1; // cannot happen: one slot per (cell, anchor)
     perImage.assign(N, SNNModelOutputBoxes());
     const int cells0 = inputs[0]->h * inputs[0]->w * GC;
     for (int n = 0; n < N; ++n) {
         std::vector<const float*> rows(counts[n]);
-        for (int i = 0; i < counts[n]; ++i) rows[i] = cand + ((size_t) n * YOLO_MAX_CAND + i) * 8;
+        for (int i = 0; i < counts[n]; ++i) rows[i] = cand + ((size_t) n * maxc + i) * 8;
         auto scan = [](const float* r) {
             int v;
             memcpy(&v, r, sizeof v);

@@ -1,4 +1,6 @@
 // extern "C" surface for the whole-model engine (snnb_model_*). See include/snnb.h.
+#include <dlfcn.h>
+
 #include <cstring>
 
 #include "engine.h"
@@ -171,6 +173,91 @@ int snnb_model_weight_arena(snnb_model* m, void** device_ptr, size_t* bytes) {
     SNNB_REQUIRE(m && device_ptr && bytes, "snnb_model_weight_arena: null argument");
     *device_ptr = m->core->arena;
     *bytes      = m->core->arenaBytes;
+    return 0;
+}
+
+// ---- the one collective: ncclBroadcast of the packed weight arena (NCCL resolved at run time, see snnb.h) ----
+namespace {
+struct NcclApi {
+    struct Id { // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+        char b[128];
+    };
+    typedef int (*GetUniqueId)(void*);
+    typedef int (*CommInitRank)(void**, int, Id, int);
+    typedef int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    typedef int (*CommDestroy)(void*);
+    typedef const char* (*GetErrorString)(int);
+    GetUniqueId getUniqueId = nullptr;
+    CommInitRank commInitRank = nullptr;
+    Broadcast broadcast = nullptr;
+    CommDestroy commDestroy = nullptr;
+    GetErrorString errorString = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = RTLD_DEFAULT; // the host process's own NCCL first (PyTorch bundles one): the communicator must live in ONE library
+        if (!dlsym(h, "ncclBroadcast")) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.getUniqueId  = (NcclApi::GetUniqueId) dlsym(h, "ncclGetUniqueId");
+            api.commInitRank = (NcclApi::CommInitRank) dlsym(h, "ncclCommInitRank");
+            api.broadcast    = (NcclApi::Broadcast) dlsym(h, "ncclBroadcast");
+            api.commDestroy  = (NcclApi::CommDestroy) dlsym(h, "ncclCommDestroy");
+            api.errorString  = (NcclApi::GetErrorString) dlsym(h, "ncclGetErrorString");
+            api.ok           = api.getUniqueId && api.commInitRank && api.broadcast && api.commDestroy;
+        }
+    }
+    return api;
+}
+const char* ncclErr(int rc) { return nccl().errorString ? nccl().errorString(rc) : "?"; }
+} // namespace
+
+struct snnb_comm {
+    snnb_context* ctx = nullptr;
+    void* comm        = nullptr;
+    int rank = 0, world = 1;
+};
+
+int snnb_nccl_unique_id(unsigned char id128[128]) {
+    SNNB_REQUIRE(id128, "snnb_nccl_unique_id: null argument");
+    SNNB_REQUIRE(nccl().ok, "snnb_nccl_unique_id: NCCL (libnccl.so.2) is not available in this process");
+    const int rc = nccl().getUniqueId(id128);
+    SNNB_REQUIRE(rc == 0, "ncclGetUniqueId failed: %s", ncclErr(rc));
+    return 0;
+}
+int snnb_nccl_comm_create(snnb_context* ctx, int rank, int world_size, const unsigned char id128[128], snnb_comm** out) {
+    SNNB_REQUIRE(ctx && id128 && out && world_size >= 1 && rank >= 0 && rank < world_size, "snnb_nccl_comm_create: bad argument");
+    SNNB_REQUIRE(nccl().ok, "snnb_nccl_comm_create: NCCL (libnccl.so.2) is not available in this process");
+    SNNB_CUDA_OK(cudaSetDevice(ctx->device));
+    NcclApi::Id id;
+    memcpy(id.b, id128, 128);
+    auto* c  = new snnb_comm();
+    c->ctx = ctx, c->rank = rank, c->world = world_size;
+    const int rc = nccl().commInitRank(&c->comm, world_size, id, rank);
+    if (rc != 0) {
+        delete c;
+        set_error("ncclCommInitRank(rank %d of %d) failed: %s", rank, world_size, ncclErr(rc));
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+int snnb_nccl_comm_destroy(snnb_comm* comm) {
+    if (!comm) return 0;
+    if (comm->comm && nccl().ok) nccl().commDestroy(comm->comm);
+    delete comm;
+    return 0;
+}
+int snnb_bcast_weights(snnb_model* m, snnb_comm* comm, int root) {
+    SNNB_REQUIRE(m && comm && root >= 0 && root < comm->world, "snnb_bcast_weights: bad argument");
+    SNNB_REQUIRE(m->core->ctx == comm->ctx, "snnb_bcast_weights: the communicator was created on another context");
+    SNNB_CUDA_OK(cudaSetDevice(comm->ctx->device));
+    // in place: rank `root` sends its arena, everyone else receives into theirs (all ranks packed the same layout)
+    const int rc = nccl().broadcast(m->core->arena, m->core->arena, m->core->arenaBytes, /* ncclUint8 */ 1, root, comm->comm, comm->ctx->stream);
+    SNNB_REQUIRE(rc == 0, "ncclBroadcast(%zu bytes) failed: %s", m->core->arenaBytes, ncclErr(rc));
     return 0;
 }
 

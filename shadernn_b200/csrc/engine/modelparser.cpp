@@ -458,7 +458,47 @@ void initLayerRegisty() { // layerFactory.cpp:109-129 (Conv2DTranspose, Calculat
     registerLayer("Activation", ActivationCreator); // creatable-only in the reference (layerFactory.h:125-148)
 }
 
+// ---- layers registered through the C-ABI (snnb_register_layer) ----
+struct PluginEntry {
+    snnb_layer_creator creator;
+    void* user;
+};
+static std::map<std::string, PluginEntry>& pluginRegistry() {
+    static std::map<std::string, PluginEntry> r;
+    return r;
+}
+void PluginLayer::getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const {
+    std::vector<int> in;
+    for (auto& dim : inputDims) in.push_back((int) dim.height), in.push_back((int) dim.width), in.push_back((int) dim.depth);
+    int out[3] = {0, 0, 0};
+    if (!impl.output_dims || impl.output_dims(impl.user, (int) inputDims.size(), in.data(), out) || out[0] <= 0 || out[1] <= 0 || out[2] <= 0)
+        throw std::runtime_error(name + ": the registered layer's output_dims callback failed");
+    h = (uint32_t) out[0], w = (uint32_t) out[1], d = (uint32_t) out[2];
+}
+int PluginLayer::run(snnb_context* ctx, const ExecOptions&) {
+    std::vector<const snnb_tensor*> ins(inputs.begin(), inputs.end());
+    if (!impl.run || impl.run(impl.user, ctx, (int) ins.size(), ins.data(), output)) {
+        if (!*snnb::get_error()) snnb::set_error("%s: the registered layer's run callback failed", name.c_str());
+        return 1;
+    }
+    return 0;
+}
+
 GenericModelLayer* createLayerInstance(std::string layerName, ModelParser& parser, int i) { // layerFactory.cpp:136-159
+    {
+        auto pit = pluginRegistry().find(layerName);
+        if (pit != pluginRegistry().end()) {
+            auto* L = new PluginLayer();
+            common(L, parser, i);
+            if (pit->second.creator(pit->second.user, reinterpret_cast<const snnb_layer_json*>(&parser.layer(i)), &L->impl) || !L->impl.output_dims || !L->impl.run) {
+                delete L;
+                throw std::runtime_error("ModelParser: the creator registered for layer type '" + layerName + "' failed on layer " + std::to_string(i));
+            }
+            L->typeName = layerName;
+            L->layerId  = i;
+            return L;
+        }
+    }
     if (layerName == "DepthwiseConv2D" || layerName == "Depthwise") layerName = "SeparableConv2D";
     if (layerName == "InstanceNormalization") layerName = "InstanceNorm";
     if (layerName == "ZeroPadding2D") layerName = "Pad";
@@ -478,3 +518,52 @@ GenericModelLayer* createLayerInstance(std::string layerName, ModelParser& parse
 
 } // namespace dp
 } // namespace snn
+
+// ---- C-ABI: layer registration + read-only JSON accessors (include/snnb.h) ----
+extern "C" {
+int snnb_register_layer(const char* type_name, snnb_layer_creator creator, void* registry_user) {
+    SNNB_REQUIRE(type_name && *type_name && creator, "snnb_register_layer: null argument");
+    snn::dp::pluginRegistry()[type_name] = snn::dp::PluginEntry {creator, registry_user};
+    return 0;
+}
+int snnb_unregister_layer(const char* type_name) {
+    SNNB_REQUIRE(type_name, "snnb_unregister_layer: null argument");
+    SNNB_REQUIRE(snn::dp::pluginRegistry().erase(type_name) == 1, "snnb_unregister_layer: '%s' is not registered", type_name);
+    return 0;
+}
+static const snn::json::Value* jsonAt(const snnb_layer_json* layer, const char* path) {
+    const snn::json::Value* v = reinterpret_cast<const snn::json::Value*>(layer);
+    std::string p(path ? path : "");
+    size_t pos = 0;
+    while (v && pos <= p.size()) {
+        const size_t dot = p.find('.', pos);
+        const std::string key = p.substr(pos, dot == std::string::npos ? std::string::npos : dot - pos);
+        v = v->isObject() ? v->find(key) : nullptr;
+        if (dot == std::string::npos) break;
+        pos = dot + 1;
+    }
+    return v;
+}
+int snnb_layer_json_number(const snnb_layer_json* layer, const char* key, double* out) {
+    SNNB_REQUIRE(layer && key && out, "snnb_layer_json_number: null argument");
+    const snn::json::Value* v = jsonAt(layer, key);
+    if (!v || !v->isNumber()) return 1;
+    *out = v->num;
+    return 0;
+}
+int snnb_layer_json_string(const snnb_layer_json* layer, const char* key, char* buf, int cap) {
+    SNNB_REQUIRE(layer && key && buf && cap > 0, "snnb_layer_json_string: bad argument");
+    const snn::json::Value* v = jsonAt(layer, key);
+    if (!v || !v->isString()) return 1;
+    strncpy(buf, v->str.c_str(), (size_t) cap - 1);
+    buf[cap - 1] = 0;
+    return 0;
+}
+int snnb_layer_json_numbers(const snnb_layer_json* layer, const char* path, const double** data, size_t* count) {
+    SNNB_REQUIRE(layer && path && data && count, "snnb_layer_json_numbers: null argument");
+    const snn::json::Value* v = jsonAt(layer, path);
+    if (!v || v->type != snn::json::Value::NumArray) return 1;
+    *data = v->nums.data(), *count = v->nums.size();
+    return 0;
+}
+} // extern "C"

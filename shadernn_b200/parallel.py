@@ -58,15 +58,34 @@ def broadcast_buffer(t, src=0):
 
 
 def broadcast_model_weights(model, device, src=0):
-    """The single collective of the whole engine: rank `src`'s packed (BN-folded, split-bf16) weight arena overwrites
-    every other rank's, in place, over NCCL. Returns the number of bytes broadcast."""
+    """The single collective of the whole engine: rank `src`'s packed (BN-folded, split-fp16) weight arena overwrites every other
+    rank's, in place. On GPUs this is the library's own C++ path - snnb_nccl_comm_create + snnb_bcast_weights = one ncclBroadcast
+    on the engine's stream (include/snnb.h); torch.distributed only carries the 128-byte NCCL id to the other ranks. Without a GPU
+    (the gloo CPU tests) the same bytes travel through torch.distributed itself. Returns the number of bytes broadcast."""
     ptr, nbytes = model.weight_arena()
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return nbytes
+    if str(device).startswith("cuda"):
+        import ctypes as C
+
+        from ._lib import check, lib
+        rank, world = dist.get_rank(), dist.get_world_size()
+        idbuf = C.create_string_buffer(128)
+        if rank == src:
+            check(lib().snnb_nccl_unique_id(idbuf), "snnb_nccl_unique_id")
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).to(device)
+        dist.broadcast(t, src=src)
+        idbuf = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+        comm = C.c_void_p()
+        check(lib().snnb_nccl_comm_create(model.ctx.h, rank, world, idbuf, C.byref(comm)), "snnb_nccl_comm_create")
+        try:
+            check(lib().snnb_bcast_weights(model.h, comm, src), "snnb_bcast_weights")
+            model.ctx.sync()  # the arena is complete before the first forward pass reads it
+        finally:
+            lib().snnb_nccl_comm_destroy(comm)
+        return nbytes
     t = arena_as_tensor(ptr, nbytes, device)
     broadcast_buffer(t, src)
-    # NCCL ran on torch's stream; the engine computes on its own non-blocking stream, which has no implicit ordering with it:
-    # the arena must be complete before the first forward pass reads it
-    if t.is_cuda:
-        torch.cuda.synchronize(t.device)
     return nbytes
 
 

@@ -389,6 +389,72 @@ def test_model_error_paths(ctx, tmp_path):
         core.MixedInferenceCore(ctx, str(trunc))
 
 
+def test_layer_registration_through_the_c_abi(ctx, tmp_path):
+    # snnb_register_layer = snn::dp::registerLayer(name, LayerCreator) (layerFactory.h:116-122) at the C boundary: the host registers
+    # a creator for a new layer type; the model file names it; the creator reads its JSON through the accessors and supplies dims +
+    # launches. Here: "GatedSiLU" = SiLU of the input through the library's own activation launch, output dims = input dims.
+    import ctypes as C
+    import json
+
+    from shadernn_b200._lib import SnnbError, lib
+    DIMS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int))
+    RUN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p)
+    DESTROY = C.CFUNCTYPE(None, C.c_void_p)
+
+    class Impl(C.Structure):
+        _fields_ = [("user", C.c_void_p), ("output_dims", DIMS), ("run", RUN), ("destroy", DESTROY)]
+
+    CREATOR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Impl))
+    seen = {}
+
+    def dims(user, n, in_hwc, out_hwc):
+        for k in range(3):
+            out_hwc[k] = in_hwc[k]
+        return 0
+
+    def run(user, ctx_h, n, inputs, output):
+        seen["runs"] = seen.get("runs", 0) + 1
+        return lib().snnb_activation_launch(ctx_h, core.ACT["SiLU"], 0.0, inputs[0], output)
+
+    keep = [DIMS(dims), RUN(run), DESTROY(lambda u: seen.__setitem__("destroyed", seen.get("destroyed", 0) + 1))]
+
+    def creator(reg_user, layer, out):
+        num, buf = C.c_double(), C.create_string_buffer(32)
+        data, cnt = C.POINTER(C.c_double)(), C.c_size_t()
+        assert lib().snnb_layer_json_number(layer, b"gain", C.byref(num)) == 0 and num.value == 2.5
+        assert lib().snnb_layer_json_string(layer, b"flavour", buf, 32) == 0 and buf.value == b"sweet"
+        assert lib().snnb_layer_json_numbers(layer, b"weights.table", C.byref(data), C.byref(cnt)) == 0 and [data[i] for i in range(cnt.value)] == [1.0, 2.0, 3.0]
+        assert lib().snnb_layer_json_number(layer, b"missing", C.byref(num)) != 0
+        out[0].user, out[0].output_dims, out[0].run, out[0].destroy = None, keep[0], keep[1], keep[2]
+        seen["created"] = seen.get("created", 0) + 1
+        return 0
+
+    cb = CREATOR(creator)
+    model = {"numLayers": {"count": 2},
+             "Layer_0": {"type": "InputLayer", "name": "input_1", "Input Width": 12, "Input Height": 10, "outputPlanes": 5, "inputPlanes": 5, "numInputs": 0, "inputId": [],
+                         "inputIndex": 0},
+             "Layer_1": {"type": "GatedSiLU", "name": "gated", "inputPlanes": 5, "outputPlanes": 5, "numInputs": 1, "inputId": [0], "gain": 2.5, "flavour": "sweet",
+                         "weights": {"table": [1, 2, 3]}}}
+    path = tmp_path / "custom.json"
+    path.write_text(json.dumps(model))
+    with pytest.raises(SnnbError) as e:  # unknown until registered (layerFactory.cpp:155-157)
+        core.MixedInferenceCore(ctx, str(path), batch=2)
+    assert "Not found layer" in str(e.value)
+    assert lib().snnb_register_layer(b"GatedSiLU", C.cast(cb, C.c_void_p), None) == 0
+    try:
+        m = core.MixedInferenceCore(ctx, str(path), batch=2)
+        x = np.random.default_rng(3).uniform(-3, 3, (2, 10, 12, 5)).astype(np.float32)
+        out, _ = m.run(x, want_classes=False)
+        want = x / (1.0 + np.exp(-x))
+        assert out.shape == x.shape and float(np.abs(out - want).max()) < 1e-5
+        assert seen["created"] == 1 and seen["runs"] >= 2  # init's eager pass + the run
+        m.close()
+        assert seen.get("destroyed") == 1
+    finally:
+        assert lib().snnb_unregister_layer(b"GatedSiLU") == 0
+    assert lib().snnb_unregister_layer(b"GatedSiLU") != 0
+
+
 def test_streaming_submit_wait_matches_synchronous_run(ctx, model_dir):
     # snnb_model_submit / snnb_model_wait: double-buffered pipeline, results identical to run(), tickets enforce depth 2
     import ctypes as C
