@@ -201,6 +201,23 @@ int snnb_model_submit(snnb_model* m, const float* host_input_nhwc, float* host_o
  * quarter of the fp32 bytes cross PCIe. */
 int snnb_model_submit_u8(snnb_model* m, const uint8_t* host_input_nhwc_u8, const float* mean4, const float* norm4, float* host_output, size_t out_capacity,
                          int* classes_1based, int* ticket);
+/* Image in, image (or tensor) out, all pre/post-processing on the device (SURVEY §8 f-N3): the 8-bit input may have ANY size - it is
+ * resized to the model's input with the linear or nearest filter exactly as ImageTexture::resize does (imageTexture.h:137,
+ * shadertemplate_vk_resize.comp:42-61: output texel centres sampled from the source) and normalised in the same kernel; the result comes
+ * back either as fp32 (output_f32) or as an 8-bit image, clamp(round(v * out_scale + out_offset), 0, 255) (style transfer: scale 1;
+ * a tanh output: 127.5 / 127.5). Same ticket / wait protocol as snnb_model_submit. */
+typedef struct {
+    const uint8_t* input_u8; /* N * src_height * src_width * C bytes, NHWC, dense */
+    int src_height, src_width;
+    int linear_filter;       /* 1 = linear (the reference's default), 0 = nearest */
+    float mean4[4], norm4[4];
+    float* output_f32;       /* exactly one of output_f32 / output_u8 may be non-NULL (both NULL: no output copy) */
+    size_t output_capacity;  /* elements */
+    uint8_t* output_u8;
+    float out_scale, out_offset;
+    int* classes_1based;     /* classifiers only, may be NULL */
+} snnb_image_io;
+int snnb_model_submit_image(snnb_model* m, const snnb_image_io* io, int* ticket);
 int snnb_model_wait(snnb_model* m, int ticket);
 /* Device-resident variant: inputs already uploaded with snnb_model_set_input(); forward only, asynchronous. */
 int snnb_model_set_input(snnb_model* m, int idx, const float* host_input_nhwc);

@@ -247,6 +247,38 @@ def yolo(head0, head1, net_hw=(416, 416), conf=0.35, iou=0.45):
     return out[:n]
 
 
+def resize_normalize(images_u8, out_hw, mean4, norm4, linear=True):
+    """ImageTexture::resize + normalisation (core/inc/snn/imageTexture.h:137; shadertemplate_vk_resize.comp:42-61): output texel
+    (x, y) samples the source at ((x + 0.5) / outW, (y + 0.5) / outH) with the sampler's filter - linear: texel centres at
+    (i + 0.5) / inW, weights from the fractional part, clamp to edge; nearest: floor - then (v - mean[c & 3]) * norm[c & 3].
+    fp32 arithmetic in the order of the CUDA kernel it checks (bilinear as two lerps along x, then one along y)."""
+    img = np.asarray(images_u8, np.uint8).astype(np.float32)
+    n, sh, sw, c = img.shape
+    oh, ow = out_hw
+    f32 = np.float32
+    fx = (np.arange(ow, dtype=f32) + f32(0.5)) / f32(ow) * f32(sw)
+    fy = (np.arange(oh, dtype=f32) + f32(0.5)) / f32(oh) * f32(sh)
+    if linear:
+        sx, sy = fx - f32(0.5), fy - f32(0.5)
+        x0f, y0f = np.floor(sx), np.floor(sy)
+        ax, ay = (sx - x0f).astype(f32), (sy - y0f).astype(f32)
+        x0, x1 = np.clip(x0f.astype(int), 0, sw - 1), np.clip(x0f.astype(int) + 1, 0, sw - 1)
+        y0, y1 = np.clip(y0f.astype(int), 0, sh - 1), np.clip(y0f.astype(int) + 1, 0, sh - 1)
+        ax_, ay_ = ax[None, None, :, None], ay[None, :, None, None]
+        p00, p01 = img[:, y0][:, :, x0], img[:, y0][:, :, x1]
+        p10, p11 = img[:, y1][:, :, x0], img[:, y1][:, :, x1]
+        top = p00 + ax_ * (p01 - p00)
+        bot = p10 + ax_ * (p11 - p10)
+        v = top + ay_ * (bot - top)
+    else:
+        x0 = np.minimum(fx.astype(int), sw - 1)
+        y0 = np.minimum(fy.astype(int), sh - 1)
+        v = img[:, y0][:, :, x0]
+    mean = np.array([mean4[i & 3] for i in range(c)], f32)
+    norm = np.array([norm4[i & 3] for i in range(c)], f32)
+    return ((v.astype(f32) - mean) * norm).astype(f32)
+
+
 def compare(a, b, eps):
     """Number of mismatches under the reference's comparator (demo/common/testutil.cpp:351-361)."""
     a, b = _f(a).ravel(), _f(b).ravel()

@@ -43,6 +43,24 @@ class ModelOptions(C.Structure):
     ]
 
 
+class ImageIO(C.Structure):
+    """snnb_image_io"""
+    _fields_ = [
+        ("input_u8", C.c_void_p),
+        ("src_height", C.c_int),
+        ("src_width", C.c_int),
+        ("linear_filter", C.c_int),
+        ("mean4", C.c_float * 4),
+        ("norm4", C.c_float * 4),
+        ("output_f32", C.c_void_p),
+        ("output_capacity", C.c_size_t),
+        ("output_u8", C.c_void_p),
+        ("out_scale", C.c_float),
+        ("out_offset", C.c_float),
+        ("classes_1based", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes): every symbol include/snnb.h declares
 SIGNATURES = {
     "snnb_version": (C.c_int, []),
@@ -102,6 +120,7 @@ SIGNATURES = {
     "snnb_graph_destroy": (C.c_int, [vp]),
     "snnb_model_submit": (C.c_int, [vp, vp, vp, C.c_size_t, vp, c_int_p]),
     "snnb_model_submit_u8": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, vp, c_int_p]),
+    "snnb_model_submit_image": (C.c_int, [vp, C.POINTER(ImageIO), c_int_p]),
     "snnb_model_wait": (C.c_int, [vp, C.c_int]),
     "snnb_model_set_input": (C.c_int, [vp, C.c_int, vp]),
     "snnb_model_forward": (C.c_int, [vp]),

@@ -394,6 +394,29 @@ class MixedInferenceCore:
         self.wait(t)
         return out, (np.array(list(classes), dtype=np.int32) if want_classes else None)
 
+    def run_image(self, images_u8, mean4, norm4, linear=True, out_u8=False, out_scale=1.0, out_offset=0.0, want_classes=False):
+        """snnb_model_submit_image + wait: u8 NHWC images of ANY size in (resized + normalised on the device), fp32 tensor or u8 image out."""
+        from ._lib import ImageIO
+        images_u8 = np.ascontiguousarray(images_u8, dtype=np.uint8)
+        n, sh, sw, c = images_u8.shape
+        oshape = self.output_shape(0)
+        out = np.empty(oshape, np.uint8 if out_u8 else np.float32)
+        classes = (C.c_int * self.batch)() if want_classes else None
+        io = ImageIO()
+        io.input_u8, io.src_height, io.src_width, io.linear_filter = images_u8.ctypes.data, sh, sw, int(bool(linear))
+        io.mean4 = (C.c_float * 4)(*[float(v) for v in mean4])
+        io.norm4 = (C.c_float * 4)(*[float(v) for v in norm4])
+        io.output_capacity = out.size
+        if out_u8:
+            io.output_u8, io.out_scale, io.out_offset = out.ctypes.data, float(out_scale), float(out_offset)
+        else:
+            io.output_f32 = out.ctypes.data
+        io.classes_1based = C.cast(classes, C.c_void_p) if want_classes else None
+        t = C.c_int()
+        check(lib().snnb_model_submit_image(self.h, C.byref(io), C.byref(t)), "snnb_model_submit_image")
+        self.wait(t.value)
+        return out, (np.array(list(classes), dtype=np.int32) if want_classes else None)
+
     def wait(self, ticket):
         check(lib().snnb_model_wait(self.h, int(ticket)), "snnb_model_wait")
 

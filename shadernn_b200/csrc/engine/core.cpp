@@ -30,6 +30,7 @@ MixedInferenceCore::~MixedInferenceCore() {
         if (sl.yoloDev) cudaFree(sl.yoloDev);
         if (sl.yoloHost) cudaFreeHost(sl.yoloHost);
         if (sl.stageIn) cudaFree(sl.stageIn);
+        if (sl.stageResize) cudaFree(sl.stageResize);
         if (sl.stageOut) cudaFree(sl.stageOut);
         if (sl.argmax) cudaFree(sl.argmax);
         if (sl.h2dDone) cudaEventDestroy(sl.h2dDone);
@@ -485,8 +486,13 @@ int MixedInferenceCore::submitU8(const uint8_t* hostInput, const float mean[4], 
     SNNB_REQUIRE(mean && norm, "submitU8: null mean / norm");
     return submitImpl(hostInput, true, mean, norm, hostOutput, capacityFloats, classes1, ticket);
 }
+int MixedInferenceCore::submitImage(const snnb_image_io& io, int* ticket) {
+    SNNB_REQUIRE(io.input_u8 && io.src_height > 0 && io.src_width > 0, "submit_image: bad input");
+    SNNB_REQUIRE(!(io.output_f32 && io.output_u8), "submit_image: choose ONE of output_f32 / output_u8");
+    return submitImpl(io.input_u8, true, io.mean4, io.norm4, io.output_f32, io.output_capacity, io.classes_1based, ticket, &io);
+}
 int MixedInferenceCore::submitImpl(const void* hostInput, bool u8, const float* mean, const float* norm, float* hostOutput, size_t capacityFloats, int* classes1,
-                                   int* ticket) {
+                                   int* ticket, const snnb_image_io* io) {
     SNNB_REQUIRE(hostInput && ticket, "submit: null argument");
     if (ensureStreaming()) return 1;
     Slot& sl = slots[nextTicket & 1];
@@ -495,20 +501,41 @@ int MixedInferenceCore::submitImpl(const void* hostInput, bool u8, const float* 
     snnb_tensor* in  = inputLayers[0]->output;
     snnb_tensor* out = outputLayers[outIdx]->output; // nullptr for a detection model: its output is the box list (snnb_model_get_boxes)
     if (!out) hostOutput = nullptr, classes1 = nullptr;
-    const size_t inBytes = in->pixels() * in->c * (u8 ? sizeof(uint8_t) : sizeof(float)), outFloats = out ? out->pixels() * out->c : 0;
+    const bool resize = io && (io->src_height != in->h || io->src_width != in->w);
+    const size_t inBytes = resize ? (size_t) in->n * io->src_height * io->src_width * in->c : in->pixels() * in->c * (u8 ? sizeof(uint8_t) : sizeof(float));
+    const size_t outFloats = out ? out->pixels() * out->c : 0;
     SNNB_REQUIRE(!hostOutput || capacityFloats >= outFloats, "submit: output buffer too small (%zu < %zu floats)", capacityFloats, outFloats);
+    SNNB_REQUIRE(!(io && io->output_u8) || (out && io->output_capacity >= outFloats), "submit_image: u8 output buffer too small or the model has no tensor output");
+    void* stage = sl.stageIn;
+    if (resize) { // a source image of another size does not fit the model-sized staging: its own buffer, grown on demand
+        if (inBytes > sl.stageResizeBytes) {
+            SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+            if (sl.stageResize) SNNB_CUDA_OK(cudaFree(sl.stageResize));
+            SNNB_CUDA_OK(cudaMalloc(&sl.stageResize, inBytes));
+            sl.stageResizeBytes = inBytes;
+        }
+        stage = sl.stageResize;
+    }
     // copy stream: wait until the split kernel of the submission that last used this slot has consumed the staging
     if (sl.everUsed) SNNB_CUDA_OK(cudaStreamWaitEvent(copyStream, sl.stageFree, 0));
-    SNNB_CUDA_OK(cudaMemcpyAsync(sl.stageIn, hostInput, inBytes, cudaMemcpyHostToDevice, copyStream));
+    SNNB_CUDA_OK(cudaMemcpyAsync(stage, hostInput, inBytes, cudaMemcpyHostToDevice, copyStream));
     SNNB_CUDA_OK(cudaEventRecord(sl.h2dDone, copyStream));
     // compute stream
     SNNB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, sl.h2dDone, 0));
-    if (u8 ? launch_split_u8(ctx, reinterpret_cast<const uint8_t*>(sl.stageIn), in, mean, norm) : launch_split_f32(ctx, sl.stageIn, in)) return 1;
+    if (resize) {
+        if (launch_resize_u8(ctx, reinterpret_cast<const uint8_t*>(stage), io->src_height, io->src_width, in, mean, norm, io->linear_filter != 0)) return 1;
+    } else if (u8 ? launch_split_u8(ctx, reinterpret_cast<const uint8_t*>(sl.stageIn), in, mean, norm) : launch_split_f32(ctx, sl.stageIn, in)) {
+        return 1;
+    }
     SNNB_CUDA_OK(cudaEventRecord(sl.stageFree, ctx->stream));
     if (forward()) return 1;
     if (hostOutput) {
         if (launch_merge_f32(ctx, out, sl.stageOut)) return 1;
         SNNB_CUDA_OK(cudaMemcpyAsync(hostOutput, sl.stageOut, outFloats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (io && io->output_u8) { // the output as an 8-bit image: clamp(round(v * scale + offset), 0, 255) on the device, a quarter of the bytes back
+        if (launch_merge_u8(ctx, out, reinterpret_cast<uint8_t*>(sl.stageOut), io->out_scale, io->out_offset)) return 1;
+        SNNB_CUDA_OK(cudaMemcpyAsync(io->output_u8, sl.stageOut, outFloats, cudaMemcpyDeviceToHost, ctx->stream));
     }
     sl.classesHost = nullptr;
     if (classes1 && isClassifier) {

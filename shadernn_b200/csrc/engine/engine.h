@@ -336,7 +336,9 @@ public:
     int submit(const float* hostInput, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
     // same with a u8 NHWC image batch, normalised on the device as (x - mean[c]) * norm[c] (imageTexture.h:114)
     int submitU8(const uint8_t* hostInput, const float mean[4], const float norm[4], float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
-    int submitImpl(const void* hostInput, bool u8, const float* mean, const float* norm, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket);
+    int submitImpl(const void* hostInput, bool u8, const float* mean, const float* norm, float* hostOutput, size_t capacityFloats, int* classes1, int* ticket,
+                   const snnb_image_io* io = nullptr);
+    int submitImage(const snnb_image_io& io, int* ticket);
     int wait(int ticket);
     int layerOutput(int layerId, float* host, size_t capacityFloats);
     int timeLayers(std::vector<float>& ms);
@@ -370,6 +372,8 @@ private:
     int decodeYolo(void* dev, void* host, bool sync); // candidates kernel + D2H (+ sync + host NMS into `boxes`)
     // streaming state
     struct Slot {
+        void* stageResize = nullptr; // device staging of a differently-sized u8 input (grown on demand)
+        size_t stageResizeBytes = 0;
         float* stageIn = nullptr;   // device fp32 staging for this slot's input batch
         float* stageOut = nullptr;  // device fp32 staging for output 0
         int* argmax = nullptr;

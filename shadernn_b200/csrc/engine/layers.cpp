@@ -395,7 +395,7 @@ int YOLOLayer::finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes
         if (counts[n] > maxc) return -1; // cannot happen: one slot per (cell, anchor)
     perImage.assign(N, SNNModelOutputBoxes());
     const int cells0 = inputs[0]->h * inputs[0]->w * GC;
-    for (int n = 0; n < N; ++n) {
+    auto finishImage = [&](int n) {
         std::vector<const float*> rows(counts[n]);
         for (int i = 0; i < counts[n]; ++i) rows[i] = cand + ((size_t) n * maxc + i) * 8;
         auto scan = [](const float* r) {
@@ -416,6 +416,20 @@ int YOLOLayer::finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes
             if (decodeCell(r + 1, yi, gx, gy, gc, gw, gh, b)) list.push_back(b);
         }
         nms(list, perImage[n]);
+    };
+    // NMS is quadratic in an image's candidate count: images with many candidates get a host thread each (as decode() does)
+    long long work = 0;
+    for (int n = 0; n < N; ++n) work += (long long) counts[n] * counts[n];
+    const int nthreads = work < 200000 ? 1 : std::max(1, std::min(N, (int) std::min(32u, std::max(1u, std::thread::hardware_concurrency()))));
+    if (nthreads == 1) {
+        for (int n = 0; n < N; ++n) finishImage(n);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t)
+            pool.emplace_back([&, t]() {
+                for (int n = t; n < N; n += nthreads) finishImage(n);
+            });
+        for (auto& th : pool) th.join();
     }
     return 0;
 }

@@ -113,6 +113,11 @@ int snnb_model_submit_u8(snnb_model* m, const uint8_t* host_input_u8, const floa
     SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
     return m->core->submitU8(host_input_u8, mean4, norm4, host_output, out_capacity, classes, ticket);
 }
+int snnb_model_submit_image(snnb_model* m, const snnb_image_io* io, int* ticket) {
+    SNNB_REQUIRE(m && io && ticket, "snnb_model_submit_image: null argument");
+    SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));
+    return m->core->submitImage(*io, ticket);
+}
 int snnb_model_wait(snnb_model* m, int ticket) {
     SNNB_REQUIRE(m, "snnb_model_wait: null model");
     SNNB_CUDA_OK(cudaSetDevice(m->core->ctx->device));

@@ -1077,6 +1077,73 @@ int launch_split_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, snnb_tensor* 
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
+// u8 image of ANOTHER size -> resize (linear or nearest) -> (x - mean[c]) * norm[c] -> split-fp16: ImageTexture::resize
+// (core/inc/snn/imageTexture.h:137) = shadertemplate_vk_resize.comp:42-61: the output texel centre (x + 0.5) / outW is sampled from
+// the source texture with the sampler's filter (texel centres at (i + 0.5) / inW, clamp to edge), then normalised.
+__global__ void resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, TV t, U8Norm q, int linear) {
+    pdl_wait();
+    const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG    = t.Cp >> 3;
+    const size_t px = gid / CG;
+    const int c     = (int) (gid % CG) * 8;
+    const int ox = (int) (px % t.W), oy = (int) ((px / t.W) % t.H), n = (int) (px / ((size_t) t.W * t.H));
+    const float fx = ((float) ox + 0.5f) / (float) t.W * (float) sw, fy = ((float) oy + 0.5f) / (float) t.H * (float) sh;
+    const uint8_t* img = src + (size_t) n * sh * sw * t.C;
+    float v[8];
+    if (linear) {
+        const float sx = fx - 0.5f, sy = fy - 0.5f;
+        const float x0f = floorf(sx), y0f = floorf(sy);
+        const float ax = sx - x0f, ay = sy - y0f;
+        const int x0 = min(max((int) x0f, 0), sw - 1), x1 = min(max((int) x0f + 1, 0), sw - 1);
+        const int y0 = min(max((int) y0f, 0), sh - 1), y1 = min(max((int) y0f + 1, 0), sh - 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float r = 0.0f;
+            if (c + j < t.C) {
+                const float p00 = (float) __ldg(img + ((size_t) y0 * sw + x0) * t.C + c + j), p01 = (float) __ldg(img + ((size_t) y0 * sw + x1) * t.C + c + j);
+                const float p10 = (float) __ldg(img + ((size_t) y1 * sw + x0) * t.C + c + j), p11 = (float) __ldg(img + ((size_t) y1 * sw + x1) * t.C + c + j);
+                const float top = p00 + ax * (p01 - p00), bot = p10 + ax * (p11 - p10);
+                r               = ((top + ay * (bot - top)) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3];
+            }
+            v[j] = r;
+        }
+    } else {
+        const int x0 = min((int) fx, sw - 1), y0 = min((int) fy, sh - 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? ((float) __ldg(img + ((size_t) y0 * sw + x0) * t.C + c + j) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3] : 0.0f;
+    }
+    store8(t.hi, t.lo, gid * 8, v);
+}
+int launch_resize_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, int src_h, int src_w, snnb_tensor* t, const float mean[4], const float norm[4], bool linear) {
+    U8Norm q;
+    for (int i = 0; i < 4; ++i) q.mean[i] = mean[i], q.norm[i] = norm[i];
+    launch_k(resize_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc_u8, src_h, src_w, view(t), q, linear ? 1 : 0);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+// tensor -> 8-bit image, dense NHWC: clamp(round(v * scale + offset), 0, 255) (the image-to-image models' outputs: style transfer,
+// super-resolution); a quarter of the fp32 bytes cross PCIe on the way back
+__global__ void merge_u8_kernel(TV t, uint8_t* __restrict__ dst, float scale, float offset) {
+    pdl_wait();
+    const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
+    const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int CG    = t.Cp >> 3;
+    const size_t px = gid / CG;
+    const int c     = (int) (gid % CG) * 8;
+    float v[8];
+    load8(t.hi, t.lo, gid * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (c + j < t.C) dst[px * t.C + c + j] = (uint8_t) fminf(fmaxf(rintf(v[j] * scale + offset), 0.0f), 255.0f);
+}
+int launch_merge_u8(snnb_context* ctx, const snnb_tensor* t, uint8_t* dev_nhwc_u8, float scale, float offset) {
+    launch_k(merge_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, view(t), dev_nhwc_u8, scale, offset);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
 int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc) {
     launch_k(merge_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, view(t), dev_nhwc);
     SNNB_LAUNCH_CHECK(ctx);

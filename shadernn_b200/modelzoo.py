@@ -473,12 +473,19 @@ def yolov3_tiny(input_hw=(416, 416), head_channels=18, seed=SEED):
     x = cbl(x, 1024, 3)
     route_b = cbl(x, 256, 1)
     y = cbl(route_b, 512, 3)
-    head13 = b.conv(y, head_channels, 1, 1, "valid", "linear", bias=True, bn=False, gain=1.0)
+    def head(t):
+        # objectness biased low, as in a trained detector (a handful of cells pass the 0.35 confidence threshold, not thousands:
+        # with random heads the host NMS, quadratic in the candidate count, was all the end-to-end number measured)
+        i = b.conv(t, head_channels, 1, 1, "valid", "linear", bias=True, bn=False, gain=1.0)
+        b.layers[i]["_w"]["bias"][4::head_channels // 3] = -2.0
+        return i
+
+    head13 = head(y)
     z = cbl(route_b, 128, 1)
     z = b.upsample(z, 2, "nearest")
     z = b.concat(z, route_a)
     z = cbl(z, 256, 3)
-    head26 = b.conv(z, head_channels, 1, 1, "valid", "linear", bias=True, bn=False, gain=1.0)
+    head26 = head(z)
     b.yolo(head13, head26)
     return b.layers
 

@@ -389,6 +389,35 @@ def test_model_error_paths(ctx, tmp_path):
         core.MixedInferenceCore(ctx, str(trunc))
 
 
+@pytest.mark.parametrize("linear", [True, False])
+def test_device_resize_normalise_and_u8_output(ctx, model_dir, linear):
+    # SURVEY §8 f-N3: pre/post-processing on the device. snnb_model_submit_image takes 8-bit images of any size, resizes them like
+    # ImageTexture::resize (vk_resize.comp:42-61), normalises, runs the model and can return an 8-bit image
+    # (clamp(round(v * scale + offset))). Checked against the oracle's restatement of the resize + the same model fed with the
+    # resized fp32 image through the plain run().
+    path, _ = modelzoo.build("candy", model_dir, input_hw=(64, 80))
+    m = core.MixedInferenceCore(ctx, path, batch=2, input_hw=(64, 80), fuse=True)
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (2, 150, 233, 3), dtype=np.uint8)
+    mean4, norm4 = [10.0, 20.0, 30.0, 0.0], [1.0, 0.5, 2.0, 1.0]
+    resized = oracle.resize_normalize(img, (64, 80), mean4, norm4, linear)
+    want, _ = m.run(resized, want_classes=False)
+    got, _ = m.run_image(img, mean4, norm4, linear=linear)
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) <= 2e-4 * float(np.abs(want).max())  # resize arithmetic agrees to fp32 rounding
+    # the resized input itself, observed through an identity-sized run: up-scaling too
+    up = oracle.resize_normalize(img[:, :40, :50], (64, 80), [0.0] * 4, [1.0] * 4, linear)
+    got_up, _ = m.run_image(img[:, :40, :50].copy(), [0.0] * 4, [1.0] * 4, linear=linear)
+    want_up, _ = m.run(up, want_classes=False)
+    assert float(np.abs(got_up - want_up).max()) <= 2e-4 * float(np.abs(want_up).max())
+    # 8-bit output
+    scale, offset = 0.7, 12.0
+    got_u8, _ = m.run_image(img, mean4, norm4, linear=linear, out_u8=True, out_scale=scale, out_offset=offset)
+    want_u8 = np.clip(np.rint(got * np.float32(scale) + np.float32(offset)), 0, 255).astype(np.uint8)
+    assert got_u8.dtype == np.uint8 and int(np.abs(got_u8.astype(int) - want_u8.astype(int)).max()) <= 1
+    assert float((got_u8 != want_u8).mean()) < 1e-3  # only exact .5 ties may round differently
+
+
 def test_layer_registration_through_the_c_abi(ctx, tmp_path):
     # snnb_register_layer = snn::dp::registerLayer(name, LayerCreator) (layerFactory.h:116-122) at the C boundary: the host registers
     # a creator for a new layer type; the model file names it; the creator reads its JSON through the accessors and supplies dims +
