@@ -308,8 +308,8 @@ class Workload:
 
     def d2h_bytes(self):
         if self.detector:
-            cells = sum(l_h * l_w for (l_h, l_w) in self.head_dims) * 3
-            return self.batch * (4 + cells * 8 * 4)  # candidate lists of the device-side YOLO threshold + compaction (one slot per cell and anchor)
+            cells = self.batch * sum(l_h * l_w for (l_h, l_w) in self.head_dims) * 3
+            return 32 + min(cells, 2048) * 32  # header + head of the candidate list of the device-side YOLO threshold + compaction
         return int(np.prod(self.out_shape)) * 4 + self.batch * 4
 
 

@@ -452,10 +452,10 @@ int MixedInferenceCore::run(const float* hostInput, float* hostOutput, size_t ca
 // to the host, then the exact score formula, score sort and NMS there (identical lists, identical order: finishDecode).
 int MixedInferenceCore::decodeYolo(void* dev, void* host, bool sync) {
     if (yolo->enqueueCandidates(ctx, dev)) return 1;
-    SNNB_CUDA_OK(cudaMemcpyAsync(host, dev, yolo->candidateBytes(), cudaMemcpyDeviceToHost, ctx->stream));
+    SNNB_CUDA_OK(cudaMemcpyAsync(host, dev, yolo->headBytes(), cudaMemcpyDeviceToHost, ctx->stream)); // count + the first rows
     if (!sync) return 0;
     SNNB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    const int rc = yolo->finishDecode(host, boxes);
+    const int rc = yolo->finishDecode(host, dev, boxes);
     if (rc < 0) return yolo->decode(ctx, boxes); // an image overflowed its candidate list: all-host decode of the (still resident) heads
     return rc;
 }
@@ -559,7 +559,7 @@ int MixedInferenceCore::wait(int ticket) {
         for (uint32_t i = 0; i < options.batch; ++i) sl.classesHost[i] += 1; // core.cpp:228-233: argmax + 1
     sl.busy = false;
     if (yolo) {
-        const int rc = yolo->finishDecode(sl.yoloHost, boxes);
+        const int rc = yolo->finishDecode(sl.yoloHost, sl.yoloDev, boxes);
         SNNB_REQUIRE(rc >= 0, "wait: corrupt detection candidate list");
         return rc;
     }

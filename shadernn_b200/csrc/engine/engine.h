@@ -12,6 +12,7 @@
 // into a single device arena, one CUDA kernel launch per layer (fewer with fusion), optional CUDA-graph replay.
 #pragma once
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -281,13 +282,17 @@ public:
     // all-host decode (downloads both heads): the fallback when an image has more candidates than the device list holds
     int decode(snnb_context* ctx, std::vector<SNNModelOutputBoxes>& perImage);
     // device threshold + compaction into `devCounts` / `devCand` ([N] ints, [N][YOLO_MAX_CAND][8] floats), asynchronous
-    // one slot per (cell, anchor) of both heads: the list can never overflow, whatever the scores
-    int maxCand() const { return inputs.size() < 2 ? 0 : (inputs[0]->h * inputs[0]->w + inputs[1]->h * inputs[1]->w) * 3; }
-    size_t candidateBytes() const { return inputs.size() < 2 ? 0 : (size_t) inputs[0]->n * (sizeof(int) + (size_t) maxCand() * 8 * sizeof(float)); }
+    // one slot per (image, cell, anchor) of both heads: the list can never overflow, whatever the scores. Layout: 32-byte header
+    // (word 0 = number of candidates) + rows of 8 floats. The host copies the header and the first YOLO_HEAD_ROWS rows with every
+    // submission; the (rare) rest is fetched in wait().
+    static constexpr int YOLO_HEAD_ROWS = 2048;
+    int maxCand() const { return inputs.size() < 2 ? 0 : inputs[0]->n * (inputs[0]->h * inputs[0]->w + inputs[1]->h * inputs[1]->w) * 3; }
+    size_t candidateBytes() const { return 32 + (size_t) maxCand() * 8 * sizeof(float); }
+    size_t headBytes() const { return 32 + (size_t) std::min(maxCand(), YOLO_HEAD_ROWS) * 8 * sizeof(float); }
     int enqueueCandidates(snnb_context* ctx, void* devBuf);
     // host part on the downloaded buffer: exact score formula, confidence threshold, score sort, NMS (yololayer.cpp:56-164).
     // Returns 0, or -1 when some image overflowed the candidate list (caller falls back to decode()).
-    int finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes>& perImage) const;
+    int finishDecode(const void* hostBuf, const void* devBuf, std::vector<SNNModelOutputBoxes>& perImage) const;
 };
 
 // -------------------------------------------------------------------------------------------------------------

@@ -379,47 +379,55 @@ int YOLOLayer::enqueueCandidates(snnb_context* ctx, void* devBuf) {
         set_error("%s: YOLO expects two heads of >= %d channels", name.c_str(), GC * ONUM);
         return 2;
     }
-    const int N = inputs[0]->n;
     int* counts = static_cast<int*>(devBuf);
-    float* cand = reinterpret_cast<float*>(counts + N);
+    float* cand = reinterpret_cast<float*>(static_cast<char*>(devBuf) + 32);
     // margin below the threshold: the device's expf may differ from the host's std::exp in the last bits; the host decides
     return launch_yolo_candidates(ctx, inputs[0], inputs[1], kConfThresh - 1e-3f, maxCand(), counts, cand);
 }
 
-int YOLOLayer::finishDecode(const void* hostBuf, std::vector<SNNModelOutputBoxes>& perImage) const {
-    const int N       = inputs[0]->n;
-    const int* counts = static_cast<const int*>(hostBuf);
-    const float* cand = reinterpret_cast<const float*>(counts + N);
-    const int maxc = maxCand();
-    for (int n = 0; n < N; ++n)
-        if (counts[n] > maxc) return -1; // cannot happen: one slot per (cell, anchor)
+int YOLOLayer::finishDecode(const void* hostBuf, const void* devBuf, std::vector<SNNModelOutputBoxes>& perImage) const {
+    const int N     = inputs[0]->n;
+    const int total = *static_cast<const int*>(hostBuf);
+    if (total < 0 || total > maxCand()) return -1;
+    const float* cand = reinterpret_cast<const float*>(static_cast<const char*>(hostBuf) + 32);
+    if (total > YOLO_HEAD_ROWS) { // more candidates than the head copy carried: fetch the rest now (the device list is still intact)
+        float* rest = const_cast<float*>(cand) + (size_t) YOLO_HEAD_ROWS * 8;
+        if (cudaMemcpy(rest, static_cast<const char*>(devBuf) + 32 + (size_t) YOLO_HEAD_ROWS * 32, (size_t) (total - YOLO_HEAD_ROWS) * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+    }
+    auto word = [](const float* r, int i) {
+        int v;
+        memcpy(&v, r + i, sizeof v);
+        return v;
+    };
+    std::vector<std::vector<const float*>> byImage(N);
+    for (int i = 0; i < total; ++i) {
+        const float* r = cand + (size_t) i * 8;
+        const int n    = word(r, 0);
+        if (n < 0 || n >= N) return -1;
+        byImage[n].push_back(r);
+    }
     perImage.assign(N, SNNModelOutputBoxes());
     const int cells0 = inputs[0]->h * inputs[0]->w * GC;
     auto finishImage = [&](int n) {
-        std::vector<const float*> rows(counts[n]);
-        for (int i = 0; i < counts[n]; ++i) rows[i] = cand + ((size_t) n * maxc + i) * 8;
-        auto scan = [](const float* r) {
-            int v;
-            memcpy(&v, r, sizeof v);
-            return v;
-        };
+        auto& rows = byImage[n];
         // the device appended in arbitrary order: back to the order the reference's loops visit the cells
-        std::sort(rows.begin(), rows.end(), [&](const float* a, const float* b) { return scan(a) < scan(b); });
+        std::sort(rows.begin(), rows.end(), [&](const float* a, const float* b) { return word(a, 1) < word(b, 1); });
         std::vector<Box> list;
         for (const float* r : rows) {
-            int s        = scan(r);
+            int s        = word(r, 1);
             const int yi = s >= cells0 ? 1 : 0;
             if (yi) s -= cells0;
             const int gw = inputs[yi]->w, gh = inputs[yi]->h;
             const int gc = s % GC, cell = s / GC, gx = cell % gw, gy = cell / gw;
             Box b;
-            if (decodeCell(r + 1, yi, gx, gy, gc, gw, gh, b)) list.push_back(b);
+            if (decodeCell(r + 2, yi, gx, gy, gc, gw, gh, b)) list.push_back(b);
         }
         nms(list, perImage[n]);
     };
     // NMS is quadratic in an image's candidate count: images with many candidates get a host thread each (as decode() does)
     long long work = 0;
-    for (int n = 0; n < N; ++n) work += (long long) counts[n] * counts[n];
+    for (int n = 0; n < N; ++n) work += (long long) byImage[n].size() * (long long) byImage[n].size();
     const int nthreads = work < 200000 ? 1 : std::max(1, std::min(N, (int) std::min(32u, std::max(1u, std::thread::hardware_concurrency()))));
     if (nthreads == 1) {
         for (int n = 0; n < N; ++n) finishImage(n);

@@ -534,21 +534,34 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(TV in, TV out) {
 // more in ramp-up than in work. One CTA per image: pooled vector in shared memory (sequential sum per channel, deterministic),
 // one warp per output unit (lanes over input channels, shuffle tree), then the activation or a max-subtracted softmax
 // (cpulayer.h:175-191). Weights fp32 [IC][OCw] (the CUDA-core conv layout).
-__global__ void __launch_bounds__(256) gap_dense_kernel(TV in, TV out, const float* __restrict__ w, int ocw, const float* __restrict__ bias, int act, float alpha,
-                                                        int softmax) {
+// r02: 1024 threads and a Dense phase with lanes over the UNITS (coalesced weight rows, independent loads): the r01 version (256
+// threads, one warp per unit striding the channels) was a chain of ~45 dependent L2 round trips = 16 us for 0.3 MFLOP.
+constexpr int GD_THREADS = 1024;
+__global__ void __launch_bounds__(GD_THREADS) gap_dense_kernel(TV in, TV out, const float* __restrict__ w, int ocw, const float* __restrict__ bias, int act, float alpha,
+                                                               int softmax, int parts) {
     pdl_wait();
-    extern __shared__ float hs[]; // [parts][in.Cp] partial sums (row 0 becomes the pooled vector), then [out.Cp] logits
+    extern __shared__ float hs[]; // [parts][in.Cp] partial sums (row 0 becomes the pooled vector), [32 warps][out.Cp] Dense partials, [out.Cp] logits
     const int n = blockIdx.x, HW = in.H * in.W, CG = in.Cp >> 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int parts = max(1, min((int) blockDim.x / CG, 8)); // pixel ranges summed by different threads (49 dependent loads otherwise)
-    float* xs     = hs;
-    float* logits = hs + parts * in.Cp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = GD_THREADS / 32;
+    float* xs     = hs; // `parts` pixel ranges are summed by different threads
+    float* red    = hs + parts * in.Cp;
+    float* logits = red + nwarps * out.Cp;
     for (int item = threadIdx.x; item < CG * parts; item += blockDim.x) {
         const int cg = item % CG, part = item / CG;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-        for (int px = part; px < HW; px += parts) {
+        int px = part;
+        for (; px + 3 * parts < HW; px += 4 * parts) { // four independent loads in flight; summed in pixel order (deterministic)
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8(in.hi, in.lo, ((size_t) n * HW + px + u * parts) * in.Cp + cg * 8, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+        }
+        for (; px < HW; px += parts) {
             float v[8];
             load8(in.hi, in.lo, ((size_t) n * HW + px) * in.Cp + cg * 8, v);
 #pragma unroll
@@ -564,11 +577,32 @@ __global__ void __launch_bounds__(256) gap_dense_kernel(TV in, TV out, const flo
         xs[c] = t / (float) HW;
     }
     __syncthreads();
-    for (int oc = warp; oc < out.C; oc += (int) (blockDim.x >> 5)) {
-        float s = 0.0f;
-        for (int c = lane; c < in.C; c += 32) s = fmaf(xs[c], __ldg(w + (size_t) c * ocw + oc), s);
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) logits[oc] = softmax ? s + bias[oc] : apply_act(s + bias[oc], act, alpha);
+    // Dense: warp `warp` takes the channels c = warp, warp + 32, ...; its lanes take the units oc = lane, lane + 32, ... (<= 8 per lane:
+    // out.C <= 256): every load of a weight row is coalesced and the loads of different channels are independent
+    {
+        float part[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[k] = 0.0f;
+        for (int c = warp; c < in.C; c += nwarps) {
+            const float xv    = xs[c];
+            const float* wrow = w + (size_t) c * ocw;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int oc = lane + 32 * k;
+                if (oc < out.C) part[k] = fmaf(xv, __ldg(wrow + oc), part[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int oc = lane + 32 * k;
+            if (oc < out.C) red[warp * out.Cp + oc] = part[k];
+        }
+    }
+    __syncthreads();
+    for (int oc = threadIdx.x; oc < out.C; oc += blockDim.x) { // warps added in order: deterministic
+        float s = red[oc];
+        for (int q = 1; q < nwarps; ++q) s += red[q * out.Cp + oc];
+        logits[oc] = softmax ? s + bias[oc] : apply_act(s + bias[oc], act, alpha);
     }
     __syncthreads();
     if (softmax && warp == 0) { // max-subtracted softmax over the units, fixed-shape tree
@@ -584,15 +618,22 @@ __global__ void __launch_bounds__(256) gap_dense_kernel(TV in, TV out, const flo
     for (int oc = threadIdx.x; oc < out.Cp; oc += blockDim.x) store1(out.hi, out.lo, (size_t) n * out.Cp + oc, oc < out.C ? logits[oc] : 0.0f);
 }
 
+// pixel ranges per channel group, limited by the 48 KB of shared memory available without opt-in; 0 = does not fit
+static int gap_dense_parts(const snnb_tensor* in, const snnb_tensor* out) {
+    int parts = std::max(1, std::min(GD_THREADS / (in->cp >> 3), 8));
+    while (parts > 1 && (size_t) (parts * in->cp + (GD_THREADS / 32 + 1) * out->cp) * sizeof(float) > 48 * 1024) --parts;
+    return (size_t) (parts * in->cp + (GD_THREADS / 32 + 1) * out->cp) * sizeof(float) > 48 * 1024 ? 0 : parts;
+}
 bool gap_dense_supported(const snnb_tensor* in, const snnb_tensor* out, const snnb_weights* w) {
-    return w && w->w_f32 && in->h * in->w >= 4 && in->cp <= 4096 && out->c <= 256 && out->h * out->w == 1 && in->n == out->n;
+    return w && w->w_f32 && in->h * in->w >= 4 && in->cp <= 4096 && out->c <= 256 && out->h * out->w == 1 && in->n == out->n && gap_dense_parts(in, out) > 0;
 }
 int launch_gap_dense(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, const snnb_weights* w, int act, float alpha, bool softmax) {
     ctx->last_kernel = "gap_dense_kernel";
-    const int parts   = std::max(1, std::min(256 / (in->cp >> 3), 8));
-    const size_t smem = (size_t) (parts * in->cp + out->cp) * sizeof(float);
-    launch_k(gap_dense_kernel, dim3((unsigned) in->n), dim3(256), smem, ctx->stream, view(in), view(out), (const float*) w->w_f32, w->ocw, (const float*) w->bias, act, alpha,
-             softmax ? 1 : 0);
+    const int parts   = gap_dense_parts(in, out);
+    SNNB_REQUIRE(parts > 0, "launch_gap_dense: the head does not fit in shared memory");
+    const size_t smem = (size_t) (parts * in->cp + (GD_THREADS / 32 + 1) * out->cp) * sizeof(float);
+    launch_k(gap_dense_kernel, dim3((unsigned) in->n), dim3(GD_THREADS), smem, ctx->stream, view(in), view(out), (const float*) w->w_f32, w->ocw, (const float*) w->bias, act, alpha,
+             softmax ? 1 : 0, parts);
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -734,7 +775,7 @@ int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx) {
 // YOLO decode, device part (yololayer.cpp:115-164): threshold + compaction. One thread per (image, head, cell, anchor) reads the
 // six values of its box and evaluates the reference's score formula; cells that could pass the confidence threshold (0.35,
 // tested with a safety margin: the HOST re-evaluates the exact std::exp formula and applies the real threshold) append
-// {scan index, d0..d5} to the image's candidate list. The host then sorts the few survivors by scan index - the order the
+// {image, scan index, d0..d5} to the batch's candidate list. The host then sorts the few survivors by scan index - the order the
 // reference's loops visit them - and runs score-sort + NMS exactly as before: the detection list is bit-identical to the
 // all-host decode while 16 images x 2535 cells x 18 floats no longer cross PCIe.
 // ------------------------------------------------------------------------------------------------------------
@@ -754,18 +795,18 @@ __global__ void yolo_candidates_kernel(TV h0, TV h1, float thresh, int maxc, int
     for (int i = 0; i < 6; ++i) d[i] = load1(t.hi, t.lo, base + i);
     const float prob = 1.f / ((1.f + expf(-d[4]) * (1.f + expf(-d[5])))); // yololayer.cpp:136, as parenthesised; one class: maxLogit = d[5]
     if (prob > thresh) {
-        const int slot = atomicAdd(counts + n, 1);
+        const int slot = atomicAdd(counts, 1); // ONE list for the whole batch: the host copies its head, not N fixed-size lists
         if (slot < maxc) {
-            float* o = cand + ((size_t) n * maxc + slot) * 8;
-            o[0]     = __int_as_float(r); // scan index: (head, gy, gx, gc) in the reference's loop order
+            float* o = cand + (size_t) slot * 8;
+            o[0]     = __int_as_float(n);
+            o[1]     = __int_as_float(r); // scan index: (head, gy, gx, gc) in the reference's loop order
 #pragma unroll
-            for (int i = 0; i < 6; ++i) o[1 + i] = d[i];
-            o[7] = prob;
+            for (int i = 0; i < 6; ++i) o[2 + i] = d[i];
         }
     }
 }
 int launch_yolo_candidates(snnb_context* ctx, const snnb_tensor* h0, const snnb_tensor* h1, float thresh, int maxc, int* counts, float* cand) {
-    SNNB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * h0->n, ctx->stream));
+    SNNB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int), ctx->stream));
     const long long total = (long long) h0->n * ((long long) h0->h * h0->w + (long long) h1->h * h1->w) * 3;
     launch_k(yolo_candidates_kernel, dim3((unsigned) ((total + 255) / 256)), dim3(256), 0, ctx->stream, view(h0), view(h1), thresh, maxc, counts, cand);
     SNNB_LAUNCH_CHECK(ctx);

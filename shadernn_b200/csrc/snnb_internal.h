@@ -190,7 +190,7 @@ int launch_batchnorm(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out,
 int launch_activation(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, int act, float alpha);
 int launch_softmax(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
 int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx);
-// YOLO decode, device part: cells whose score can pass `thresh` -> per-image candidate lists [N][maxc][8] = {scan index, d0..d5, score}
+// YOLO decode, device part: cells whose score can pass `thresh` -> ONE candidate list [maxc][8] = {image, scan index, d0..d5}; counts[0] = its length
 int launch_yolo_candidates(snnb_context* ctx, const snnb_tensor* h0, const snnb_tensor* h1, float thresh, int maxc, int* counts, float* cand);
 int launch_flatten(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out);
 int launch_concat(snnb_context* ctx, const snnb_tensor* a, const snnb_tensor* b, snnb_tensor* out);

@@ -27,9 +27,22 @@ def main(path):
     hdr, units = rows[0], rows[1]
     idx = [(hdr.index(k), n) for k, n in WANT if k in hdr]
     w = csv.writer(sys.stdout)
-    w.writerow([n + ("" if not units[i] or n in ("kernel", "grid", "block") else "[" + units[i] + "]") for i, n in idx])
+    # byte counters come back in whatever unit ncu picked per column (byte / Kbyte / Mbyte / Gbyte): the *_MB columns are always MB
+    scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+
+    def cell(r, i, n):
+        if n == "kernel":
+            return r[i].split("(")[0]
+        if n.endswith("_MB") and units[i] in scale:
+            try:
+                return "%.3f" % (float(r[i].replace(",", "")) * scale[units[i]])
+            except ValueError:
+                return r[i]
+        return r[i]
+
+    w.writerow([n + ("" if not units[i] or n in ("kernel", "grid", "block") or n.endswith("_MB") else "[" + units[i] + "]") for i, n in idx])
     for r in rows[2:]:
-        w.writerow([r[i].split("(")[0] if n == "kernel" else r[i] for i, n in idx])
+        w.writerow([cell(r, i, n) for i, n in idx])
 
 
 if __name__ == "__main__":

@@ -75,6 +75,103 @@ __global__ void __launch_bounds__(64, 1) bench(int terms, int n, int halo, int k
     }
 }
 
+// The same loop with what conv_umma_kernel's issue thread does besides the MMAs, as compile-time variants (scalar work between
+// K blocks is NOT hidden behind queued MMAs, so the variants must not add runtime branching of their own):
+//   ORDER 0: A_hi x cat, A_lo x B_hi alternating per K step      ORDER 1: the kernel's order, cat x4 then lo x4
+//   FENCE: tcgen05.fence::after_thread_sync per K block
+//   WAIT 0 none | 1 mbarrier.test_wait (completed phase) after the first MMA | 2 mbarrier.try_wait (completed phase) before the first MMA
+template <int ORDER, int FENCE, int WAIT>
+__global__ void __launch_bounds__(64, 1) bench3(int n, int kblocks, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bars[10];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 10; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[9])) : "memory"); // bars[9]: phase 0 complete
+    }
+    for (int i = threadIdx.x; i < (200 * 1024) / 4; i += blockDim.x) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4u * i), "r"(0));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = slot;
+    if (warp == 1) {
+        const uint64_t a_hi0 = make_desc(base, 1280), a_lo0 = make_desc(base + 24576, 1280), b = make_desc(base + 49152, 1024);
+        const uint32_t id_cat = make_idesc(128, 2 * n), id = make_idesc(128, n), done = smem_u32(&bars[9]);
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+        if (pred) {
+            const long long t0 = clock64();
+            uint32_t off = 0, bad = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const uint64_t a_hi = a_hi0 + off, a_lo = a_lo0 + off;
+                if (WAIT == 2) {
+                    uint32_t ok;
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(done) : "memory");
+                    bad += ok ^ 1u;
+                }
+                if (FENCE) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (ORDER == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mma(tmem, a_hi + 2u * j, b + 2u * j, id_cat, 1u);
+                        mma(tmem, a_lo + 2u * j, b + 2u * j, id, 1u);
+                        if (j == 0 && WAIT == 1) {
+                            uint32_t ok;
+                            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(done) : "memory");
+                            bad += ok ^ 1u;
+                        }
+                    }
+                } else {
+                    mma(tmem, a_hi, b, id_cat, 1u);
+                    if (WAIT == 1) {
+                        uint32_t ok;
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(done) : "memory");
+                        bad += ok ^ 1u;
+                    }
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) mma(tmem, a_hi + 2u * j, b + 2u * j, id_cat, 1u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma(tmem, a_lo + 2u * j, b + 2u * j, id, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[kb & 7])) : "memory");
+                off = off == 176u ? 0u : off + 8u; // walks (and wraps) the halo offsets
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[8])) : "memory");
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bars[8])) : "memory");
+            const long long t1 = clock64();
+            if (blockIdx.x == 0) out[0] = t1 - t0 + (bad ? 1000000000LL : 0);
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+template <int ORDER, int FENCE, int WAIT> static void run3(long long* d) {
+    cudaFuncSetAttribute(bench3<ORDER, FENCE, WAIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+    for (int n : {64, 128}) {
+        bench3<ORDER, FENCE, WAIT><<<148, 64, 202 * 1024>>>(n, 900, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long c = -1;
+        if (e == cudaSuccess) cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+        printf("3-term n_blk %3d halo | order %s | fence.after %d | %s: %7.1f clk per K block%s\n", n, ORDER ? "cat x4, lo x4 (kernel)" : "hi/lo alternating     ", FENCE,
+               WAIT == 0 ? "no barrier op          " : (WAIT == 1 ? "test_wait after 1st MMA" : "try_wait before MMAs   "), (double) c / 900, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
+}
+
 int main() {
     long long* d;
     cudaMalloc(&d, 8);
@@ -98,5 +195,12 @@ int main() {
                        100.0 * ideal * kblocks / (double) c);
             }
         }
+    run3<0, 0, 0>(d);
+    run3<1, 0, 0>(d);
+    run3<1, 1, 0>(d);
+    run3<1, 0, 1>(d);
+    run3<1, 0, 2>(d);
+    run3<1, 1, 1>(d);
+    run3<0, 1, 1>(d);
     return 0;
 }
