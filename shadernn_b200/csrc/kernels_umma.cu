@@ -1295,10 +1295,12 @@ static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int
         if (blk * t < OC) continue;
         // boxes narrower than 8 pixels (7x7 maps) move ~20 % fewer bytes per clock through the TMA unit (measured 59 vs 74-77 B/clk)
         const double ingest  = tile_w < 8 ? 58.0 : 72.0;
-        // halo mode: one (8+2) x (16+2) halo tile per channel block serves all nine taps
-        const double a_bytes = (terms == 1 ? 1.0 : 2.0) * (halo ? HL_W * HL_H * 128 / 9.0 : rows_used * 128.0), b_bytes = (terms == 3 ? 2.0 : 1.0) * blk * 128;
+        // Measured K-block cadences (r02 traces, 3-term): plain 650 clk at n_blk 64 / 811-830 at 128 (the load ring keeps ~3 x 48-64 KB in
+        // flight: ~76 B/clk per SM), halo 630 / 890 (tensor-pipe time + ~125 clk: its weight ring runs only a few K blocks ahead). The
+        // halo mode therefore wins where the plain mode is ring-bound (n_blk 64) and loses a little where it is MMA-bound (n_blk 128).
+        const double a_bytes = (terms == 1 ? 1.0 : 2.0) * rows_used * 128.0, b_bytes = (terms == 3 ? 2.0 : 1.0) * blk * 128;
         const double mma     = terms == 3 ? 4.0 * (mma_clk(2 * blk) + mma_clk(blk)) : 4.0 * terms * mma_clk(blk); // per 64-wide K block
-        const double kb_cost = std::max((a_bytes + b_bytes) / ingest, mma) + 60.0;
+        const double kb_cost = halo ? mma + 125.0 : std::max((a_bytes + b_bytes) / (ingest * 1.05), mma + 45.0);
         for (int sp = 1; sp <= ((no_split || halo) ? 1 : 4); ++sp) {
             if (sp > 1 && (num_kb < 8 * sp)) break; // not worth a reduction for short K
             const int kbps          = (num_kb + sp - 1) / sp;
