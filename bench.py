@@ -81,7 +81,20 @@ def layer_work(layers, shapes, batch):
         inb = sum(4.0 * a * b * c * d for (a, b, c, d) in ins) if t != "YOLO" else 0.0
         outb = 4.0 * n * oh * ow * oc if t != "YOLO" else 0.0
         work.append((t, flops, inb + outb + wbytes))
+        WRITE_BYTES[i] = outb
     return work
+
+
+# HBM bandwidth by direction, measured on this pool's B200 with tools/hbm_rw_probe.py (profiles/r02_hbm_rw.txt): the copy figure is
+# the roofline denominator of MEASURED_PEAKS.json; a write-dominated layer cannot beat the fill figure
+HBM_WRITE_GBS, HBM_READ_GBS = 3930.0, 6126.0
+WRITE_BYTES = {}
+
+
+def hbm_dir_floor(i, by, pk):
+    """max(total / copy bandwidth, written / write-only bandwidth, read / read-only bandwidth), seconds"""
+    wr = WRITE_BYTES.get(i, 0.0)
+    return max(by / (pk["hbm_gbs"] * 1e9), wr / (HBM_WRITE_GBS * 1e9), (by - wr) / (HBM_READ_GBS * 1e9))
 
 
 class ClockSampler:
@@ -348,8 +361,13 @@ def kernel_roofline(wl, work, pk, terms, step_ms, reps=5):
     roof["launches_per_step"] = dn
     roof["kernel_ms_per_step"] = dms
     roof["share_of_eager_step"] = dms / float(lt.sum())
+    tach = sum(max(hbm_dir_floor(i, by, pk), terms * fl / (peak_t * 1e12)) for i, ((t, fl, by), ms_l, kn) in enumerate(zip(work, lt, kernels))
+               if ms_l > 0 and kn.split("<")[0] == dom)
     roof["per_layer_roofline_frac"] = tmin / (dms * 1e-3)
     roof["per_layer_ceiling_frac"] = tceil / (dms * 1e-3)
+    roof["per_layer_achievable_frac"] = tach / (dms * 1e-3)
+    roof["achievable_note"] = "ceiling + direction-aware HBM floor: this GPU writes at most %.0f GB/s and reads %.0f GB/s alone (tools/hbm_rw_probe.py), %.0f only as a copy" % (
+        HBM_WRITE_GBS, HBM_READ_GBS, pk["hbm_gbs"])
     roof["ceiling_note"] = ("a product costs %d fp16 MMAs (snnb.h SNNB_PRECISION_*): the tensor-bound layers' ceiling is peak / %d; per_layer_ceiling_frac measures against "
                             "that achievable bound, per_layer_roofline_frac / frac against SURVEY 8d's algorithmic roofline" % (terms, terms))
     roof["algorithmic_per_step"] = {"flops": dfl, "bytes": dby}
@@ -387,14 +405,17 @@ def layer_table(desc, batch, work, lt, kernels, pk, terms, step_ms, out):
     out.write("# %s, batch %d per GPU; per-layer event pairs (eager pass). roofline%% = max(bytes/HBM, flops/peak) / t with the algorithmic work of SURVEY 8d (fp32\n"
               "# bytes, 2*MAC flops; peak = measured sustained dense fp16/bf16); ceiling%% = the same with flops x %d (a product is %d fp16 MMAs): the achievable bound\n"
               % (desc, batch, terms, terms))
-    out.write("# %-3s %-18s %-26s %8s %8s %8s %8s %8s %6s %9s %9s\n" % ("id", "layer", "kernel", "ms", "GFLOP", "MB", "TF/s", "GB/s", "bound", "roofline%", "ceiling%"))
+    out.write("# achievable%% = against max(ceiling, the direction-aware HBM floor: written bytes / %.0f GB/s write-only, read / %.0f read-only - tools/hbm_rw_probe.py)\n"
+              % (HBM_WRITE_GBS, HBM_READ_GBS))
+    out.write("# %-3s %-18s %-26s %8s %8s %8s %8s %8s %6s %9s %9s %11s\n" % ("id", "layer", "kernel", "ms", "GFLOP", "MB", "TF/s", "GB/s", "bound", "roofline%", "ceiling%",
+                                                                               "achievable%"))
     for i, ((t, fl, by), ms_l, kn) in enumerate(zip(work, lt, kernels)):
         if ms_l <= 0 or not kn:
             continue
         t_h, t_t = by / (pk["hbm_gbs"] * 1e9), fl / (pk["bf16_tflops_sustained"] * 1e12)
-        out.write("[%02d] %-18s %-26s %8.3f %8.2f %8.2f %8.1f %8.0f %6s %8.1f%% %8.1f%%\n" %
+        out.write("[%02d] %-18s %-26s %8.3f %8.2f %8.2f %8.1f %8.0f %6s %8.1f%% %8.1f%% %10.1f%%\n" %
                   (i, t, kn, ms_l, fl / 1e9, by / 1e6, fl / ms_l / 1e9, by / ms_l / 1e6, "tensor" if t_t > t_h else "hbm",
-                   100 * max(t_h, t_t) / (ms_l * 1e-3), 100 * max(t_h, terms * t_t) / (ms_l * 1e-3)))
+                   100 * max(t_h, t_t) / (ms_l * 1e-3), 100 * max(t_h, terms * t_t) / (ms_l * 1e-3), 100 * max(hbm_dir_floor(i, by, pk), terms * t_t) / (ms_l * 1e-3)))
     out.write("# total eager %.3f ms; CUDA-graph step %.3f ms\n" % (float(lt.sum()), step_ms))
 
 

@@ -520,6 +520,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const __grid_constant__ CUtensorMap tmR_lo64, const __grid_constant__ CUtensorMap tmR_hiT, const __grid_constant__ CUtensorMap tmR_loT,
                  const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr bool ONE_BLOCK = TERMS != 3 || SPLIT_EPI; // the accumulator is one column block of n_blk (else [hi.hi + lo.hi | hi.lo])
+    constexpr int EPI_TERMS  = ONE_BLOCK ? 2 : 3;       // what the epilogue templates need to know: one block or two
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
     // HALO: [A ring: HL_A_STAGES x (hi plane, lo plane)] [B ring: STAGES x 32 KB] [staging]; else [ring: STAGES x 64 KB] [staging]
     const uint32_t b_ring    = smem_base + (HALO ? HL_A_STAGES * HL_A_STAGE_BYTES : 0);
@@ -816,10 +818,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const uint64_t b_cat = a_hi + (2 * UM_A_BYTES >> 4); // rows [0, n_blk) = B_hi, [n_blk, 2 n_blk) = B_lo
                     // UMMA_K = 16 fp16 = 32 bytes: K step j advances the start address by 2 (x16 B)
                     const uint32_t first = kb > kb0 ? 1u : 0u;
+                    // ONE_BLOCK (short-K layers, 3-term): all three products go to the SAME accumulator block as separate N = n_blk MMAs
+                    // (12 instead of 8 per K block, A_hi fetched twice) - these layers run at the speed of their epilogue, not of the
+                    // tensor pipe, and this way the epilogue reads one TMEM block instead of two and adds nothing.
+                    const uint64_t b_lo = b_cat + (uint64_t) ((uint32_t) p.n_blk * 8u); // B_lo rows follow B_hi's (n_blk x 128 B)
                     // first K step | look-ahead test of the next stage (latency hidden behind the remaining MMAs) | the rest
                     if (!no_mma) {
-                        umma_f16(d_tmem, a_hi, b_cat, TERMS == 3 ? idesc_cat : idesc, first);
+                        umma_f16(d_tmem, a_hi, b_cat, (TERMS == 3 && !ONE_BLOCK) ? idesc_cat : idesc, first);
                         if (TERMS == 2) umma_f16(d_tmem, a_lo, b_cat, idesc, 1u);
+                        if (TERMS == 3 && ONE_BLOCK) umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
                     }
                     const int cur         = stage;
                     const uint32_t nphase = phase ^ (stage == STAGES - 1 ? 1u : 0u);
@@ -827,7 +834,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     phase                 = nphase;
                     ready                 = mbar_test_wait(full_bar(stage), phase); // non-blocking
                     if (!no_mma) {
-                        if (TERMS == 3) {
+                        if (TERMS == 3 && ONE_BLOCK) {
+#pragma unroll
+                            for (int j = 1; j < UM_BLOCK_K / 16; ++j) {
+                                umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc, 1u);
+                                umma_f16(d_tmem, a_hi + 2u * j, b_lo + 2u * j, idesc, 1u);
+                            }
+#pragma unroll
+                            for (int j = 0; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_lo + 2u * j, b_cat + 2u * j, idesc, 1u);
+                        } else if (TERMS == 3) {
 #pragma unroll
                             for (int j = 1; j < UM_BLOCK_K / 16; ++j) umma_f16(d_tmem, a_hi + 2u * j, b_cat + 2u * j, idesc_cat, 1u);
 #pragma unroll
@@ -892,7 +907,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
             if (p.ksplit > 1) {
                 float* tile_parts = p.partials + (size_t) tile * p.ksplit * (UM_BLOCK_M * p.n_blk);
-                epilogue_dump_partial<UM_EPI_WARPS, TERMS>(e, taddr, tile_parts + (size_t) split * (UM_BLOCK_M * p.n_blk), row, half, lane);
+                epilogue_dump_partial<UM_EPI_WARPS, EPI_TERMS>(e, taddr, tile_parts + (size_t) split * (UM_BLOCK_M * p.n_blk), row, half, lane);
                 __threadfence(); // partial tile visible device-wide before the arrival is counted
                 named_bar_sync(1, UM_EPI_WARPS * 32);
                 if (warp == 2 && lane == 0) {
@@ -910,9 +925,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             }
             if (SPLIT_EPI)
-                epilogue_tile<UM_EPI_WARPS / 2, TERMS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, 0, leader, lane, res_phase);
+                epilogue_tile<UM_EPI_WARPS / 2, EPI_TERMS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, 0, leader, lane, res_phase);
             else
-                epilogue_tile<UM_EPI_WARPS, TERMS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, leader, lane, res_phase);
+                epilogue_tile<UM_EPI_WARPS, EPI_TERMS>(e, taddr, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, row, half, leader, lane, res_phase);
             e.part_src = nullptr;
             if (leader) UM_TRACE(4, it);
         }
