@@ -628,12 +628,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     }
                 }
                 if (work >= total_work) break;
-                int next = 0; // drawn now, needed only after this item's loads are issued: the atomic's latency is hidden
-                if (elect_one()) {
-                    const int c = atomicAdd(p.sched_counter, 1);
-                    next        = (int) gridDim.x + c;
-                    if (c == draws_total - 1) *p.sched_counter = 0; // the very last draw of the launch: ready for the next one
-                }
+                // The next work item is drawn NOW but its result is not touched until this item's loads are issued: 148 CTAs hit the same
+                // counter at kernel start (a ~1.3 k clk round trip). r01 tested the result right away (`if (c == last) reset`), which put that
+                // round trip in front of every item's first load - the producer's whole run-ahead margin (r02 trace: first load 2.3-5.4 k clk
+                // after kernel entry, ~1.3 k clk of bubble at every tile boundary).
+                int drawn = 0;
+                if (elect_one()) drawn = atomicAdd(p.sched_counter, 1);
+                auto take_next = [&]() { // consumes the draw: next work id for all lanes; the launch's last draw re-zeroes the counter
+                    const int c = __shfl_sync(0xffffffffu, drawn, 0); // elect.sync picks lane 0 of the converged warp
+                    if (lane == 0 && c == draws_total - 1) *p.sched_counter = 0;
+                    return (int) gridDim.x + c;
+                };
                 const int tile = work % total_tiles, split = work / total_tiles;
                 const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
@@ -674,7 +679,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                 if (cb + 1 < cbs) {
                                     issue_halo(work, cb + 1);
                                 } else {
-                                    nwork = __shfl_sync(0xffffffffu, next, 0);
+                                    nwork = take_next();
                                     if (nwork < total_work) issue_halo(nwork, 0);
                                 }
                             }
@@ -722,7 +727,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (++kx == ks) kx = 0, ++ky;
                     }
                 }
-                work = __shfl_sync(0xffffffffu, next, 0); // elect.sync picks lane 0 of the converged warp
+                work = take_next();
             }
         }
     } else if (warp == 1) {
