@@ -589,7 +589,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    pdl_wait(); // everything above (barriers, TMEM, tensor-map prefetch) overlapped with the previous kernel's tail
+    // The WEIGHTS of this CTA's first work item do not depend on the previous kernel: their loads go out before the dependency wait
+    // (plain mode: the first K block's; halo mode: the first three taps'), so only the activations' latency is left after it.
+    const int pre_total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
+    const bool pre_b          = (p.ablate & 2) == 0 && (int) blockIdx.x < pre_total_tiles * p.ksplit;
+    if (warp == 0 && pre_b && elect_one()) {
+        const int tile = (int) blockIdx.x % pre_total_tiles, split = (int) blockIdx.x / pre_total_tiles;
+        const int oc0  = (tile / (p.tiles_x * p.tiles_y * p.tiles_n)) * p.n_blk;
+        const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u;
+        if (HALO) {
+            for (int tap = 0; tap < 3; ++tap) {
+                const uint32_t sB = b_ring + tap * p.b_stage_bytes, fb = full_bar(tap);
+                mbar_expect_tx(fb, (TERMS == 3 ? 2u : 1u) * (uint32_t) p.n_blk * 128u);
+                tma_load_2d(sB, &tmB_hi, fb, tap * p.ICp, oc0);
+                if (TERMS == 3) tma_load_2d(sB + b_lo_off, &tmB_lo, fb, tap * p.ICp, oc0);
+            }
+        } else {
+            const int kb0 = split * p.kb_per_split, cb = kb0 % p.cblocks, tap0 = kb0 / p.cblocks;
+            const uint32_t fb = full_bar(0);
+            mbar_expect_tx(fb, (TERMS == 1 ? 1u : 2u) * (uint32_t) p.rows_used * 128u + (TERMS == 3 ? 2u : 1u) * (uint32_t) p.n_blk * 128u);
+            tma_load_2d(smem_base + 2 * UM_A_BYTES, &tmB_hi, fb, tap0 * p.ICp + cb * UM_BLOCK_K, oc0);
+            if (TERMS == 3) tma_load_2d(smem_base + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, tap0 * p.ICp + cb * UM_BLOCK_K, oc0);
+        }
+    }
+    pdl_wait(); // everything above (barriers, TMEM, tensor-map prefetch, first weights) overlapped with the previous kernel's tail
     if (warp == 0) UM_TRACE(5, 0); // kernel entry (after the dependency wait)
     if (p.trace && threadIdx.x == 0) { // wall-clock (ns) envelope over ALL CTAs: [5][8] = earliest entry, [5][9] = latest exit, [5][10..11] CTA 0's own
         unsigned long long g;
@@ -686,7 +709,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             UM_TRACE(0, tr);
                             ++tr;
-                            if (elect_one()) {
+                            if (seq == 0 && cb == 0 && tap < 3 && pre_b) {
+                                // this CTA's first three weight stages went out before the dependency wait
+                            } else if (elect_one()) {
                                 const uint32_t sB = b_ring + stage * p.b_stage_bytes, fb = full_bar(stage);
                                 if (skip_tma) {
                                     mbar_arrive(fb);
@@ -714,11 +739,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (skip_tma) {
                             mbar_arrive(fb);
                         } else {
-                            mbar_expect_tx(fb, tx_bytes);
+                            const bool pre = seq == 0 && kb == kb0 && pre_b; // expect_tx + the weights went out before the dependency wait
+                            if (!pre) mbar_expect_tx(fb, tx_bytes);
                             tma_load_4d(sA, &tmA_hi, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
                             if (TERMS >= 2) tma_load_4d(sA + UM_A_BYTES, &tmA_lo, fb, cb * UM_BLOCK_K, ix0 + kx, iy0 + ky, n0);
-                            tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, fb, wk + cb * UM_BLOCK_K, oc0);
-                            if (TERMS == 3) tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
+                            if (!pre) {
+                                tma_load_2d(sA + 2 * UM_A_BYTES, &tmB_hi, fb, wk + cb * UM_BLOCK_K, oc0);
+                                if (TERMS == 3) tma_load_2d(sA + 2 * UM_A_BYTES + b_lo_off, &tmB_lo, fb, wk + cb * UM_BLOCK_K, oc0);
+                            }
                         }
                     }
                     if (++stage == STAGES) stage = 0, phase ^= 1u;
