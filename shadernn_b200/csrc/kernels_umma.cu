@@ -1021,6 +1021,7 @@ struct RowWinParams {
     int act;
     float alpha;
     long long* trace; // profiling aid, see UmmaParams
+    int ablate;       // profiling aid (SNNB_UMMA_ABLATE, results WRONG when set): 2 skip the activation loads, 1 skip the epilogue work
 };
 
 // SWIZZLE_NONE K-major descriptor with an overlapping K stride: LBO = 16 B (next chunk = next pixel), SBO = 128 B
@@ -1108,12 +1109,16 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     if (elect_one()) {
                         const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
-                        mbar_expect_tx(full_bar(stage), tx_bytes);
-                        tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
-                        if (TERMS >= 2) tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
-                        if (p.parities == 2) {
-                            tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
-                            if (TERMS >= 2) tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                        if (p.ablate & 2) {
+                            mbar_arrive(full_bar(stage));
+                        } else {
+                            mbar_expect_tx(full_bar(stage), tx_bytes);
+                            tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                            if (TERMS >= 2) tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                            if (p.parities == 2) {
+                                tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                                if (TERMS >= 2) tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                            }
                         }
                     }
                     __syncwarp();
@@ -1429,6 +1434,8 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     p.ksteps   = rp.ksteps, p.panels = (rp.ksteps + 3) / 4;
     for (int q = 0; q < 8; ++q) p.ks_parity[q] = q < rp.ksteps ? rp.ks_parity[q] : 0, p.ks_erel[q] = q < rp.ksteps ? rp.ks_erel[q] : 0;
     p.act = a.act, p.alpha = a.alpha;
+    static const int rw_ablate = getenv("SNNB_UMMA_ABLATE") ? atoi(getenv("SNNB_UMMA_ABLATE")) : 0;
+    p.ablate                   = rw_ablate;
 
     // A: per plane and column parity a 4-D view (8 ch | de-interleaved pixel index | row | image) of the NHWC plane
     CUtensorMap tmA[4], tmB[2];

@@ -160,6 +160,64 @@ __global__ void __launch_bounds__(64, 1) bench3(int n, int kblocks, long long* o
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
+// The row-window kernel's stage (stems: IC <= 8): the A operand is read through a SWIZZLE_NONE K-major descriptor whose K-chunk stride
+// (LBO) is 16 B - chunk j of row m is pixel m + j of a dense pixel row. `ksteps` K steps per stage (7x7 stride 2: 4), each
+// A_hi x [B_hi;B_lo] (N = 2n) + A_lo x B_hi (N = n); B panels are SWIZZLE_128B as in the kernel. Is this operand form as fast as the swizzled one?
+__global__ void __launch_bounds__(64, 1) bench_window(int n, int ksteps, int stages, int swizzled_a, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bars[9];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 9; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < (200 * 1024) / 4; i += blockDim.x) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4u * i), "r"(0));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = slot;
+    if (warp == 1) {
+        // window descriptor: LBO 16 B, SBO 128 B, version 1, layout type 0 (no swizzle); or the canonical swizzled one for comparison
+        const uint64_t a_hi0 = swizzled_a ? make_desc(base, 1024) : ((uint64_t) ((base >> 4) & 0x3FFFu) | (1ull << 16) | (8ull << 32) | (1ull << 46));
+        const uint64_t a_lo0 = a_hi0 + (4608u >> 4);
+        const uint64_t b     = make_desc(base + 49152, 1024);
+        const uint32_t id_cat = make_idesc(128, 2 * n), id = make_idesc(128, n);
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+        if (pred) {
+            const long long t0 = clock64();
+            for (int st = 0; st < stages; ++st) {
+                for (int q = 0; q < ksteps; ++q) {
+                    const uint32_t ao = swizzled_a ? 2u * (q & 3) : 2u * q; // window: next K step = 2 pixels further; swizzled: +32 B
+                    mma(tmem, a_hi0 + ao, b + 2u * (q & 3), id_cat, 1u);
+                    mma(tmem, a_lo0 + ao, b + 2u * (q & 3), id, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[st & 7])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[8])) : "memory");
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bars[8])) : "memory");
+            const long long t1 = clock64();
+            if (blockIdx.x == 0) out[0] = t1 - t0;
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
 template <int ORDER, int FENCE, int WAIT> static void run3(long long* d) {
     cudaFuncSetAttribute(bench3<ORDER, FENCE, WAIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
     for (int n : {64, 128}) {
@@ -194,6 +252,16 @@ int main() {
                 printf("terms %d n_blk %3d %-6s: %7.1f clk per K block   (math floor %5.0f, %.0f%% of it)\n", terms, n, halo ? "halo" : "plain", (double) c / kblocks, ideal,
                        100.0 * ideal * kblocks / (double) c);
             }
+        }
+    cudaFuncSetAttribute(bench_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+    for (int sw : {1, 0})
+        for (int n : {64, 32, 16}) {
+            bench_window<<<148, 64, 202 * 1024>>>(n, 4, 900, sw, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long c = -1;
+            if (e == cudaSuccess) cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+            printf("row-window stage, 4 K steps, 3-term, n_blk %2d, A operand %s: %7.1f clk per stage (math floor %4.0f)%s\n", n,
+                   sw ? "SWIZZLE_128B (canonical)       " : "SWIZZLE_NONE window (LBO 16 B) ", (double) c / 900, 4.0 * 3 * 128 * n * 16 / 4096.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
     run3<0, 0, 0>(d);
     run3<1, 0, 0>(d);
