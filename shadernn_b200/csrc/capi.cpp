@@ -61,6 +61,19 @@ int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** ou
     return 0;
 }
 
+// The compact 4-channel copy a stride-2 RGB stem reads (snnb_tensor::feed_*): zeroed once, the input kernels only ever write
+// the image area, so the margins stay the constant padding.
+int tensor_alloc_feed(snnb_tensor* t, int feed_h, int feed_w, int py, int px) {
+    SNNB_REQUIRE(t && !t->feed_hi && t->c <= 4 && feed_h >= t->h + py && feed_w >= t->w + px && (feed_w & 1) == 0 && (px & 1) == 0, "tensor_alloc_feed: bad argument");
+    const size_t plane  = ((size_t) t->n * feed_h * feed_w * 4 + 63) / 64 * 64;
+    const size_t planes = t->lo ? 2 : 1;
+    SNNB_CUDA_OK(cudaMalloc(&t->feed_hi, plane * planes * sizeof(__half)));
+    SNNB_CUDA_OK(cudaMemsetAsync(t->feed_hi, 0, plane * planes * sizeof(__half), t->ctx->stream));
+    t->feed_lo = t->lo ? t->feed_hi + plane : nullptr;
+    t->feed_h = feed_h, t->feed_w = feed_w, t->feed_py = py, t->feed_px = px;
+    return 0;
+}
+
 } // namespace snnb
 
 using namespace snnb;
@@ -123,6 +136,7 @@ int snnb_tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor
 int snnb_tensor_free(snnb_tensor* t) {
     if (!t) return 0;
     if (t->owns && t->hi) cudaFree(t->hi);
+    if (t->feed_hi) cudaFree(t->feed_hi);
     delete t;
     return 0;
 }

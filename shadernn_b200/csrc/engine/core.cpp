@@ -215,6 +215,30 @@ bool MixedInferenceCore::init(std::string& err) {
                 }
                 ownedTensors.push_back(cl->prepadded);
             }
+            // a stride-2 RGB stem fed straight by a model input: give that input tensor the compact 4-channel copy (feed mode)
+            {
+                static const bool noFeed = getenv("SNNB_NO_FEED") != nullptr;
+                GenericModelLayer* src   = resolve(L->prevLayers[0]);
+                snnb_tensor* in          = L->inputs[0];
+                const int mode           = padModeId(cl->_desc.padding.mode);
+                uint32_t offs[4];
+                cl->_desc.padding.offsets((int) cl->_desc.kernelSize, true, offs);
+                const int k = (int) cl->_desc.kernelSize, padX = (int) offs[0], padY = (int) offs[2];
+                FeedPlan fp;
+                if (!noFeed && !prepad && src->isInputLayer && !in->feed_hi && options.convAlgo != SNNB_ALGO_SIMT && !L->residual && L->output->c <= 64 &&
+                    (mode == SNNB_PAD_NONE || mode == SNNB_PAD_CONSTANT) && make_feed_plan(k, (int) cl->_desc.stride, padX, in->c, fp)) {
+                    const int tilesX = (L->output->w + 127) / 128;
+                    const int needW  = 2 * (tilesX * 128 - 1) + 2 * fp.nch;          // last pixel a tile's window segment touches + 1
+                    const int needH  = 2 * (L->output->h - 1) + k - padY + padY;      // last input row + 1, shifted by feed_py = padY
+                    const int feedW  = (std::max(in->w + fp.px, needW) + 1) & ~1;
+                    const int feedH  = std::max(in->h + padY, needH);
+                    if (tensor_alloc_feed(in, feedH, feedW, padY, fp.px)) {
+                        err = get_error();
+                        return false;
+                    }
+                    cl->feedInput = true;
+                }
+            }
         }
         if (L->typeName == "Dense") {
             auto* dl = static_cast<DenseLayer*>(L);
@@ -384,9 +408,21 @@ bool MixedInferenceCore::init(std::string& err) {
 int MixedInferenceCore::enqueueForward(bool) {
     ExecOptions eo;
     eo.convAlgo = options.convAlgo, eo.precision = options.precision;
+    // SNNB_SYNC_LAYERS: debugging aid - wait for every layer and name the one whose kernel faulted (eager passes only)
+    static const bool syncLayers = getenv("SNNB_SYNC_LAYERS") != nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (syncLayers) cudaStreamIsCapturing(ctx->stream, &cap);
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
     for (auto* L : graph.sorted) {
         if (L->fusedAway || L->isInputLayer || L->typeName == "YOLO") continue;
         if (int rc = L->run(ctx, eo)) return rc;
+        if (syncLayers && !capturing) {
+            const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                set_error("%s (%s): %s", L->name.c_str(), ctx->last_kernel ? ctx->last_kernel : "?", cudaGetErrorString(e));
+                return 1;
+            }
+        }
     }
     return 0;
 }

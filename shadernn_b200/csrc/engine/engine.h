@@ -59,6 +59,7 @@ private:
 
 // Padding spec as the parser leaves it: four strings, either all digits or a keyword ("same"/"valid"/"none")
 // (modelparser.cpp:584-609), plus the conv "mode".
+int padModeId(const std::string& mode); // SNNB_PAD_* of a padding mode string (conv2dVulkan.cpp:73-80)
 struct PaddingSpec {
     std::string t = "valid", b = "valid", l = "valid", r = "valid";
     std::string mode; // "constant" | "replicate" | "reflect" | "" (unset)
@@ -171,6 +172,9 @@ public:
     // Replicate / reflect padding on the tensor path: the TMA unit can only zero-fill, so the engine materialises the
     // padded input once (pad kernel, vk_pad.comp semantics) and runs the tcgen05 kernel over it with zero padding.
     snnb_tensor* prepadded = nullptr;
+    // Stride-2 stem with <= 4 input channels reading a model input: the input tensor carries a compact 4-channel copy
+    // (snnb_tensor::feed_hi) and the weights get the matching K order (FeedPlan, kernels_umma.cu conv_rowwin_kernel feed mode).
+    bool feedInput = false;
     bool wantsPrepad(const snnb_tensor* in, const snnb_tensor* out, int convAlgo, int& ph, int& pw) const;
     Transform getOutputScaleDimAdjustment() const override; // conv2d.cpp:102-113
     void getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const override;

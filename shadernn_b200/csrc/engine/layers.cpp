@@ -56,7 +56,7 @@ void Conv2DLayer::getOutputDims(uint32_t& w, uint32_t& h, uint32_t& d) const { /
     GenericModelLayer::getOutputDims(w, h, d);
     d = numOutputPlanes;
 }
-static int padModeId(const std::string& m) { // conv2dVulkan.cpp:73-80
+int padModeId(const std::string& m) { // conv2dVulkan.cpp:73-80
     if (m == "constant") return SNNB_PAD_CONSTANT;
     if (m == "replicate") return SNNB_PAD_REPLICATE;
     if (m == "reflect") return SNNB_PAD_REFLECT;
@@ -77,8 +77,12 @@ void Conv2DLayer::packWeights(PackedHost& p) {
         _desc.padding.offsets((int) _desc.kernelSize, true, offs);
         const int mode = padModeId(_desc.padding.mode);
         // reflect / replicate convolutions run on a pre-padded copy of the input with pad 0 (wantsPrepad)
-        if (mode == SNNB_PAD_NONE || mode == SNNB_PAD_CONSTANT) pack_rowwin_host(p, (int) _desc.stride, _desc.kernelSize == 1 ? 0 : (int) offs[0]);
-        else pack_rowwin_host(p, (int) _desc.stride, 0);
+        if (mode == SNNB_PAD_NONE || mode == SNNB_PAD_CONSTANT) {
+            pack_rowwin_host(p, (int) _desc.stride, _desc.kernelSize == 1 ? 0 : (int) offs[0]);
+            if (feedInput) pack_feed_host(p, (int) _desc.stride, _desc.kernelSize == 1 ? 0 : (int) offs[0]);
+        } else {
+            pack_rowwin_host(p, (int) _desc.stride, 0);
+        }
     }
     std::vector<float>().swap(_desc.weights); // host copy no longer needed
 }

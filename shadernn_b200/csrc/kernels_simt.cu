@@ -59,6 +59,23 @@ __device__ __forceinline__ void store8(__half* __restrict__ hi, __half* __restri
     if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
 }
 
+struct FeedV { // the compact 4-channel copy of a model input (snnb_tensor::feed_hi), or hi == nullptr
+    __half* hi;
+    __half* lo;
+    int H, W, py, px;
+};
+// channels 0..3 of image pixel `pix` (linear n, y, x index of a tensor H x W) into the stem feed (C <= 4: one thread per pixel)
+__device__ __forceinline__ void store_feed(const FeedV& f, size_t pix, int H, int W, const float v[8]) {
+    const int x = (int) (pix % W), y = (int) ((pix / W) % H);
+    const size_t n = pix / ((size_t) W * H);
+    const size_t off = ((n * f.H + y + f.py) * f.W + x + f.px) * 4;
+    uint2 h, l;
+    split2(v[0], v[1], h.x, l.x);
+    split2(v[2], v[3], h.y, l.y);
+    *reinterpret_cast<uint2*>(f.hi + off) = h;
+    if (f.lo) *reinterpret_cast<uint2*>(f.lo + off) = l;
+}
+
 __device__ __forceinline__ float load1(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off) {
     return __half2float(hi[off]) + (lo ? __half2float(lo[off]) : 0.0f);
 }
@@ -104,6 +121,7 @@ struct TV { // kernel-side tensor view
     int N, H, W, C, Cp;
 };
 static TV view(const snnb_tensor* t) { return TV {t->hi, t->lo, t->n, t->h, t->w, t->c, t->cp}; }
+static FeedV feed_view(const snnb_tensor* t) { return FeedV {t->feed_hi, t->feed_lo, t->feed_h, t->feed_w, t->feed_py, t->feed_px}; }
 
 #define SNNB_LAUNCH_CHECK(ctx)                                                                          \
     do {                                                                                                \
@@ -1061,7 +1079,7 @@ int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, 
 // ------------------------------------------------------------------------------------------------------------
 // API edge: fp32 NHWC (dense pitch C) <-> split-fp16 (pitch Cp).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void split_kernel(const float* __restrict__ src, TV t) {
+__global__ void split_kernel(const float* __restrict__ src, TV t, FeedV f) {
     pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1073,13 +1091,14 @@ __global__ void split_kernel(const float* __restrict__ src, TV t) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? __ldg(src + px * t.C + c + j) : 0.0f;
     store8(t.hi, t.lo, gid * 8, v);
+    if (f.hi) store_feed(f, px, t.H, t.W, v);
 }
 // u8 image (dense pitch C) -> (x - mean[c]) * norm[c] -> split-fp16: the reference's convertToRGBA32FAndNormalize
 // (core/inc/snn/imageTexture.h:114) done on the device, so only a quarter of the fp32 bytes cross PCIe.
 struct U8Norm {
     float mean[4], norm[4];
 };
-__global__ void split_u8_kernel(const uint8_t* __restrict__ src, TV t, U8Norm q) {
+__global__ void split_u8_kernel(const uint8_t* __restrict__ src, TV t, U8Norm q, FeedV f) {
     pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1091,6 +1110,7 @@ __global__ void split_u8_kernel(const uint8_t* __restrict__ src, TV t, U8Norm q)
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? ((float) __ldg(src + px * t.C + c + j) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3] : 0.0f;
     store8(t.hi, t.lo, gid * 8, v);
+    if (f.hi) store_feed(f, px, t.H, t.W, v);
 }
 __global__ void merge_kernel(TV t, float* __restrict__ dst) {
     pdl_wait();
@@ -1107,21 +1127,21 @@ __global__ void merge_kernel(TV t, float* __restrict__ dst) {
         if (c + j < t.C) dst[px * t.C + c + j] = v[j];
 }
 int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t) {
-    launch_k(split_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc, view(t));
+    launch_k(split_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc, view(t), feed_view(t));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 int launch_split_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, snnb_tensor* t, const float mean[4], const float norm[4]) {
     U8Norm q;
     for (int i = 0; i < 4; ++i) q.mean[i] = mean[i], q.norm[i] = norm[i];
-    launch_k(split_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc_u8, view(t), q);
+    launch_k(split_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc_u8, view(t), q, feed_view(t));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }
 // u8 image of ANOTHER size -> resize (linear or nearest) -> (x - mean[c]) * norm[c] -> split-fp16: ImageTexture::resize
 // (core/inc/snn/imageTexture.h:137) = shadertemplate_vk_resize.comp:42-61: the output texel centre (x + 0.5) / outW is sampled from
 // the source texture with the sampler's filter (texel centres at (i + 0.5) / inW, clamp to edge), then normalised.
-__global__ void resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, TV t, U8Norm q, int linear) {
+__global__ void resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, TV t, U8Norm q, int linear, FeedV f) {
     pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1156,11 +1176,12 @@ __global__ void resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw
         for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? ((float) __ldg(img + ((size_t) y0 * sw + x0) * t.C + c + j) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3] : 0.0f;
     }
     store8(t.hi, t.lo, gid * 8, v);
+    if (f.hi) store_feed(f, px, t.H, t.W, v);
 }
 int launch_resize_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, int src_h, int src_w, snnb_tensor* t, const float mean[4], const float norm[4], bool linear) {
     U8Norm q;
     for (int i = 0; i < 4; ++i) q.mean[i] = mean[i], q.norm[i] = norm[i];
-    launch_k(resize_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc_u8, src_h, src_w, view(t), q, linear ? 1 : 0);
+    launch_k(resize_u8_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, dev_nhwc_u8, src_h, src_w, view(t), q, linear ? 1 : 0, feed_view(t));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -134,7 +134,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {
-            printf("conv_umma_kernel: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            uint32_t dyn;
+            asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+            printf("tcgen05 kernel (dynamic smem %u B): mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", dyn, blockIdx.x, threadIdx.x, bar, parity);
             __trap();
         }
     }
@@ -195,6 +197,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, completion on an mbarrier; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -272,6 +278,7 @@ struct EpiArgs {
     int part_splits;
     long long* trace; // profiling aid: leader warp stamps the phases of its first slabs into [4][64 + 8 * slab_seq ...]
     int trace_seq;
+    bool no_store = false; // profiling aid (SNNB_UMMA_ABLATE & 8, row-window kernel): everything but the TMA store of the tile
 };
 
 // Fused residual (Conv2D -> Add): TMA box load of the residual tile's slab into the staging buffer. The previous bulk store
@@ -452,7 +459,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
         named_bar_sync(e.bar_id, NWARPS * 32);
         EPI_STAMP(6); // bar B
         if (leader) {
-            if (elect_one()) {
+            if (!e.no_store && elect_one()) {
                 tma_store_4d(sw ? e.o_hi64 : e.o_hiT, e.stg, slab_oc, c1, c2, c3);
                 if (e.has_lo) tma_store_4d(sw ? e.o_lo64 : e.o_loT, e.stg + UM_BLOCK_M * 128, slab_oc, c1, c2, c3);
                 bulk_commit();
@@ -999,15 +1006,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // gathered 16-byte requests. The weight panel [kh][n_blk][64] (hi + lo, K columns in RowPlan order) is loaded once per
 // persistent CTA and stays resident. Tiles = up to 128 consecutive output pixels of one output row.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RW_STAGES        = 5;
+constexpr int RW_MAX_STAGES    = 16;                           // ring depth is chosen per launch: whatever shared memory is left, see RowWinParams::stages
 constexpr int RW_EPI_WARPS     = 8;
 constexpr int RW_THREADS       = 64 + 32 * RW_EPI_WARPS;
 constexpr int RW_MAX_N         = 64;
 constexpr int RW_BOXW          = 144;                          // 128 tile pixels + up to 8 of window overhang, padded
 constexpr int RW_ARR_BYTES     = RW_BOXW * 16;                 // one (plane, parity) pixel row segment
-constexpr int RW_STAGE_BYTES   = 4 * RW_ARR_BYTES;             // hi/lo x parity 0/1 = 9216 B
-constexpr int RW_B_BYTES       = 144 * 1024;                   // resident weight panels: [ky][panel][B_hi rows ; B_lo rows] x 128 B
-constexpr int RW_SMEM_BYTES    = RW_B_BYTES + RW_STAGES * RW_STAGE_BYTES + UM_STG_BYTES + 1024 + 256;
+constexpr int RW_SMEM_BYTES    = 227 * 1024;                   // everything: resident weight panels | epilogue staging | A ring | barriers
+constexpr int RW_BAR_BYTES     = 512;
+constexpr int RW_B_MAX_BYTES   = RW_SMEM_BYTES - 1024 - RW_BAR_BYTES - UM_STG_BYTES - 4 * 4 * RW_ARR_BYTES; // weights must leave room for >= 4 stages
 
 struct RowWinParams {
     __half* out_hi;
@@ -1021,14 +1028,30 @@ struct RowWinParams {
     int act;
     float alpha;
     long long* trace; // profiling aid, see UmmaParams
-    int ablate;       // profiling aid (SNNB_UMMA_ABLATE, results WRONG when set): 2 skip the activation loads, 1 skip the epilogue work
+    int ablate;       // profiling aid (SNNB_UMMA_ABLATE, results WRONG when set): 1 skip the epilogue work, 2 the activation loads, 4 the MMAs, 8 the TMA stores
+    // FEED mode (stride 2, <= 4 input channels; FeedPlan in snnb_internal.h): the A rows come from the input tensor's compact
+    // 4-channel copy, one contiguous segment per plane and filter row (a plain bulk copy, the margins are real zeros)
+    const __half* feed_hi;
+    const __half* feed_lo;
+    int feed_h, feed_w, feed_py;
+    uint32_t feed_seg_bytes; // 0 = not in feed mode
+    // shared-memory carve-up (host-computed): the weight panels take b_bytes (multiple of 1024), the ring gets `stages` stages of
+    // stage_bytes = planes x parities x RW_ARR_BYTES; the lo plane's arrays follow the hi plane's at lo_off. The ring is as deep as
+    // shared memory allows: a stage is only ~2-9 KB, and the cycle load -> MMA -> commit -> producer wake-up is ~2.5 k clk long, so a
+    // 5-deep ring ran the 7x7 stem at one stage per ~560 clk whatever the stage's own work was (profiles/r02_stem_ablation.txt).
+    int stages;
+    uint32_t stage_bytes, lo_off, b_bytes;
 };
 
 // SWIZZLE_NONE K-major descriptor with an overlapping K stride: LBO = 16 B (next chunk = next pixel), SBO = 128 B
 // (8 rows x 16 B), version 1, layout type 0.
 __device__ __forceinline__ uint64_t make_window_desc(uint32_t saddr) { return (uint64_t) ((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (8ull << 32) | (1ull << 46); }
 
-template <int TERMS> // see conv_umma_kernel
+// FKS > 0: FEED mode with FKS K steps per filter row (see RowWinParams::feed_hi). Its producer and MMA-issue loops are written out
+// separately and kept to a few dozen instructions per stage: both run in ONE thread, a stage of the 7x7 stem holds only four MMAs
+// (224 clk of tensor time), and the generic loops below cost ~290 SASS instructions = ~400 clk per stage whatever the stage's work
+// was (profiles/r02_stem_ablation.txt: with loads, MMAs and epilogue all ablated the kernel still took 48 of its 75 us).
+template <int TERMS, int FKS> // TERMS: see conv_umma_kernel
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_constant__ CUtensorMap tmA_hi1, const __grid_constant__ CUtensorMap tmA_lo0,
                    const __grid_constant__ CUtensorMap tmA_lo1, const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -1036,15 +1059,16 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB = smem_base; // weight panel: per kernel row ky, [n_blk rows of B_hi ; n_blk rows of B_lo] x 128 B
-    const uint32_t stg      = smem_base + RW_B_BYTES; // epilogue staging (1024-aligned)
+    const uint32_t stg      = smem_base + p.b_bytes; // epilogue staging (1024-aligned)
     const uint32_t sA0      = stg + UM_STG_BYTES;
-    const uint32_t bar_base = sA0 + RW_STAGES * RW_STAGE_BYTES;
+    const uint32_t bar_base = sA0 + (uint32_t) p.stages * p.stage_bytes;
+    const int RW_STAGES     = p.stages;
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar      = [&](int s) { return bar_base + 8u * (RW_STAGES + s); };
-    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * RW_STAGES + a); };
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * RW_STAGES + 2 + a); };
-    const uint32_t b_bar     = bar_base + 8u * (2 * RW_STAGES + 4);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * RW_STAGES + 5);
+    auto empty_bar      = [&](int s) { return bar_base + 8u * (RW_MAX_STAGES + s); };
+    auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (2 * RW_MAX_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * RW_MAX_STAGES + 2 + a); };
+    const uint32_t b_bar     = bar_base + 8u * (2 * RW_MAX_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * RW_MAX_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
@@ -1100,7 +1124,39 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             // activation row segments
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (TERMS == 1 ? 1u : 2u) * (uint32_t) p.parities * RW_ARR_BYTES;
+            const uint32_t tx_bytes = (TERMS == 1 ? 1u : 2u) * (p.feed_seg_bytes ? p.feed_seg_bytes : (uint32_t) p.parities * RW_ARR_BYTES);
+            if constexpr (FKS > 0) {
+                // one contiguous segment per plane and filter row; running pointers, no per-stage address arithmetic
+                const uint32_t seg  = p.feed_seg_bytes;
+                const size_t pitch  = (size_t) p.feed_w * 4; // fp16 elements per feed row
+                const int per_image = p.OH * p.tiles_x;
+                int rem = (int) blockIdx.x % per_image, n = (int) blockIdx.x / per_image;
+                uint32_t sA = sA0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int oy = p.tiles_x == 1 ? rem : rem / p.tiles_x, xt = p.tiles_x == 1 ? 0 : rem % p.tiles_x;
+                    const size_t off = (((size_t) n * p.feed_h + (oy * 2 - p.pad_y + p.feed_py)) * p.feed_w + 2 * xt * UM_BLOCK_M) * 4;
+                    const __half* src_hi = p.feed_hi + off;
+                    const __half* src_lo = p.feed_lo + off;
+                    for (int ky = 0; ky < p.kh; ++ky) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        if (elect_one()) {
+                            if (p.ablate & 2) {
+                                mbar_arrive(full_bar(stage));
+                            } else {
+                                mbar_expect_tx(full_bar(stage), tx_bytes);
+                                bulk_load_1d(sA, src_hi, seg, full_bar(stage));
+                                if (TERMS >= 2) bulk_load_1d(sA + RW_ARR_BYTES, src_lo, seg, full_bar(stage));
+                            }
+                        }
+                        __syncwarp();
+                        src_hi += pitch, src_lo += pitch;
+                        sA += p.stage_bytes;
+                        if (++stage == RW_STAGES) stage = 0, phase ^= 1u, sA = sA0;
+                    }
+                    rem += (int) gridDim.x;
+                    while (rem >= per_image) rem -= per_image, ++n;
+                }
+            } else
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int xt = tile % p.tiles_x, oy = (tile / p.tiles_x) % p.OH, n = tile / (p.tiles_x * p.OH);
                 const int ox0 = xt * UM_BLOCK_M;
@@ -1108,16 +1164,16 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     const int iy = oy * p.stride - p.pad_y + ky; // out of range -> the whole row is zero-filled
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     if (elect_one()) {
-                        const uint32_t sA = sA0 + stage * RW_STAGE_BYTES;
+                        const uint32_t sA = sA0 + stage * p.stage_bytes;
                         if (p.ablate & 2) {
                             mbar_arrive(full_bar(stage));
                         } else {
                             mbar_expect_tx(full_bar(stage), tx_bytes);
                             tma_load_4d(sA, &tmA_hi0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
-                            if (TERMS >= 2) tma_load_4d(sA + 2 * RW_ARR_BYTES, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
+                            if (TERMS >= 2) tma_load_4d(sA + p.lo_off, &tmA_lo0, full_bar(stage), 0, ox0 + p.dmin[0], iy, n);
                             if (p.parities == 2) {
                                 tma_load_4d(sA + RW_ARR_BYTES, &tmA_hi1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
-                                if (TERMS >= 2) tma_load_4d(sA + 3 * RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
+                                if (TERMS >= 2) tma_load_4d(sA + p.lo_off + RW_ARR_BYTES, &tmA_lo1, full_bar(stage), 0, ox0 + p.dmin[1], iy, n);
                             }
                         }
                     }
@@ -1144,6 +1200,49 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             int stage = 0, it = 0, tr = 0;
             uint32_t phase = 0;
             bool ready     = false;
+            const bool no_mma = (p.ablate & 4) != 0;
+            const uint64_t lo_off16 = (uint64_t) (p.lo_off >> 4);
+            if constexpr (FKS > 0) {
+                // FEED mode: K step q of a stage = window start + 2 q pixels pairs (32 B), weights columns 16 q ..; everything a constant offset
+                constexpr uint32_t LO16 = RW_ARR_BYTES >> 4;
+                const uint32_t stage16  = p.stage_bytes >> 4;
+                const bool tracing      = p.trace != nullptr && blockIdx.x == 0;
+                uint64_t a_cur = wdesc0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(tmem_empty_bar(acc), ((uint32_t) (it >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t) (acc * 2 * RW_MAX_N);
+                    uint64_t b_cat = bdesc0;
+                    for (int ky = 0; ky < p.kh; ++ky, b_cat += b_ky) {
+                        if (!ready) mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        if (tracing && tr < 256) p.trace[1 * 256 + tr] = clock64();
+                        if (!no_mma) {
+                            umma_f16(d_tmem, a_cur, b_cat, idesc_cat, ky > 0 ? 1u : 0u);
+                            if (TERMS >= 2) umma_f16(d_tmem, a_cur + LO16, b_cat, idesc, 1u);
+                        }
+                        const int cur        = stage;
+                        const bool wrap      = stage == RW_STAGES - 1;
+                        const uint64_t a_now = a_cur;
+                        phase ^= wrap ? 1u : 0u;
+                        stage = wrap ? 0 : stage + 1;
+                        a_cur = wrap ? wdesc0 : a_cur + stage16;
+                        ready = mbar_test_wait(full_bar(stage), phase); // look-ahead, overlaps with the MMAs already queued
+                        if (!no_mma) {
+#pragma unroll
+                            for (int q = 1; q < FKS; ++q) {
+                                umma_f16(d_tmem, a_now + 2u * q, b_cat + 2u * q, idesc_cat, 1u);
+                                if (TERMS >= 2) umma_f16(d_tmem, a_now + LO16 + 2u * q, b_cat + 2u * q, idesc, 1u);
+                            }
+                        }
+                        umma_commit(empty_bar(cur));
+                        if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
+                        if (tracing && tr < 256) p.trace[2 * 256 + tr] = clock64();
+                        ++tr;
+                    }
+                }
+            } else
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
@@ -1155,13 +1254,13 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     if (!ready) mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     UM_TRACE(1, tr);
-                    const uint64_t a0 = wdesc0 + (uint64_t) (uint32_t) (stage * (RW_STAGE_BYTES >> 4));
+                    const uint64_t a0 = wdesc0 + (uint64_t) ((uint32_t) stage * (p.stage_bytes >> 4));
 #pragma unroll
                     for (int q = 0; q < 8; ++q) { // K step q lives in weight panel q / 4, columns 16 (q % 4) ..
-                        if (q < last_q) {
+                        if (q < last_q && !no_mma) {
                             const uint64_t bq = b_cat + (uint64_t) ((q >> 2) * b_panel + 2u * (q & 3));
                             umma_f16(d_tmem, a0 + koff[q], bq, idesc_cat, (ky > 0 || q > 0) ? 1u : 0u);           // -> [hi.hi | hi.lo]
-                            if (TERMS >= 2) umma_f16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff[q], bq, idesc, 1u); // lo.hi onto the first block
+                            if (TERMS >= 2) umma_f16(d_tmem, a0 + lo_off16 + koff[q], bq, idesc, 1u); // lo.hi onto the first block
                         }
                     }
                     const uint64_t b_last = b_cat + (uint64_t) ((last_q >> 2) * b_panel + 2u * (last_q & 3));
@@ -1169,8 +1268,10 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     phase ^= (stage == RW_STAGES - 1) ? 1u : 0u;
                     stage = stage == RW_STAGES - 1 ? 0 : stage + 1;
                     ready = mbar_test_wait(full_bar(stage), phase); // look-ahead, overlaps with the MMAs already queued
-                    umma_f16(d_tmem, a0 + koff_last, b_last, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
-                    if (TERMS >= 2) umma_f16(d_tmem, a0 + (2 * RW_ARR_BYTES >> 4) + koff_last, b_last, idesc, 1u);
+                    if (!no_mma) {
+                        umma_f16(d_tmem, a0 + koff_last, b_last, idesc_cat, (ky > 0 || last_q > 0) ? 1u : 0u);
+                        if (TERMS >= 2) umma_f16(d_tmem, a0 + lo_off16 + koff_last, b_last, idesc, 1u);
+                    }
                     umma_commit(empty_bar(cur));
                     if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
                     UM_TRACE(2, tr);
@@ -1192,6 +1293,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         e.has_lo = TERMS >= 2;
         e.stg = stg, e.res_bar = 0, e.bar_id = 1;
         e.part_src = nullptr, e.part_splits = 0;
+        e.no_store = (p.ablate & 8) != 0;
         uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -1204,6 +1306,12 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             e.tmem_empty = tmem_empty_bar(acc);
             e.trace = p.trace, e.trace_seq = it;
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * 2 * RW_MAX_N);
+            if (p.ablate & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e.tmem_empty);
+                continue;
+            }
             epilogue_tile<RW_EPI_WARPS, TERMS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, half, warp == 2, lane, res_phase);
             if (warp == 2) UM_TRACE(4, it);
         }
@@ -1402,7 +1510,7 @@ static bool rowwin_supported(const ConvArgs& a) {
     RowPlan rp;
     return a.in->cp == 8 && a.w && a.w->w_row_hi && a.w->w_row_lo && a.w->row_stride == a.stride && a.w->row_pad == a.pad_x &&
            a.out->c <= RW_MAX_N && a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW &&
-           a.k * ((rp.ksteps + 3) / 4) * 2 * round_up(a.out->c, 16) * 128 <= RW_B_BYTES; // the whole weight panel set stays resident
+           a.k * ((rp.ksteps + 3) / 4) * 2 * round_up(a.out->c, 16) * 128 <= RW_B_MAX_BYTES; // the whole weight panel set stays resident
 }
 
 bool conv2d_umma_supported(const ConvArgs& a) {
@@ -1418,12 +1526,41 @@ bool conv2d_umma_supported(const ConvArgs& a) {
 
 enum { ATTR_UMMA = 1u, ATTR_ROWWIN = 2u, ATTR_DW1 = 4u, ATTR_DW2 = 8u }; // bits of snnb_context::func_attr_mask
 
+typedef void (*RowWinKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const RowWinParams);
+template <int TERMS> static RowWinKernel rowwin_kernel_fks(int fks) {
+    switch (fks) {
+    case 1: return conv_rowwin_kernel<TERMS, 1>;
+    case 2: return conv_rowwin_kernel<TERMS, 2>;
+    case 3: return conv_rowwin_kernel<TERMS, 3>;
+    case 4: return conv_rowwin_kernel<TERMS, 4>;
+    default: return conv_rowwin_kernel<TERMS, 0>;
+    }
+}
+static RowWinKernel rowwin_kernel_of(int terms, int fks) { return terms == 3 ? rowwin_kernel_fks<3>(fks) : (terms == 2 ? rowwin_kernel_fks<2>(fks) : rowwin_kernel_fks<1>(fks)); }
+
+// FEED mode: the input tensor carries the compact 4-channel copy this layer's weights were packed for, and it is large enough
+static bool feed_usable(const ConvArgs& a, FeedPlan& fp) {
+    const snnb_tensor* in = a.in;
+    if (!in->feed_hi || !a.w->w_feed_hi || !a.w->w_feed_lo || a.w->feed_pad != a.pad_x) return false;
+    if (!make_feed_plan(a.k, a.stride, a.pad_x, in->c, fp) || fp.px != in->feed_px || in->feed_py != a.pad_y) return false;
+    const int tiles_x = (a.out->w + UM_BLOCK_M - 1) / UM_BLOCK_M;
+    return in->feed_w >= 2 * (tiles_x * UM_BLOCK_M - 1) + 2 * fp.nch && in->feed_h >= 2 * (a.out->h - 1) + a.k &&
+           (254 + 2 * fp.nch) * 8 <= RW_ARR_BYTES;
+}
+
 static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTiledFn encode) {
-    ctx->last_kernel = "conv_rowwin_kernel";
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;
     RowPlan rp;
     SNNB_REQUIRE(make_row_plan(a.k, a.stride, a.pad_x, rp), "launch_conv2d_rowwin: no row plan");
+    FeedPlan fp;
+    const bool feed = feed_usable(a, fp);
+    if (feed) { // one dense segment per plane, K steps at consecutive 32-byte offsets
+        rp.parities = 1, rp.ksteps = fp.ksteps;
+        for (int q = 0; q < fp.ksteps; ++q) rp.ks_parity[q] = 0, rp.ks_erel[q] = 2 * q;
+    }
+    ctx->last_kernel = feed ? "conv_rowwin_kernel<feed>" : "conv_rowwin_kernel";
     RowWinParams p;
     p.out_hi = out->hi, p.out_lo = out->lo, p.bias = a.w->bias;
     p.N = out->n, p.OH = out->h, p.OW = out->w, p.OC = out->c, p.OCp = out->cp;
@@ -1436,6 +1573,14 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     p.act = a.act, p.alpha = a.alpha;
     static const int rw_ablate = getenv("SNNB_UMMA_ABLATE") ? atoi(getenv("SNNB_UMMA_ABLATE")) : 0;
     p.ablate                   = rw_ablate;
+    p.feed_hi = in->feed_hi, p.feed_lo = in->feed_lo, p.feed_h = in->feed_h, p.feed_w = in->feed_w, p.feed_py = in->feed_py;
+    p.feed_seg_bytes = feed ? (uint32_t) (254 + 2 * fp.nch) * 8u : 0u;
+    const int terms = conv_terms(ctx, a);
+    p.lo_off      = (uint32_t) p.parities * RW_ARR_BYTES;
+    p.stage_bytes = (terms == 1 ? 1u : 2u) * p.lo_off;
+    p.b_bytes     = (uint32_t) round_up((terms == 3 ? 2 : 1) * a.k * p.panels * p.n_blk * 128, 1024);
+    p.stages      = std::min(RW_MAX_STAGES, (int) ((RW_SMEM_BYTES - 1024 - RW_BAR_BYTES - UM_STG_BYTES - (int) p.b_bytes) / (int) p.stage_bytes));
+    SNNB_REQUIRE(p.stages >= 2, "launch_conv2d_rowwin: weight panels of %u bytes leave no room for the activation ring", p.b_bytes);
 
     // A: per plane and column parity a 4-D view (8 ch | de-interleaved pixel index | row | image) of the NHWC plane
     CUtensorMap tmA[4], tmB[2];
@@ -1452,13 +1597,12 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, rowwin) failed: %d", (int) r);
         }
-    const int terms = conv_terms(ctx, a);
     {
         const cuuint64_t dims[2]    = {64, (cuuint64_t) a.k * p.panels * a.w->ocr}; // [ky][panel][OCr] rows of 64 K columns
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2]     = {64, (cuuint32_t) p.n_blk};
         const cuuint32_t estr[2]    = {1, 1};
-        void* planes[2]             = {(void*) a.w->w_row_hi, (void*) a.w->w_row_lo}; // the 2-term product uses the hi plane alone: fp16_rn(w)
+        void* planes[2] = {(void*) (feed ? a.w->w_feed_hi : a.w->w_row_hi), (void*) (feed ? a.w->w_feed_lo : a.w->w_row_lo)}; // 2-term: the hi plane alone = fp16_rn(w)
         for (int i = 0; i < 2; ++i) {
             CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, planes[i], dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1468,21 +1612,20 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     CUtensorMap tmO[2];
     if (encode_nhwc_box_maps(encode, out, p.n_blk, UM_BLOCK_M, 1, 1, p.n_blk == 64, tmO)) return 2;
     if (!(ctx->func_attr_mask & ATTR_ROWWIN)) {
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
-        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
+        for (int t = 1; t <= 3; ++t)
+            for (int f = 0; f <= 4; ++f) SNNB_CUDA_OK(cudaFuncSetAttribute(rowwin_kernel_of(t, f), cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM_BYTES));
         ctx->func_attr_mask |= ATTR_ROWWIN;
     }
     const int total_tiles = p.N * p.OH * p.tiles_x;
     const int grid        = std::min(total_tiles, ctx->sm_count);
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
-    auto* kern = terms == 3 ? conv_rowwin_kernel<3> : (terms == 2 ? conv_rowwin_kernel<2> : conv_rowwin_kernel<1>);
+    auto* kern = rowwin_kernel_of(terms, feed ? fp.ksteps : 0);
     const cudaError_t le = launch_k_pdl(kern, dim3(grid), dim3(RW_THREADS), RW_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmA[2], tmA[3], tmB[0], tmB[1], tmO[0], tmO[1], p);
     if (p.trace) {
         char hdr[256];
-        snprintf(hdr, sizeof hdr, "rowwin k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d kh %d ksteps %d terms %d", a.k, a.stride, a.in->c, a.out->c, a.out->n, a.out->h, a.out->w,
-                 p.n_blk, total_tiles, grid, p.kh, p.ksteps, terms);
+        snprintf(hdr, sizeof hdr, "rowwin%s k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d kh %d ksteps %d terms %d", feed ? "<feed>" : "", a.k, a.stride, a.in->c,
+                 a.out->c, a.out->n, a.out->h, a.out->w, p.n_blk, total_tiles, grid, p.kh, p.ksteps, terms);
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

@@ -20,6 +20,8 @@ size_t PackedHost::device_bytes() const {
     b += align256(w_lo.size() * sizeof(__half));
     b += align256(w_row_hi.size() * sizeof(__half));
     b += align256(w_row_lo.size() * sizeof(__half));
+    b += align256(w_feed_hi.size() * sizeof(__half));
+    b += align256(w_feed_lo.size() * sizeof(__half));
     b += align256(bias.size() * sizeof(float));
     b += align256(gamma.size() * sizeof(float));
     b += align256(beta.size() * sizeof(float));
@@ -103,6 +105,28 @@ void pack_rowwin_host(PackedHost& p, int stride, int pad_x) {
                 }
 }
 
+void pack_feed_host(PackedHost& p, int stride, int pad_x) {
+    FeedPlan fp;
+    if (p.kind != 1 || p.out_ch > 64 || p.w_row_hi.empty() || !make_feed_plan(p.kernel, stride, pad_x, p.in_ch, fp)) return;
+    const int k = p.kernel, IC = p.in_ch, OC = p.out_ch;
+    p.feed_pad = pad_x;
+    p.w_feed_hi.assign((size_t) k * p.ocr * 64, __float2half_rn(0.0f));
+    p.w_feed_lo.assign((size_t) k * p.ocr * 64, __float2half_rn(0.0f));
+    for (int ky = 0; ky < k; ++ky)
+        for (int o = 0; o < OC; ++o)
+            for (int off = 0; off < 2 * fp.nch; ++off) { // pixel offset within the window = chunk off / 2, pixel off % 2
+                const int t = off - fp.d;
+                if (t < 0 || t >= k) continue;
+                for (int c = 0; c < IC; ++c) {
+                    const float wv   = p.w_f32[(size_t) ((ky * k + t) * IC + c) * p.ocw + o]; // BN already folded in
+                    const size_t idx = ((size_t) ky * p.ocr + o) * 64 + off * 4 + c;
+                    const __half hh  = __float2half_rn(wv);
+                    p.w_feed_hi[idx] = hh;
+                    p.w_feed_lo[idx] = __float2half_rn(wv - __half2float(hh));
+                }
+            }
+}
+
 void pack_depthwise_host(int C, int k, const float* w_chw, const float* bias, const float* g, const float* b, const float* m, const float* v,
                          PackedHost& out) {
     out.kind = 2, out.in_ch = C, out.out_ch = C, out.kernel = k;
@@ -153,6 +177,9 @@ int place_weights(snnb_context* ctx, const PackedHost& p, char* base, snnb_weigh
     if (put(ctx, p.w_lo, cur, &w->w_lo)) return 1;
     if (put(ctx, p.w_row_hi, cur, &w->w_row_hi)) return 1;
     if (put(ctx, p.w_row_lo, cur, &w->w_row_lo)) return 1;
+    w->feed_pad = p.feed_pad;
+    if (put(ctx, p.w_feed_hi, cur, &w->w_feed_hi)) return 1;
+    if (put(ctx, p.w_feed_lo, cur, &w->w_feed_lo)) return 1;
     if (put(ctx, p.bias, cur, &w->bias)) return 1;
     if (put(ctx, p.gamma, cur, &w->gamma)) return 1;
     if (put(ctx, p.beta, cur, &w->beta)) return 1;

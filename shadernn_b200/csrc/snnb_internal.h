@@ -97,6 +97,13 @@ struct snnb_tensor {
     int n = 0, h = 0, w = 0, c = 0, cp = 0;
     size_t plane_elems = 0;      // n*h*w*cp rounded up to 64 elements (128 B)
     bool owns = true;
+    // Optional "stem feed" (model input tensors consumed by a stride-2 convolution with <= 4 input channels, see FeedPlan and
+    // conv_rowwin_kernel): a second, compact copy of the image with 4 channels per pixel, [n][feed_h][feed_w][4] fp16 per plane,
+    // image pixel (y, x) at (y + feed_py, x + feed_px), zero margins. Written by the input kernels (split / normalise / resize)
+    // together with the regular planes; the regular planes stay valid for every other consumer.
+    __half* feed_hi = nullptr;
+    __half* feed_lo = nullptr;
+    int feed_h = 0, feed_w = 0, feed_py = 0, feed_px = 0;
     size_t pixels() const { return (size_t) n * h * w; }
 };
 
@@ -116,6 +123,9 @@ struct snnb_weights {
     __half* w_row_hi = nullptr;
     __half* w_row_lo = nullptr;
     int row_stride = 0, row_pad = 0;
+    __half* w_feed_hi = nullptr; // feed-mode operand [kh][OCr][64] (FeedPlan K order), or null
+    __half* w_feed_lo = nullptr;
+    int feed_pad = -1;           // the x padding it was packed for
     // depthwise: fp32 [k*k][Cp]
     // folded bias: fp32 [round_up(OC, 64)]
     float* bias = nullptr;
@@ -245,11 +255,31 @@ static inline bool make_row_plan(int k, int stride, int pad_x, RowPlan& rp) {
     return rp.ksteps > 0;
 }
 
+// K ordering of the row-window kernel's FEED mode (stride 2, <= 4 input channels: the RGB stems). With 4 channels per pixel one
+// 16-byte K chunk holds TWO horizontally adjacent pixels, and for stride 2 the window of output pixel m starts at input pixel 2 m:
+// chunk j of A row m is the pair (2 m + 2 j, 2 m + 2 j + 1) = 16 m + 16 j bytes into a plain dense pixel row - the canonical
+// row pitch and LBO = 16 B again, but with NO parity de-interleave and half the K of the 8-channel form (7 taps x 4 ch + 1 pad
+// tap = 32 K instead of 64). The feed copy is shifted right by px (even, >= pad_x) so that pairs start on even pixels; tap t of
+// the filter sits at pixel offset d + t, d = px - pad_x in {0, 1}; offsets without a tap get zero weights.
+struct FeedPlan {
+    int px = 0, d = 0, nch = 0, ksteps = 0; // nch = 16-byte chunks per window (even), ksteps = nch / 2
+};
+static inline bool make_feed_plan(int k, int stride, int pad_x, int ic, FeedPlan& fp) {
+    if (stride != 2 || ic > 4 || k < 2 || k > 9 || pad_x < 0 || pad_x > 8) return false;
+    fp.px     = (pad_x + 1) & ~1;
+    fp.d      = fp.px - pad_x;
+    fp.nch    = ((fp.d + k + 1) / 2 + 1) & ~1;
+    fp.ksteps = fp.nch / 2;
+    return fp.ksteps <= 4;
+}
+
 struct PackedHost {
     std::vector<float> w_f32;           // [K][OCw]
     std::vector<__half> w_hi, w_lo; // [OCr][Kp]
     std::vector<__half> w_row_hi, w_row_lo; // [kh][OCr][64] (row-window kernel), empty unless IC <= 8
     int row_stride = 0, row_pad = 0;
+    std::vector<__half> w_feed_hi, w_feed_lo; // [kh][OCr][64] in FeedPlan K order (stride-2 stems with <= 4 input channels)
+    int feed_pad = -1;
     std::vector<float> bias;            // [round_up(OC,64)]
     std::vector<float> gamma, beta, mean, var;
     int kind = 0, in_ch = 0, out_ch = 0, kernel = 1, ocw = 0, kp = 0, ocr = 0;
@@ -259,6 +289,8 @@ void pack_conv2d_host(int IC, int OC, int k, const float* w_oihw, const float* b
                       PackedHost& out);
 // Adds the row-window operand (w_row_hi/lo) for small-IC convolutions; needs the layer's stride and x padding.
 void pack_rowwin_host(PackedHost& p, int stride, int pad_x);
+// Adds the feed-mode operand (w_feed_hi/lo) when make_feed_plan() accepts the layer.
+void pack_feed_host(PackedHost& p, int stride, int pad_x);
 void pack_depthwise_host(int C, int k, const float* w_chw, const float* bias, const float* g, const float* b, const float* m, const float* v,
                          PackedHost& out);
 void pack_channels_host(int C, const float* g, const float* b, const float* m, const float* v, PackedHost& out);
@@ -266,5 +298,6 @@ void pack_channels_host(int C, const float* g, const float* b, const float* m, c
 int place_weights(snnb_context* ctx, const PackedHost& p, char* base, snnb_weights* w);
 
 int tensor_alloc(snnb_context* ctx, int n, int h, int w, int c, snnb_tensor** out, bool lo_plane = true);
+int tensor_alloc_feed(snnb_tensor* t, int feed_h, int feed_w, int py, int px); // see snnb_tensor::feed_hi
 
 } // namespace snnb

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(64, 1) bench3(int n, int kblocks, long long* o
 // The row-window kernel's stage (stems: IC <= 8): the A operand is read through a SWIZZLE_NONE K-major descriptor whose K-chunk stride
 // (LBO) is 16 B - chunk j of row m is pixel m + j of a dense pixel row. `ksteps` K steps per stage (7x7 stride 2: 4), each
 // A_hi x [B_hi;B_lo] (N = 2n) + A_lo x B_hi (N = n); B panels are SWIZZLE_128B as in the kernel. Is this operand form as fast as the swizzled one?
-__global__ void __launch_bounds__(64, 1) bench_window(int n, int ksteps, int stages, int swizzled_a, long long* out) {
+__global__ void __launch_bounds__(64, 1) bench_window(int n, int ksteps, int stages, int swizzled_a, long long* out, int commit_every = 1) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ uint64_t bars[9];
@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(64, 1) bench_window(int n, int ksteps, int sta
                     mma(tmem, a_hi0 + ao, b + 2u * (q & 3), id_cat, 1u);
                     mma(tmem, a_lo0 + ao, b + 2u * (q & 3), id, 1u);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[st & 7])) : "memory");
+                if ((st + 1) % commit_every == 0)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[st & 7])) : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[8])) : "memory");
             uint32_t ok = 0;
@@ -262,6 +263,15 @@ int main() {
             if (e == cudaSuccess) cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
             printf("row-window stage, 4 K steps, 3-term, n_blk %2d, A operand %s: %7.1f clk per stage (math floor %4.0f)%s\n", n,
                    sw ? "SWIZZLE_128B (canonical)       " : "SWIZZLE_NONE window (LBO 16 B) ", (double) c / 900, 4.0 * 3 * 128 * n * 16 / 4096.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+    // how much issue-thread time does a tcgen05.commit cost? stages of `ksteps` K steps (2 MMAs each, n_blk 64), one commit every `ce` stages
+    for (int ks : {0, 1, 2, 4})
+        for (int ce : {1, 2, 7, 900}) {
+            bench_window<<<148, 64, 202 * 1024>>>(64, ks, 900, 0, d, ce);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long c = -1;
+            if (e == cudaSuccess) cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+            printf("commit cost: %d K steps per stage (math floor %3d clk), commit every %3d stages: %7.1f clk per stage%s\n", ks, ks * 112, ce, (double) c / 900, e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
     run3<0, 0, 0>(d);
     run3<1, 0, 0>(d);
