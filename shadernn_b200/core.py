@@ -18,7 +18,7 @@ from ._lib import ConvDesc, ModelOptions, check, lib, vp
 ACT = {"": 0, "linear": 0, "identity": 0, "none": 0, "relu": 1, "relu6": 2, "tanh": 3, "sigmoid": 4, "leakyRelu": 5, "leaky_relu": 5, "SiLU": 6,
        "softmax": 7}
 PAD_MODE = {"": 0, "none": 0, "constant": 1, "replicate": 2, "reflect": 3}
-ALGO = {"auto": 0, "simt": 1, "tcgen05": 2}
+ALGO = {"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05-streamk": 3}
 PRECISION = {"fp32x3": 0, "fp16w": 1, "fp16": 2}
 
 

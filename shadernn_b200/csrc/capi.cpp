@@ -283,7 +283,8 @@ int snnb_conv2d_launch(snnb_context* ctx, const snnb_conv_desc* d, const snnb_we
     SNNB_REQUIRE(in->n == out->n, "snnb_conv2d_launch: batch mismatch");
     if (residual) CHECK_DIMS_EQ(residual, out, "snnb_conv2d_launch(residual)");
     ConvArgs a {in, residual, out, w, d->kernel, d->stride, d->pad_x, d->pad_y, d->pad_mode, d->activation, d->leaky_alpha};
-    if (d->algo == SNNB_ALGO_TCGEN05) {
+    a.stream_k = d->algo == SNNB_ALGO_TCGEN05_STREAMK;
+    if (d->algo == SNNB_ALGO_TCGEN05 || d->algo == SNNB_ALGO_TCGEN05_STREAMK) {
         SNNB_REQUIRE(conv2d_umma_supported(a), "snnb_conv2d_launch: the tcgen05 path does not support this shape (IC=%d OC=%d k=%d s=%d pad_mode=%d)", in->c, out->c,
                      d->kernel, d->stride, d->pad_mode);
         return launch_conv2d_umma(ctx, a);

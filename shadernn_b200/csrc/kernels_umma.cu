@@ -93,6 +93,13 @@ struct UmmaParams {
     long long* trace; // profiling aid (env SNNB_UMMA_TRACE): CTA 0 writes clock64 stamps per role, [6][256]
     int ablate; // profiling aid (env SNNB_UMMA_ABLATE, results are WRONG when set): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs
     int has_lo; // the output tensor has a lo plane (0 in the fp16 storage mode)
+    // Stream-K (sk != 0, plain mode): the first sk_dp tiles (a multiple of the grid) are whole-tile work items, CTA b taking tiles
+    // b, b + grid, ...; the K-block units of the remaining tiles (sk_units = tiles x K blocks, laid end to end) are cut into sk_ctas
+    // equal ranges, CTA b < sk_ctas taking range b - which covers the tail of one tile and the head of the next. A tile cut into
+    // pieces is finished like a split-K tile (fp32 partials, last arriver sums them in piece order). Work ids: [0, sk_dp) tiles,
+    // sk_dp + 4 c + j = the j-th piece of CTA c's range; the schedule is static (no draw from sched_counter): pieces first, then tiles.
+    int sk, sk_dp, sk_ctas;
+    long long sk_units;
     int b_stages, b_stage_bytes; // halo mode: depth and stage size of the weight ring (3 x 32 KB, or 6 x 16 KB when a stage fits)
 };
 
@@ -128,17 +135,26 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) { 
         : "memory");
     return ok != 0;
 }
+// Progress word of every CTA's producer warp (debugging aid: printed when a wait times out)
+__device__ unsigned int g_producer_progress[1024];
+__device__ __forceinline__ void producer_progress(int lane, unsigned int code) {
+    if (lane == 0) *reinterpret_cast<volatile unsigned int*>(&g_producer_progress[blockIdx.x & 1023]) = code;
+}
 // Bounded wait: a broken descriptor or protocol bug must surface as a trapped kernel, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    bool reported      = false;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+        const long long dt = clock64() - t0;
+        if (dt > 4000000000LL && !reported) {
             uint32_t dyn;
             asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-            printf("tcgen05 kernel (dynamic smem %u B): mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", dyn, blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
+            printf("tcgen05 kernel (dynamic smem %u B): mbarrier wait timed out (block %d thread %d bar 0x%x parity %u, producer progress 0x%x)\n", dyn, blockIdx.x,
+                   threadIdx.x, bar, parity, *reinterpret_cast<volatile unsigned int*>(&g_producer_progress[blockIdx.x & 1023]));
+            reported = true;
         }
+        if (dt > 4040000000LL) __trap(); // ~20 ms after the first report: every stuck thread gets to print
     }
 }
 // One lane of a CONVERGED warp. Unlike `lane == 0` the compiler knows a single thread is active in the guarded region, so
@@ -506,6 +522,46 @@ __device__ __forceinline__ void epilogue_drain(bool leader) {
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
+// One work item of conv_umma_kernel: which tile, which K blocks, and - when the tile's K range is shared between CTAs - which piece
+// of how many, plus the slot of its partial tiles.
+struct WorkItem {
+    int tile, kb0, kb1, piece, pieces, slot;
+};
+__device__ __forceinline__ WorkItem decode_work(const UmmaParams& p, int work, int total_tiles, int num_kb) {
+    WorkItem w;
+    if (!p.sk) {
+        const int split = work / total_tiles;
+        w.tile = work - split * total_tiles, w.kb0 = split * p.kb_per_split, w.kb1 = min(num_kb, w.kb0 + p.kb_per_split);
+        w.piece = split, w.pieces = p.ksplit, w.slot = w.tile;
+    } else if (work < p.sk_dp) {
+        w.tile = work, w.kb0 = 0, w.kb1 = num_kb, w.piece = 0, w.pieces = 1, w.slot = 0;
+    } else {
+        const int c = (work - p.sk_dp) >> 2, j = (work - p.sk_dp) & 3;
+        const long long b0 = (long long) c * p.sk_units / p.sk_ctas, b1 = (long long) (c + 1) * p.sk_units / p.sk_ctas; // this CTA's units
+        const int jt = (int) (b0 / num_kb) + j; // tile (counted from sk_dp) of the CTA's j-th piece
+        const long long t0 = (long long) jt * num_kb, t1 = t0 + num_kb;
+        w.tile = p.sk_dp + jt, w.slot = jt;
+        w.kb0 = (int) (max(b0, t0) - t0), w.kb1 = (int) (min(b1, t1) - t0);
+        // CTA holding unit u: ((u + 1) * ctas - 1) / units
+        const int c_first = (int) (((t0 + 1) * p.sk_ctas - 1) / p.sk_units), c_last = (int) ((t1 * p.sk_ctas - 1) / p.sk_units);
+        w.piece = c - c_first, w.pieces = c_last - c_first + 1;
+    }
+    return w;
+}
+// Static schedule of a stream-K launch: CTA `cta` first works off the pieces of its K-block range, then its whole tiles cta, cta + grid, ...
+// (pieces first: a cut tile's last arriver sums the partials while the other CTAs are busy with whole tiles, not at the very end of the
+// launch with everybody waiting). Returns the work id after `work` (`end` when there is none) / the first one.
+__device__ __forceinline__ int sk_next_work(const UmmaParams& p, int work, int cta, int grid, int num_kb, int end) {
+    if (work < p.sk_dp) return work + grid < p.sk_dp ? work + grid : end;
+    const int c = (work - p.sk_dp) >> 2, j = ((work - p.sk_dp) & 3) + 1;
+    const long long b0 = (long long) c * p.sk_units / p.sk_ctas, b1 = (long long) (c + 1) * p.sk_units / p.sk_ctas;
+    if (j < 4 && b0 / num_kb + j <= (b1 - 1) / num_kb) return work + 1;
+    return cta < p.sk_dp ? cta : end;
+}
+__device__ __forceinline__ int sk_first_work(const UmmaParams& p, int cta, int end) {
+    return cta < p.sk_ctas ? p.sk_dp + 4 * cta : (cta < p.sk_dp ? cta : end);
+}
+
 #define UM_TRACE(role, idx)                                                                          \
     do {                                                                                             \
         if (p.trace && blockIdx.x == 0 && lane == 0 && (idx) < 256) p.trace[(role) * 256 + (idx)] = clock64(); \
@@ -599,9 +655,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // The WEIGHTS of this CTA's first work item do not depend on the previous kernel: their loads go out before the dependency wait
     // (plain mode: the first K block's; halo mode: the first three taps'), so only the activations' latency is left after it.
     const int pre_total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
-    const bool pre_b          = (p.ablate & 2) == 0 && (int) blockIdx.x < pre_total_tiles * p.ksplit;
+    const int pre_num_kb      = p.ksize * p.ksize * p.cblocks;
+    const int pre_end         = p.sk ? p.sk_dp + 4 * p.sk_ctas : pre_total_tiles * p.ksplit; // one past the last work id
+    const int first_work      = p.sk ? sk_first_work(p, (int) blockIdx.x, pre_end) : (int) blockIdx.x;
+    const bool pre_b          = (p.ablate & (2 | 16)) == 0 && first_work < pre_end; // ablate 16: no early weight loads (results stay correct)
     if (warp == 0 && pre_b && elect_one()) {
-        const int tile = (int) blockIdx.x % pre_total_tiles, split = (int) blockIdx.x / pre_total_tiles;
+        const WorkItem w0 = decode_work(p, first_work, pre_total_tiles, pre_num_kb);
+        const int tile    = w0.tile;
         const int oc0  = (tile / (p.tiles_x * p.tiles_y * p.tiles_n)) * p.n_blk;
         const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u;
         if (HALO) {
@@ -612,7 +672,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (TERMS == 3) tma_load_2d(sB + b_lo_off, &tmB_lo, fb, tap * p.ICp, oc0);
             }
         } else {
-            const int kb0 = split * p.kb_per_split, cb = kb0 % p.cblocks, tap0 = kb0 / p.cblocks;
+            const int kb0 = w0.kb0, cb = kb0 % p.cblocks, tap0 = kb0 / p.cblocks;
             const uint32_t fb = full_bar(0);
             mbar_expect_tx(fb, (TERMS == 1 ? 1u : 2u) * (uint32_t) p.rows_used * 128u + (TERMS == 3 ? 2u : 1u) * (uint32_t) p.n_blk * 128u);
             tma_load_2d(smem_base + 2 * UM_A_BYTES, &tmB_hi, fb, tap0 * p.ICp + cb * UM_BLOCK_K, oc0);
@@ -633,7 +693,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
     const int total_tiles = m_tiles * p.tiles_oc;
     const int num_kb      = p.ksize * p.ksize * p.cblocks;
-    const int total_work  = total_tiles * p.ksplit; // work item = (tile, K range); ksplit == 1: one item per tile
+    const int total_work  = p.sk ? p.sk_dp + 4 * p.sk_ctas : total_tiles * p.ksplit; // work item = (tile, K range); one past the last work id
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -647,8 +707,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u; // B_lo rows follow B_hi's: one [2 n_blk x 64] operand
             int tr = 0;
             const int draws_total = max(0, total_work - (int) gridDim.x) + (int) gridDim.x; // every CTA's last draw is past the end
-            int work = blockIdx.x;
+            int work = first_work;
             for (int seq = 0;; ++seq) {
+                if (p.ablate & 32) producer_progress(lane, ((unsigned) seq << 16) | 0x01u); // SNNB_UMMA_ABLATE=32: leave a trail for the time-out report
                 {   // publish this sequence number's work id
                     const int slot = seq & (UM_SCHED_SLOTS - 1);
                     mbar_wait(sched_empty(slot), ((uint32_t) (seq / UM_SCHED_SLOTS) & 1u) ^ 1u);
@@ -657,24 +718,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         mbar_arrive(sched_full(slot));
                     }
                 }
+                if (p.ablate & 32) producer_progress(lane, ((unsigned) seq << 16) | 0x02u);
                 if (work >= total_work) break;
                 // The next work item is drawn NOW but its result is not touched until this item's loads are issued: 148 CTAs hit the same
                 // counter at kernel start (a ~1.3 k clk round trip). r01 tested the result right away (`if (c == last) reset`), which put that
                 // round trip in front of every item's first load - the producer's whole run-ahead margin (r02 trace: first load 2.3-5.4 k clk
                 // after kernel entry, ~1.3 k clk of bubble at every tile boundary).
                 int drawn = 0;
-                if (elect_one()) drawn = atomicAdd(p.sched_counter, 1);
+                if (!p.sk && elect_one()) drawn = atomicAdd(p.sched_counter, 1);
                 auto take_next = [&]() { // consumes the draw: next work id for all lanes; the launch's last draw re-zeroes the counter
+                    if (p.sk) return sk_next_work(p, work, (int) blockIdx.x, (int) gridDim.x, num_kb, total_work); // static schedule
                     const int c = __shfl_sync(0xffffffffu, drawn, 0); // elect.sync picks lane 0 of the converged warp
                     if (lane == 0 && c == draws_total - 1) *p.sched_counter = 0;
                     return (int) gridDim.x + c;
                 };
-                const int tile = work % total_tiles, split = work / total_tiles;
+                const WorkItem wi = decode_work(p, work, total_tiles, num_kb);
+                const int tile = wi.tile;
                 const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
                 const int ix0 = bx * p.tw * p.stride - p.pad_x, iy0 = by * p.th * p.stride - p.pad_y, n0 = bn * p.tn;
                 const int oc0 = oc_idx * p.n_blk;
-                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                const int kb0 = wi.kb0, kb1 = wi.kb1;
                 // Keep this loop lean: it runs once per K block and every stall here delays the whole pipeline (no divisions,
                 // no parameter loads: ncu r01 showed ~60 dependent scalar instructions/iteration bounding the kernel).
                 // K block kb = (ky * ks + kx) * cbs + cb; the counters are decoded once per work item and then stepped.
@@ -713,11 +777,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                     if (nwork < total_work) issue_halo(nwork, 0);
                                 }
                             }
-                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            // This CTA's first three weight stages went out before the dependency wait. They must not be waited for either:
+                            // the MMA thread may already have consumed such a stage and committed its empty barrier, and a wait for
+                            // "the phase before the first" would then block for ever (seen as a rare hang of the first launches, when
+                            // the producer was slow to get here: cold instruction cache).
+                            const bool pre_stage = seq == 0 && cb == 0 && tap < 3 && pre_b;
+                            if (!pre_stage) mbar_wait(empty_bar(stage), phase ^ 1u);
                             UM_TRACE(0, tr);
                             ++tr;
-                            if (seq == 0 && cb == 0 && tap < 3 && pre_b) {
-                                // this CTA's first three weight stages went out before the dependency wait
+                            if (pre_stage) {
                             } else if (elect_one()) {
                                 const uint32_t sB = b_ring + stage * p.b_stage_bytes, fb = full_bar(stage);
                                 if (skip_tma) {
@@ -849,7 +917,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
                     continue;
                 }
-                const int kb0 = (work / total_tiles) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                const WorkItem wi = decode_work(p, work, total_tiles, num_kb);
+                const int kb0 = wi.kb0, kb1 = wi.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!ready) mbar_wait(full_bar(stage), phase); // TMA bytes have landed
                     tc_fence_after();
@@ -926,13 +995,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (;; ++it) {
             const int work = sched_take(it, lane == 0);
             if (work >= total_work) break;
-            const int tile = work % total_tiles, split = work / total_tiles;
+            const WorkItem wi = decode_work(p, work, total_tiles, num_kb);
+            const int tile = wi.tile;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
             if (SPLIT_EPI && acc != grp) continue; // the other group's accumulator buffer
             const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
             const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
-            if (p.has_res && p.ksplit == 1 && !(p.ablate & 1)) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
+            if (p.has_res && wi.pieces == 1 && !(p.ablate & 1)) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             if (leader) UM_TRACE(3, it);
@@ -945,15 +1015,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (lane == 0) mbar_arrive(e.tmem_empty);
                 continue;
             }
-            if (p.ksplit > 1) {
-                float* tile_parts = p.partials + (size_t) tile * p.ksplit * (UM_BLOCK_M * p.n_blk);
-                epilogue_dump_partial<UM_EPI_WARPS, EPI_TERMS>(e, taddr, tile_parts + (size_t) split * (UM_BLOCK_M * p.n_blk), row, half, lane);
+            if (wi.pieces > 1) {
+                float* tile_parts = p.partials + (size_t) wi.slot * (p.sk ? 4 : p.ksplit) * (UM_BLOCK_M * p.n_blk);
+                epilogue_dump_partial<UM_EPI_WARPS, EPI_TERMS>(e, taddr, tile_parts + (size_t) wi.piece * (UM_BLOCK_M * p.n_blk), row, half, lane);
                 __threadfence(); // partial tile visible device-wide before the arrival is counted
                 named_bar_sync(1, UM_EPI_WARPS * 32);
                 if (warp == 2 && lane == 0) {
-                    const int old  = atomicAdd(p.counters + tile, 1);
-                    const int last = old == p.ksplit - 1;
-                    if (last) p.counters[tile] = 0; // every split has arrived: leave the counter ready for the next launch
+                    const int old  = atomicAdd(p.counters + wi.slot, 1);
+                    const int last = old == wi.pieces - 1;
+                    if (last) p.counters[wi.slot] = 0; // every piece has arrived: leave the counter ready for the next launch
                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(last_flag), "r"(last) : "memory");
                 }
                 named_bar_sync(1, UM_EPI_WARPS * 32);
@@ -961,7 +1031,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(last) : "r"(last_flag) : "memory");
                 if (!last) continue;
                 __threadfence();
-                e.part_src = tile_parts, e.part_splits = p.ksplit;
+                e.part_src = tile_parts, e.part_splits = wi.pieces;
                 if (p.has_res) epilogue_residual_load(e, 0, oc_idx * p.n_blk, bx * p.tw, by * p.th, bn * p.tn, leader);
             }
             if (SPLIT_EPI)
@@ -1005,6 +1075,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // L2 -> SM traffic per 128-pixel tile: kh * s * ~136 * 16 B * 2 planes (61 KB for the 7x7 stem) instead of 224 KB of
 // gathered 16-byte requests. The weight panel [kh][n_blk][64] (hi + lo, K columns in RowPlan order) is loaded once per
 // persistent CTA and stays resident. Tiles = up to 128 consecutive output pixels of one output row.
+//
+// FEED mode (r02; stride 2, <= 4 input channels = the RGB stems): the input kernels also write a compact copy of the image with
+// FOUR channels per pixel and zero margins (snnb_tensor::feed_hi). With 8-byte pixels one 16-byte K chunk is a PAIR of adjacent
+// pixels, and for stride 2 the window of output pixel m starts at pixel 2 m = 16 m bytes: the plain dense row is already the
+// canonical operand (row pitch 16 B, LBO 16 B) - no parity de-interleave, half the K (7 taps x 4 channels + 1 pad tap = 32 instead of
+// 64), one contiguous bulk copy per plane and filter row, real zeros instead of out-of-bounds fill (FeedPlan, snnb_internal.h).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RW_MAX_STAGES    = 16;                           // ring depth is chosen per launch: whatever shared memory is left, see RowWinParams::stages
 constexpr int RW_EPI_WARPS     = 8;
@@ -1441,11 +1517,14 @@ static TilePlan plan_tiles(int N, int OH, int OW, int stride) {
 struct OcPlan {
     int n_blk = 0, tiles_oc = 0, ksplit = 1, kb_per_split = 0;
     double cost = 1e300; // modelled clocks of the launch
+    // stream-K (UmmaParams::sk): whole tiles first, the rest of the tiles' K blocks cut evenly over sk_ctas CTAs
+    int sk = 0, sk_dp = 0, sk_ctas = 0;
+    long long sk_units = 0;
 };
 // Tensor-pipe time of one M = 128 tcgen05.mma with N columns (tools/umma_microbench.cu: operand fetch from shared memory, A 4 KB +
 // B N x 32 B at 128 B/clk, bounds the narrow shapes): N <= 64: 48 clk, N = 128: 64, N = 256: 128.
 static double mma_clk(int n) { return std::max(48.0, n * 0.5); }
-static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int num_kb, int sm_count, int terms, bool halo = false) {
+static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int num_kb, int sm_count, int terms, bool halo = false, bool stream_k = false) {
     OcPlan best;
     double best_cost = 1e300;
     static const int no_split = getenv("SNNB_NO_SPLITK") != nullptr;
@@ -1470,7 +1549,27 @@ static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int
             const long long rounds = (items + sm_count - 1) / sm_count;
             const double cost      = (double) rounds * (kbps * kb_cost + 7000.0 + (sp > 1 ? 9000.0 : 0.0));
             if (cost < best_cost * (sp > 1 ? 0.93 : 1.0) - 1e-9) // split only for a clear win
-                best_cost = cost, best.cost = cost, best.n_blk = blk, best.tiles_oc = t, best.ksplit = sp, best.kb_per_split = kbps;
+                best_cost = cost, best.cost = cost, best.n_blk = blk, best.tiles_oc = t, best.ksplit = sp, best.kb_per_split = kbps, best.sk = 0;
+        }
+        // Stream-K: full waves of whole tiles, then the K blocks of the last partial wave's tiles shared evenly by all CTAs (each tile cut
+        // into at most 4 pieces, reduced by its last arriver) - instead of a last round that leaves most SMs idle.
+        // Opt-in (SNNB_ALGO_TCGEN05_STREAMK / SNNB_SK=1): on ResNet-18's 28x28 and 7x7 layers it measured 3-8 % SLOWER than whole tiles /
+        // uniform split-K - the partial dump, the arrival round trip and the last arriver's 3-4 x 64 KB reduction cost more than
+        // the idle SMs of the last wave (profiles/README.md).
+        static const int env_sk = getenv("SNNB_SK") != nullptr;
+        const long long tiles = (long long) m_tiles * t;
+        if ((stream_k || env_sk) && !no_split && !halo && num_kb >= 6 && tiles % sm_count != 0) {
+            const int dp          = (int) (tiles / sm_count) * sm_count;
+            const long long units = (tiles - dp) * num_kb;
+            const int umin        = (num_kb + 2) / 3; // >= a third of a tile per CTA: no tile in more than 4 pieces
+            if (units >= umin) {
+                const int ctas    = (int) std::min<long long>(sm_count, units / umin);
+                const double u    = std::ceil((double) units / ctas);
+                const double cost = (double) (dp / sm_count) * (num_kb * kb_cost + 7000.0) + u * kb_cost + 7000.0 + 4000.0;
+                if (cost < best_cost * 0.95 - 1e-9)
+                    best_cost = cost, best.cost = cost, best.n_blk = blk, best.tiles_oc = t, best.ksplit = 1, best.kb_per_split = num_kb, best.sk = 1, best.sk_dp = dp,
+                    best.sk_ctas = ctas, best.sk_units = units;
+            }
         }
         if (blk <= 16) break;
     }
@@ -1504,13 +1603,17 @@ static int conv_terms(const snnb_context* ctx, const ConvArgs& a) {
     return prec == SNNB_PRECISION_FP16W ? 2 : (prec == SNNB_PRECISION_FP16 ? 1 : 3);
 }
 
+static bool feed_usable(const ConvArgs& a, FeedPlan& fp);
 static bool rowwin_supported(const ConvArgs& a) {
-    // small-C stems: IC <= 8 (one 16-byte vector per pixel), stride 1 or 2, <= 4 K steps per filter row, weights packed
-    // for exactly this (stride, pad_x), whole panel resident in smem
+    // small-C stems: IC <= 8 (one 16-byte vector per pixel), stride 1 or 2, <= 8 K steps per filter row, weights packed
+    // for exactly this (stride, pad_x), whole panel set resident in smem - in the layout the launch will use (feed mode: one panel)
     RowPlan rp;
-    return a.in->cp == 8 && a.w && a.w->w_row_hi && a.w->w_row_lo && a.w->row_stride == a.stride && a.w->row_pad == a.pad_x &&
-           a.out->c <= RW_MAX_N && a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW &&
-           a.k * ((rp.ksteps + 3) / 4) * 2 * round_up(a.out->c, 16) * 128 <= RW_B_MAX_BYTES; // the whole weight panel set stays resident
+    if (!(a.in->cp == 8 && a.w && a.w->w_row_hi && a.w->w_row_lo && a.w->row_stride == a.stride && a.w->row_pad == a.pad_x && a.out->c <= RW_MAX_N &&
+          a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW))
+        return false;
+    FeedPlan fp;
+    const int panels = feed_usable(a, fp) ? 1 : (rp.ksteps + 3) / 4;
+    return a.k * panels * 2 * round_up(a.out->c, 16) * 128 <= RW_B_MAX_BYTES;
 }
 
 bool conv2d_umma_supported(const ConvArgs& a) {
@@ -1658,7 +1761,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     const int terms = conv_terms(ctx, a);
     p.has_lo        = out->lo != nullptr;
     p.b_stages = 0, p.b_stage_bytes = 0;
-    OcPlan op       = plan_oc_ksplit(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, tp.tw, a.k * a.k * p.cblocks, ctx->sm_count, terms);
+    OcPlan op       = plan_oc_ksplit(out->c, tp.tiles_x * tp.tiles_y * tp.tiles_n, p.rows_used, tp.tw, a.k * a.k * p.cblocks, ctx->sm_count, terms, false, a.stream_k);
     // halo mode (3x3, stride 1): 8 x 16-pixel tiles whose nine taps share one halo load; taken when the cost model prefers it
     // (fewer bytes per K block against the MMA rows lost where 8 / 16 do not divide the feature map)
     static const bool no_halo = getenv("SNNB_NO_HALO") != nullptr;
@@ -1676,6 +1779,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     }
     SNNB_REQUIRE(op.n_blk > 0, "launch_conv2d_umma: no output-channel plan");
     p.n_blk = op.n_blk, p.tiles_oc = op.tiles_oc, p.ksplit = op.ksplit, p.kb_per_split = op.kb_per_split;
+    p.sk = halo ? 0 : op.sk, p.sk_dp = op.sk_dp, p.sk_ctas = op.sk_ctas, p.sk_units = op.sk_units;
     p.partials = nullptr, p.counters = nullptr;
     if (!ctx->sched_counter) { // created by the first (eager) launch; graph capture replays use the same word
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1688,11 +1792,12 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         ctx->sched_counter = static_cast<int*>(pnew);
     }
     p.sched_counter = ctx->sched_counter;
-    if (p.ksplit > 1) {
-        const size_t tiles = (size_t) p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
+    if (p.ksplit > 1 || p.sk) {
+        // partial-tile slots: split-K [tile][split]; stream-K [tile past sk_dp][4 pieces]
+        const size_t tiles = p.sk ? (size_t) p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc - p.sk_dp : (size_t) p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         SNNB_CUDA_OK(cudaStreamIsCapturing(ctx->stream, &cap));
-        const size_t need = tiles * p.ksplit * UM_BLOCK_M * p.n_blk * sizeof(float);
+        const size_t need = tiles * (p.sk ? 4 : p.ksplit) * UM_BLOCK_M * p.n_blk * sizeof(float);
         SNNB_REQUIRE(cap == cudaStreamCaptureStatusNone || (need <= ctx->splitk_bytes && tiles <= ctx->splitk_counter_n),
                      "launch_conv2d_umma: split-K scratch must be allocated by an eager pass before graph capture");
         if (ensure_splitk_scratch(ctx, need, tiles)) return 1;
@@ -1753,11 +1858,12 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         ctx->func_attr_mask |= ATTR_UMMA;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
-    const int grid        = std::min(total_tiles * p.ksplit, ctx->sm_count);
+    const int grid        = p.sk ? (p.sk_dp > 0 ? ctx->sm_count : p.sk_ctas) : std::min(total_tiles * p.ksplit, ctx->sm_count);
     // short K loop (1x1 convolutions): the layer runs at the speed of the epilogue -> two independent epilogue groups
     static const bool no_split_epi = getenv("SNNB_NO_SPLIT_EPI") != nullptr;
-    const bool split_epi           = !halo && !no_split_epi && p.ksplit == 1 && p.ksize * p.ksize * p.cblocks <= 3 && total_tiles >= 2 * grid;
-    ctx->last_kernel = halo ? "conv_umma_kernel<halo>" : (split_epi ? "conv_umma_kernel<short-K>" : (p.ksplit > 1 ? "conv_umma_kernel<split-K>" : "conv_umma_kernel"));
+    const bool split_epi           = !halo && !no_split_epi && !p.sk && p.ksplit == 1 && p.ksize * p.ksize * p.cblocks <= 3 && total_tiles >= 2 * grid;
+    ctx->last_kernel = halo ? "conv_umma_kernel<halo>"
+                            : (split_epi ? "conv_umma_kernel<short-K>" : (p.sk ? "conv_umma_kernel<stream-K>" : (p.ksplit > 1 ? "conv_umma_kernel<split-K>" : "conv_umma_kernel")));
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
     auto* k_split = terms == 3 ? conv_umma_kernel<UM_STAGES - 1, true, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES - 1, true, 2, false> : conv_umma_kernel<UM_STAGES - 1, true, 1, false>);
@@ -1773,7 +1879,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     if (p.trace) {
         char hdr[256];
         snprintf(hdr, sizeof hdr, "conv k%d s%d IC%d OC%d out %dx%dx%d n_blk %d tiles %d grid %d num_kb %d ksplit %d terms %d halo %d", a.k, a.stride, in->c, out->c, out->n,
-                 out->h, out->w, p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -1 : p.ksplit, terms, (int) halo); // ksplit -1 = split-epilogue variant
+                 out->h, out->w, p.n_blk, total_tiles, grid, p.ksize * p.ksize * p.cblocks, split_epi ? -1 : (p.sk ? -2 : p.ksplit), terms, (int) halo); // ksplit -1 = split-epilogue variant, -2 = stream-K
         if (trace_end(ctx, p.trace, hdr)) return 1;
     }
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

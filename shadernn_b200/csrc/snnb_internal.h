@@ -184,6 +184,7 @@ struct ConvArgs {
     int k, stride, pad_x, pad_y, pad_mode, act;
     float alpha;
     int precision = -1; // SNNB_PRECISION_* of this launch; -1 = the context's default
+    bool stream_k = false; // the planner may choose the stream-K decomposition (SNNB_ALGO_TCGEN05_STREAMK)
 };
 int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a);
 int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a); // kernels_umma.cu (tcgen05 + TMA)

@@ -572,3 +572,46 @@ def test_dump_outputs_diff_against_oracle_dumps(ctx, model_dir, tmp_path):
     # 1e-3 relative to each tensor's range is layerwise_check above
     rows = dumpio.compare_dirs(str(got_dir), str(ref_dir), eps=0.01)
     assert len(rows) == 2 * m.num_layers and all(r[4] == "ok" for r in rows), [r for r in rows if r[4] != "ok"][:3]
+
+
+@pytest.mark.parametrize("h,w,c,k,oc,padding,prepad", [
+    (37, 53, 3, 7, 64, "same", None),          # the ResNet stem's shape class, ragged size
+    (64, 301, 3, 3, 32, "valid", (0, 1, 0, 1)),  # MobileNetV2's: explicit (0,1) padding folded into the convolution
+    (40, 531, 4, 5, 16, "same", None),         # three 128-pixel tiles per output row, 4 channels
+    (33, 45, 1, 3, 24, "same", None),          # 1 channel
+    (30, 41, 2, 9, 48, "same", None),          # 9 taps: three K steps per filter row
+])
+def test_stem_feed_mode_shapes(ctx, tmp_path, h, w, c, k, oc, padding, prepad):
+    # conv_rowwin_kernel's feed mode (stride-2 convolutions with <= 4 input channels reading a model input: the compact 4-channel
+    # copy written by the input kernels) against the oracle, fp32 and 8-bit input paths, fused and unfused
+    b = modelzoo.Builder(7)
+    x = b.input(w, h, c)
+    if prepad:
+        x = b.pad(x, *prepad)
+    x = b.conv(x, oc, k, 2, padding, "relu", bias=True)
+    b.conv(x, 8, 1, 1, "valid", "linear", bias=True)
+    path = str(tmp_path / "stem.json")
+    modelzoo.write_model(b.layers, path)
+    rng = np.random.default_rng(3)
+    img = rng.uniform(-1, 1, (3, h, w, c)).astype(np.float32)
+    want = oracle.Model(path).run(img, return_all=True)
+    conv_id = 2 if prepad else 1
+    for fuse in (False, True):
+        m = core.MixedInferenceCore(ctx, path, batch=3, fuse=fuse, use_cuda_graph=fuse)
+        m.set_input(img)
+        m.forward()
+        ctx.sync()
+        if not (prepad and not fuse):  # unfused, the Pad layer's output (not a model input) feeds the convolution: regular path
+            m.time_layers()
+            assert m.layer_kernel(conv_id) == "conv_rowwin_kernel<feed>", m.layer_kernel(conv_id)
+        assert_layer_close(m.layer_output(conv_id), want[conv_id], EPS, "stem conv fuse=%d" % fuse)
+        assert_layer_close(m.get_output(), want[-1], EPS, "head fuse=%d" % fuse)
+    # 8-bit images normalised on the device take the same feed (split_u8_kernel writes it)
+    if c in (3, 4):
+        u8 = rng.integers(0, 256, (3, h, w, c), dtype=np.uint8)
+        mean, norm = [127.5] * 4, [1 / 127.5] * 4
+        xf = (u8.astype(np.float32) - 127.5) * np.float32(1 / 127.5)
+        want8 = oracle.Model(path).run(xf)
+        m = core.MixedInferenceCore(ctx, path, batch=3, fuse=True, use_cuda_graph=True)
+        got8, _ = m.run_u8(u8, mean, norm, want_classes=False)
+        assert_layer_close(got8, want8.reshape(got8.shape), EPS, "u8 input")

@@ -162,3 +162,31 @@ def test_split_k(ctx, n, h, w, ic, oc, k, residual, act):
     # arriver in split order. Run twice: the second launch checks that the arrival counters were left at zero.
     run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=ic + h)
     run_case(ctx, n, h, w, ic, oc, k, act=act, residual=residual, seed=ic + h + 1)
+
+
+@pytest.mark.parametrize("n,h,w,ic,oc,k,s,residual", [
+    (32, 28, 28, 128, 128, 3, 1, True),   # 196 tiles on 148 SMs: one whole wave + 48 tiles cut into K-block ranges
+    (32, 14, 14, 256, 256, 3, 1, False),  # fewer tiles than SMs: every tile cut
+    (8, 7, 7, 512, 512, 3, 1, True),      # long K, few tiles
+    (5, 33, 21, 64, 96, 3, 2, False),     # ragged
+])
+def test_stream_k_decomposition(ctx, n, h, w, ic, oc, k, s, residual):
+    # SNNB_ALGO_TCGEN05_STREAMK: whole tiles for the full waves, the K loops of the remaining tiles cut evenly across the SMs; a cut
+    # tile's fp32 partials are summed in piece order by its last arriver -> deterministic, and equal to the oracle within the bar
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, (n, h, w, ic)).astype(np.float32)
+    wt = (rng.standard_normal((oc, ic, k, k)) * np.sqrt(2.0 / (k * k * ic))).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, oc).astype(np.float32)
+    o = oracle.same_padding(k, True)
+    oh, ow = oracle.conv_out_dim(h, k, s, o[0], o[1]), oracle.conv_out_dim(w, k, s, o[0], o[1])
+    want = oracle.conv2d(x, wt, b, None, s, o[0], o[2], "constant", "" if residual else "relu", 0.1, (oh, ow))
+    res = None
+    if residual:
+        res = rng.uniform(-1, 1, want.shape).astype(np.float32)
+        want = oracle.add(want, res, "relu", 0.1)
+    got = core.conv2d(ctx, x, wt, b, None, s, o[0], o[2], "constant", "relu", 0.1, (oh, ow), residual=res, algo="tcgen05-streamk")
+    again = core.conv2d(ctx, x, wt, b, None, s, o[0], o[2], "constant", "relu", 0.1, (oh, ow), residual=res, algo="tcgen05-streamk")
+    assert np.array_equal(got, again)  # the reduction order does not depend on which CTA arrives last
+    assert not oracle.compare(got, want, EPS), "stream-K conv differs from the oracle"
+    plain = core.conv2d(ctx, x, wt, b, None, s, o[0], o[2], "constant", "relu", 0.1, (oh, ow), residual=res, algo="tcgen05")
+    assert float(np.max(np.abs(got - plain))) <= 1e-4 * max(1.0, float(np.abs(plain).max()))
