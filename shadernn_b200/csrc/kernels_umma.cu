@@ -220,6 +220,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); } // all but the newest group
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
@@ -295,6 +296,10 @@ struct EpiArgs {
     long long* trace; // profiling aid: leader warp stamps the phases of its first slabs into [4][64 + 8 * slab_seq ...]
     int trace_seq;
     bool no_store = false; // profiling aid (SNNB_UMMA_ABLATE & 8, row-window kernel): everything but the TMA store of the tile
+    // Two staging buffers used on alternate tiles (row-window kernel, one slab per tile): only the store of the tile BEFORE the previous
+    // one must have finished reading. The TMA store drains shared memory at ~20 B/clk per SM (1.6 k clk for a 32 KB tile,
+    // profiles/r02_trace_mobilenetv2_1x1.txt); with one buffer that sat in series with the tile's arithmetic.
+    bool two_stagings = false;
 };
 
 // Fused residual (Conv2D -> Add): TMA box load of the residual tile's slab into the staging buffer. The previous bulk store
@@ -444,7 +449,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
             if (k0 == 0) {
                 if (!e.has_res) {
                     if (leader) {
-                        if (elect_one()) bulk_wait_read0();
+                        if (elect_one()) {
+                            if (e.two_stagings) bulk_wait_read1();
+                            else bulk_wait_read0();
+                        }
                         __syncwarp();
                     }
                     EPI_STAMP(2); // leader's wait for the previous store's reads
@@ -527,9 +535,10 @@ __device__ __forceinline__ void epilogue_drain(bool leader) {
 struct WorkItem {
     int tile, kb0, kb1, piece, pieces, slot;
 };
+template <bool SK> // compile-time: the stream-K arithmetic (64-bit divisions) stays out of every other instantiation's issue loops
 __device__ __forceinline__ WorkItem decode_work(const UmmaParams& p, int work, int total_tiles, int num_kb) {
     WorkItem w;
-    if (!p.sk) {
+    if constexpr (!SK) {
         const int split = work / total_tiles;
         w.tile = work - split * total_tiles, w.kb0 = split * p.kb_per_split, w.kb1 = min(num_kb, w.kb0 + p.kb_per_split);
         w.piece = split, w.pieces = p.ksplit, w.slot = w.tile;
@@ -575,7 +584,7 @@ __device__ __forceinline__ int sk_first_work(const UmmaParams& p, int cta, int e
 // TERMS: how the fp32-faithful product is formed. 3 = A_hi x [B_hi ; B_lo] + A_lo x B_hi (fp16 weight pair, accumulator of two
 // column blocks, n_blk <= 128); 2 = (A_hi + A_lo) x B16 with ONE fp16 weight plane (one column block, n_blk <= 256);
 // 1 = A_hi x B_hi only (fp16 storage mode: no lo planes anywhere).
-template <int STAGES, bool SPLIT_EPI, int TERMS, bool HALO>
+template <int STAGES, bool SPLIT_EPI, int TERMS, bool HALO, bool SK = false> // SK: stream-K work decomposition (UmmaParams::sk)
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO_hi64, const __grid_constant__ CUtensorMap tmO_lo64,
@@ -656,11 +665,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // (plain mode: the first K block's; halo mode: the first three taps'), so only the activations' latency is left after it.
     const int pre_total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
     const int pre_num_kb      = p.ksize * p.ksize * p.cblocks;
-    const int pre_end         = p.sk ? p.sk_dp + 4 * p.sk_ctas : pre_total_tiles * p.ksplit; // one past the last work id
-    const int first_work      = p.sk ? sk_first_work(p, (int) blockIdx.x, pre_end) : (int) blockIdx.x;
+    const int pre_end         = SK ? p.sk_dp + 4 * p.sk_ctas : pre_total_tiles * p.ksplit; // one past the last work id
+    const int first_work      = SK ? sk_first_work(p, (int) blockIdx.x, pre_end) : (int) blockIdx.x;
     const bool pre_b          = (p.ablate & (2 | 16)) == 0 && first_work < pre_end; // ablate 16: no early weight loads (results stay correct)
     if (warp == 0 && pre_b && elect_one()) {
-        const WorkItem w0 = decode_work(p, first_work, pre_total_tiles, pre_num_kb);
+        const WorkItem w0 = decode_work<SK>(p, first_work, pre_total_tiles, pre_num_kb);
         const int tile    = w0.tile;
         const int oc0  = (tile / (p.tiles_x * p.tiles_y * p.tiles_n)) * p.n_blk;
         const uint32_t b_lo_off = (uint32_t) p.n_blk * 128u;
@@ -693,7 +702,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int m_tiles     = p.tiles_x * p.tiles_y * p.tiles_n;
     const int total_tiles = m_tiles * p.tiles_oc;
     const int num_kb      = p.ksize * p.ksize * p.cblocks;
-    const int total_work  = p.sk ? p.sk_dp + 4 * p.sk_ctas : total_tiles * p.ksplit; // work item = (tile, K range); one past the last work id
+    const int total_work  = SK ? p.sk_dp + 4 * p.sk_ctas : total_tiles * p.ksplit; // work item = (tile, K range); one past the last work id
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -725,14 +734,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 // round trip in front of every item's first load - the producer's whole run-ahead margin (r02 trace: first load 2.3-5.4 k clk
                 // after kernel entry, ~1.3 k clk of bubble at every tile boundary).
                 int drawn = 0;
-                if (!p.sk && elect_one()) drawn = atomicAdd(p.sched_counter, 1);
+                if (!SK && elect_one()) drawn = atomicAdd(p.sched_counter, 1);
                 auto take_next = [&]() { // consumes the draw: next work id for all lanes; the launch's last draw re-zeroes the counter
-                    if (p.sk) return sk_next_work(p, work, (int) blockIdx.x, (int) gridDim.x, num_kb, total_work); // static schedule
+                    if constexpr (SK) return sk_next_work(p, work, (int) blockIdx.x, (int) gridDim.x, num_kb, total_work); // static schedule
                     const int c = __shfl_sync(0xffffffffu, drawn, 0); // elect.sync picks lane 0 of the converged warp
                     if (lane == 0 && c == draws_total - 1) *p.sched_counter = 0;
                     return (int) gridDim.x + c;
                 };
-                const WorkItem wi = decode_work(p, work, total_tiles, num_kb);
+                const WorkItem wi = decode_work<SK>(p, work, total_tiles, num_kb);
                 const int tile = wi.tile;
                 const int m_idx = tile % m_tiles, oc_idx = tile / m_tiles;
                 const int bx = m_idx % p.tiles_x, by = (m_idx / p.tiles_x) % p.tiles_y, bn = m_idx / (p.tiles_x * p.tiles_y);
@@ -917,7 +926,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     umma_commit(tmem_full_bar(acc)); // accumulator complete -> epilogue
                     continue;
                 }
-                const WorkItem wi = decode_work(p, work, total_tiles, num_kb);
+                const WorkItem wi = decode_work<SK>(p, work, total_tiles, num_kb);
                 const int kb0 = wi.kb0, kb1 = wi.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!ready) mbar_wait(full_bar(stage), phase); // TMA bytes have landed
@@ -995,7 +1004,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (;; ++it) {
             const int work = sched_take(it, lane == 0);
             if (work >= total_work) break;
-            const WorkItem wi = decode_work(p, work, total_tiles, num_kb);
+            const WorkItem wi = decode_work<SK>(p, work, total_tiles, num_kb);
             const int tile = wi.tile;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t) (it >> 1) & 1u;
@@ -1016,7 +1025,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 continue;
             }
             if (wi.pieces > 1) {
-                float* tile_parts = p.partials + (size_t) wi.slot * (p.sk ? 4 : p.ksplit) * (UM_BLOCK_M * p.n_blk);
+                float* tile_parts = p.partials + (size_t) wi.slot * (SK ? 4 : p.ksplit) * (UM_BLOCK_M * p.n_blk);
                 epilogue_dump_partial<UM_EPI_WARPS, EPI_TERMS>(e, taddr, tile_parts + (size_t) wi.piece * (UM_BLOCK_M * p.n_blk), row, half, lane);
                 __threadfence(); // partial tile visible device-wide before the arrival is counted
                 named_bar_sync(1, UM_EPI_WARPS * 32);
@@ -1117,6 +1126,12 @@ struct RowWinParams {
     // 5-deep ring ran the 7x7 stem at one stage per ~560 clk whatever the stage's own work was (profiles/r02_stem_ablation.txt).
     int stages;
     uint32_t stage_bytes, lo_off, b_bytes;
+    // FEED mode: a stage holds `rows_per_stage` filter rows (row_bytes each: hi segment, lo segment), released by ONE tcgen05.commit -
+    // a commit costs the issuing thread ~52 clk and a stage boundary ~100 more, against 224 clk of MMAs per filter row of the 7x7 stem
+    int rows_per_stage;
+    uint32_t row_bytes;
+    int stg_bufs; // epilogue staging buffers (2: alternate tiles, see EpiArgs::two_stagings)
+    int feed_prows; // feed mode: 128-byte weight rows per output channel = ceil(kh / FeedPlan::rows_per_panel)
 };
 
 // SWIZZLE_NONE K-major descriptor with an overlapping K stride: LBO = 16 B (next chunk = next pixel), SBO = 128 B
@@ -1136,7 +1151,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB = smem_base; // weight panel: per kernel row ky, [n_blk rows of B_hi ; n_blk rows of B_lo] x 128 B
     const uint32_t stg      = smem_base + p.b_bytes; // epilogue staging (1024-aligned)
-    const uint32_t sA0      = stg + UM_STG_BYTES;
+    const uint32_t sA0      = stg + (uint32_t) p.stg_bufs * UM_STG_BYTES;
     const uint32_t bar_base = sA0 + (uint32_t) p.stages * p.stage_bytes;
     const int RW_STAGES     = p.stages;
     auto full_bar       = [&](int s) { return bar_base + 8u * s; };
@@ -1185,7 +1200,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         {
             // weight panel: once per CTA
             if (elect_one()) {
-                const int vrows = p.kh * p.panels; // (filter row, panel)
+                const int vrows = FKS > 0 ? p.feed_prows : p.kh * p.panels; // (filter row, panel); feed mode: several filter rows per weight row
                 mbar_expect_tx(b_bar, (TERMS == 3 ? 2u : 1u) * (uint32_t) vrows * (uint32_t) p.n_blk * 128u);
                 for (int v = 0; v < vrows; ++v) {
                     if (TERMS == 3) {
@@ -1213,19 +1228,25 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     const size_t off = (((size_t) n * p.feed_h + (oy * 2 - p.pad_y + p.feed_py)) * p.feed_w + 2 * xt * UM_BLOCK_M) * 4;
                     const __half* src_hi = p.feed_hi + off;
                     const __half* src_lo = p.feed_lo + off;
-                    for (int ky = 0; ky < p.kh; ++ky) {
+                    for (int ky0 = 0; ky0 < p.kh; ky0 += p.rows_per_stage) {
+                        const int rows = min(p.rows_per_stage, p.kh - ky0); // this stage's group of filter rows
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         if (elect_one()) {
                             if (p.ablate & 2) {
                                 mbar_arrive(full_bar(stage));
                             } else {
-                                mbar_expect_tx(full_bar(stage), tx_bytes);
-                                bulk_load_1d(sA, src_hi, seg, full_bar(stage));
-                                if (TERMS >= 2) bulk_load_1d(sA + RW_ARR_BYTES, src_lo, seg, full_bar(stage));
+                                mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t) rows);
+                                const __half* sh = src_hi;
+                                const __half* sl = src_lo;
+                                uint32_t dst     = sA;
+                                for (int r = 0; r < rows; ++r, dst += p.row_bytes, sh += pitch, sl += pitch) {
+                                    bulk_load_1d(dst, sh, seg, full_bar(stage));
+                                    if (TERMS >= 2) bulk_load_1d(dst + RW_ARR_BYTES, sl, seg, full_bar(stage));
+                                }
                             }
                         }
                         __syncwarp();
-                        src_hi += pitch, src_lo += pitch;
+                        src_hi += pitch * rows, src_lo += pitch * rows;
                         sA += p.stage_bytes;
                         if (++stage == RW_STAGES) stage = 0, phase ^= 1u, sA = sA0;
                     }
@@ -1281,7 +1302,8 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
             if constexpr (FKS > 0) {
                 // FEED mode: K step q of a stage = window start + 2 q pixels pairs (32 B), weights columns 16 q ..; everything a constant offset
                 constexpr uint32_t LO16 = RW_ARR_BYTES >> 4;
-                const uint32_t stage16  = p.stage_bytes >> 4;
+                constexpr int RPP       = FKS == 1 ? 4 : (FKS == 2 ? 2 : 1); // FeedPlan::rows_per_panel
+                const uint32_t stage16  = p.stage_bytes >> 4, row16 = p.row_bytes >> 4;
                 const bool tracing      = p.trace != nullptr && blockIdx.x == 0;
                 uint64_t a_cur = wdesc0;
                 for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -1290,30 +1312,38 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t) (acc * 2 * RW_MAX_N);
                     uint64_t b_cat = bdesc0;
-                    for (int ky = 0; ky < p.kh; ++ky, b_cat += b_ky) {
+                    int b_sub      = 0;
+                    for (int ky0 = 0; ky0 < p.kh; ky0 += p.rows_per_stage) {
+                        const int rows = min(p.rows_per_stage, p.kh - ky0); // the group of filter rows this stage holds
                         if (!ready) mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         if (tracing && tr < 256) p.trace[1 * 256 + tr] = clock64();
-                        if (!no_mma) {
-                            umma_f16(d_tmem, a_cur, b_cat, idesc_cat, ky > 0 ? 1u : 0u);
+                        if (!no_mma) { // first K step of the group, then the look-ahead test, then the rest
+                            umma_f16(d_tmem, a_cur, b_cat, idesc_cat, ky0 > 0 ? 1u : 0u);
                             if (TERMS >= 2) umma_f16(d_tmem, a_cur + LO16, b_cat, idesc, 1u);
                         }
                         const int cur        = stage;
                         const bool wrap      = stage == RW_STAGES - 1;
-                        const uint64_t a_now = a_cur;
+                        uint64_t a_row       = a_cur;
                         phase ^= wrap ? 1u : 0u;
                         stage = wrap ? 0 : stage + 1;
                         a_cur = wrap ? wdesc0 : a_cur + stage16;
                         ready = mbar_test_wait(full_bar(stage), phase); // look-ahead, overlaps with the MMAs already queued
-                        if (!no_mma) {
+                        for (int r = 0; r < rows; ++r, a_row += row16) {
+                            // weights of the next filter row: the next K-column group of the same 128-byte rows, or the next panel
+                            const uint64_t b_now = b_cat;
+                            if (++b_sub == RPP) b_sub = 0, b_cat += b_panel - (RPP - 1) * (8 / RPP);
+                            else b_cat += 8 / RPP;
+                            if (no_mma) continue;
 #pragma unroll
-                            for (int q = 1; q < FKS; ++q) {
-                                umma_f16(d_tmem, a_now + 2u * q, b_cat + 2u * q, idesc_cat, 1u);
-                                if (TERMS >= 2) umma_f16(d_tmem, a_now + LO16 + 2u * q, b_cat + 2u * q, idesc, 1u);
+                            for (int q = 0; q < FKS; ++q) {
+                                if (r == 0 && q == 0) continue; // issued above
+                                umma_f16(d_tmem, a_row + 2u * q, b_now + 2u * q, idesc_cat, 1u);
+                                if (TERMS >= 2) umma_f16(d_tmem, a_row + LO16 + 2u * q, b_now + 2u * q, idesc, 1u);
                             }
                         }
                         umma_commit(empty_bar(cur));
-                        if (ky == p.kh - 1) umma_commit(tmem_full_bar(acc));
+                        if (ky0 + rows == p.kh) umma_commit(tmem_full_bar(acc));
                         if (tracing && tr < 256) p.trace[2 * 256 + tr] = clock64();
                         ++tr;
                     }
@@ -1370,6 +1400,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
         e.stg = stg, e.res_bar = 0, e.bar_id = 1;
         e.part_src = nullptr, e.part_splits = 0;
         e.no_store = (p.ablate & 8) != 0;
+        e.two_stagings = p.stg_bufs == 2;
         uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -1388,6 +1419,7 @@ conv_rowwin_kernel(const __grid_constant__ CUtensorMap tmA_hi0, const __grid_con
                 if (lane == 0) mbar_arrive(e.tmem_empty);
                 continue;
             }
+            e.stg = stg + (uint32_t) ((it & 1) & (p.stg_bufs - 1)) * UM_STG_BYTES;
             epilogue_tile<RW_EPI_WARPS, TERMS>(e, taddr, 0, xt * UM_BLOCK_M, oy, n, row, half, warp == 2, lane, res_phase);
             if (warp == 2) UM_TRACE(4, it);
         }
@@ -1612,8 +1644,8 @@ static bool rowwin_supported(const ConvArgs& a) {
           a.residual == nullptr && make_row_plan(a.k, a.stride, a.pad_x, rp) && 128 + rp.span <= RW_BOXW))
         return false;
     FeedPlan fp;
-    const int panels = feed_usable(a, fp) ? 1 : (rp.ksteps + 3) / 4;
-    return a.k * panels * 2 * round_up(a.out->c, 16) * 128 <= RW_B_MAX_BYTES;
+    const int wrows = feed_usable(a, fp) ? (a.k + fp.rows_per_panel - 1) / fp.rows_per_panel : a.k * ((rp.ksteps + 3) / 4); // 128-byte weight rows per channel
+    return wrows * 2 * round_up(a.out->c, 16) * 128 <= RW_B_MAX_BYTES;
 }
 
 bool conv2d_umma_supported(const ConvArgs& a) {
@@ -1680,9 +1712,18 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     p.feed_seg_bytes = feed ? (uint32_t) (254 + 2 * fp.nch) * 8u : 0u;
     const int terms = conv_terms(ctx, a);
     p.lo_off      = (uint32_t) p.parities * RW_ARR_BYTES;
-    p.stage_bytes = (terms == 1 ? 1u : 2u) * p.lo_off;
-    p.b_bytes     = (uint32_t) round_up((terms == 3 ? 2 : 1) * a.k * p.panels * p.n_blk * 128, 1024);
-    p.stages      = std::min(RW_MAX_STAGES, (int) ((RW_SMEM_BYTES - 1024 - RW_BAR_BYTES - UM_STG_BYTES - (int) p.b_bytes) / (int) p.stage_bytes));
+    p.row_bytes   = (terms == 1 ? 1u : 2u) * p.lo_off;
+    // feed mode: ceil(kh / 4) groups of filter rows, as even as possible (7 -> 4 + 3, 3 -> 3, 9 -> 3 + 3 + 3)
+    static const int one_row = getenv("SNNB_FEED_ONE_ROW") != nullptr;
+    p.rows_per_stage = (feed && !one_row) ? (a.k + (a.k + 3) / 4 - 1) / ((a.k + 3) / 4) : 1;
+    p.stage_bytes    = (uint32_t) p.rows_per_stage * p.row_bytes;
+    p.feed_prows  = feed ? (a.k + fp.rows_per_panel - 1) / fp.rows_per_panel : 0;
+    p.b_bytes     = (uint32_t) round_up((terms == 3 ? 2 : 1) * (feed ? p.feed_prows : a.k * p.panels) * p.n_blk * 128, 1024);
+    // a second staging buffer when the ring keeps >= 2 stages beside it (one slab per tile: n_blk <= 64 always holds here)
+    static const int one_stg = getenv("SNNB_ROWWIN_ONE_STAGING") != nullptr;
+    const int ring_room      = RW_SMEM_BYTES - 1024 - RW_BAR_BYTES - (int) p.b_bytes;
+    p.stg_bufs    = (!one_stg && (ring_room - 2 * UM_STG_BYTES) / (int) p.stage_bytes >= 2) ? 2 : 1;
+    p.stages      = std::min(RW_MAX_STAGES, (ring_room - p.stg_bufs * UM_STG_BYTES) / (int) p.stage_bytes);
     SNNB_REQUIRE(p.stages >= 2, "launch_conv2d_rowwin: weight panels of %u bytes leave no room for the activation ring", p.b_bytes);
 
     // A: per plane and column parity a 4-D view (8 ch | de-interleaved pixel index | row | image) of the NHWC plane
@@ -1701,7 +1742,7 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
             SNNB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, rowwin) failed: %d", (int) r);
         }
     {
-        const cuuint64_t dims[2]    = {64, (cuuint64_t) a.k * p.panels * a.w->ocr}; // [ky][panel][OCr] rows of 64 K columns
+        const cuuint64_t dims[2]    = {64, (cuuint64_t) (feed ? (a.k + fp.rows_per_panel - 1) / fp.rows_per_panel : a.k * p.panels) * a.w->ocr}; // [ky][panel][OCr] rows of 64 K columns
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2]     = {64, (cuuint32_t) p.n_blk};
         const cuuint32_t estr[2]    = {1, 1};
@@ -1855,6 +1896,9 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<HL_B_STAGES, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<HL_B_STAGES, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
         SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<HL_B_STAGES, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+        SNNB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<UM_STAGES, false, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
         ctx->func_attr_mask |= ATTR_UMMA;
     }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_oc;
@@ -1867,7 +1911,9 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     p.trace = nullptr;
     if (trace_enabled() && trace_begin(ctx, &p.trace)) return 1;
     auto* k_split = terms == 3 ? conv_umma_kernel<UM_STAGES - 1, true, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES - 1, true, 2, false> : conv_umma_kernel<UM_STAGES - 1, true, 1, false>);
-    auto* k_plain = terms == 3 ? conv_umma_kernel<UM_STAGES, false, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES, false, 2, false> : conv_umma_kernel<UM_STAGES, false, 1, false>);
+    auto* k_plain = p.sk ? (terms == 3 ? conv_umma_kernel<UM_STAGES, false, 3, false, true>
+                                       : (terms == 2 ? conv_umma_kernel<UM_STAGES, false, 2, false, true> : conv_umma_kernel<UM_STAGES, false, 1, false, true>) )
+                         : (terms == 3 ? conv_umma_kernel<UM_STAGES, false, 3, false> : (terms == 2 ? conv_umma_kernel<UM_STAGES, false, 2, false> : conv_umma_kernel<UM_STAGES, false, 1, false>) );
     auto* k_halo  = terms == 3 ? conv_umma_kernel<HL_B_STAGES, false, 3, true> : (terms == 2 ? conv_umma_kernel<HL_B_STAGES, false, 2, true> : conv_umma_kernel<HL_B_STAGES, false, 1, true>);
     const cudaError_t le =
         halo      ? launch_k_pdl(k_halo, dim3(grid), dim3(UM_THREADS), HL_SMEM_BYTES, ctx->stream, tmA[0], tmA[1], tmB[0], tmB[1], tmO64[0], tmO64[1], tmOT[0], tmOT[1], tmR64[0],

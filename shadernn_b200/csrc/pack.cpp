@@ -110,8 +110,9 @@ void pack_feed_host(PackedHost& p, int stride, int pad_x) {
     if (p.kind != 1 || p.out_ch > 64 || p.w_row_hi.empty() || !make_feed_plan(p.kernel, stride, pad_x, p.in_ch, fp)) return;
     const int k = p.kernel, IC = p.in_ch, OC = p.out_ch;
     p.feed_pad = pad_x;
-    p.w_feed_hi.assign((size_t) k * p.ocr * 64, __float2half_rn(0.0f));
-    p.w_feed_lo.assign((size_t) k * p.ocr * 64, __float2half_rn(0.0f));
+    const int rpp = fp.rows_per_panel, prows = (k + rpp - 1) / rpp, sub = 64 / rpp; // filter rows per 128-byte weight row, K columns each
+    p.w_feed_hi.assign((size_t) prows * p.ocr * 64, __float2half_rn(0.0f));
+    p.w_feed_lo.assign((size_t) prows * p.ocr * 64, __float2half_rn(0.0f));
     for (int ky = 0; ky < k; ++ky)
         for (int o = 0; o < OC; ++o)
             for (int off = 0; off < 2 * fp.nch; ++off) { // pixel offset within the window = chunk off / 2, pixel off % 2
@@ -119,7 +120,7 @@ void pack_feed_host(PackedHost& p, int stride, int pad_x) {
                 if (t < 0 || t >= k) continue;
                 for (int c = 0; c < IC; ++c) {
                     const float wv   = p.w_f32[(size_t) ((ky * k + t) * IC + c) * p.ocw + o]; // BN already folded in
-                    const size_t idx = ((size_t) ky * p.ocr + o) * 64 + off * 4 + c;
+                    const size_t idx = ((size_t) (ky / rpp) * p.ocr + o) * 64 + (ky % rpp) * sub + off * 4 + c;
                     const __half hh  = __float2half_rn(wv);
                     p.w_feed_hi[idx] = hh;
                     p.w_feed_lo[idx] = __float2half_rn(wv - __half2float(hh));

@@ -264,6 +264,10 @@ static inline bool make_row_plan(int k, int stride, int pad_x, RowPlan& rp) {
 // the filter sits at pixel offset d + t, d = px - pad_x in {0, 1}; offsets without a tap get zero weights.
 struct FeedPlan {
     int px = 0, d = 0, nch = 0, ksteps = 0; // nch = 16-byte chunks per window (even), ksteps = nch / 2
+    // A filter row needs only 16 * ksteps of the 64 K columns of a 128-byte weight row: rows_per_panel filter rows share one
+    // (filter row ky -> panel row ky / rows_per_panel, columns (ky % rows_per_panel) * 64 / rows_per_panel ..), so the resident weight
+    // panels of the 7x7 stem take 64 KB instead of 112 KB of shared memory.
+    int rows_per_panel = 1;
 };
 static inline bool make_feed_plan(int k, int stride, int pad_x, int ic, FeedPlan& fp) {
     if (stride != 2 || ic > 4 || k < 2 || k > 9 || pad_x < 0 || pad_x > 8) return false;
@@ -271,6 +275,7 @@ static inline bool make_feed_plan(int k, int stride, int pad_x, int ic, FeedPlan
     fp.d      = fp.px - pad_x;
     fp.nch    = ((fp.d + k + 1) / 2 + 1) & ~1;
     fp.ksteps = fp.nch / 2;
+    fp.rows_per_panel = fp.ksteps == 1 ? 4 : (fp.ksteps == 2 ? 2 : 1);
     return fp.ksteps <= 4;
 }
 
@@ -279,7 +284,7 @@ struct PackedHost {
     std::vector<__half> w_hi, w_lo; // [OCr][Kp]
     std::vector<__half> w_row_hi, w_row_lo; // [kh][OCr][64] (row-window kernel), empty unless IC <= 8
     int row_stride = 0, row_pad = 0;
-    std::vector<__half> w_feed_hi, w_feed_lo; // [kh][OCr][64] in FeedPlan K order (stride-2 stems with <= 4 input channels)
+    std::vector<__half> w_feed_hi, w_feed_lo; // [ceil(kh / rows_per_panel)][OCr][64] in FeedPlan K order (stride-2 stems with <= 4 input channels)
     int feed_pad = -1;
     std::vector<float> bias;            // [round_up(OC,64)]
     std::vector<float> gamma, beta, mean, var;
