@@ -423,7 +423,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr, 
                             }
                         }
                     }
-                    if (fast_act) {
+                    if (e.act == SNNB_ACT_RELU) { // the common cases one instruction per element (the epilogue is issue-bound on short-K layers)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    } else if (e.act == SNNB_ACT_NONE) {
+                    } else if (e.act == SNNB_ACT_RELU6) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 6.0f);
+                    } else if (fast_act) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], v[j] * slope), hi_clip);
                     } else {
