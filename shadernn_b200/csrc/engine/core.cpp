@@ -298,6 +298,24 @@ bool MixedInferenceCore::init(std::string& err) {
         }
     }
 
+    // input tensors whose ONLY readers are feed-mode stems need no regular planes (snnb_tensor::feed_only)
+    for (auto* in : inputLayers) {
+        snnb_tensor* t = in->output;
+        if (!t || !t->feed_hi || getenv("SNNB_NO_FEED_ONLY")) continue;
+        bool only = true;
+        int readers = 0;
+        for (auto* L : graph.sorted) {
+            if (L->fusedAway || L->isInputLayer) continue;
+            const bool reads = std::find(L->inputs.begin(), L->inputs.end(), t) != L->inputs.end() || L->residual == t;
+            if (!reads) continue;
+            ++readers;
+            only = only && L->typeName == "Conv2D" && static_cast<Conv2DLayer*>(L)->feedInput && L->inputs.size() >= 1 && L->inputs[0] == t && L->residual != t &&
+                   std::count(L->inputs.begin(), L->inputs.end(), t) == 1;
+        }
+        for (auto* o : outputLayers) only = only && o->output != t; // a model that returns its input
+        t->feed_only = only && readers > 0;
+    }
+
     // ---- weights: fold + pack on the host, then ONE device arena (broadcastable with a single NCCL call) ----
     std::vector<std::pair<GenericModelLayer*, PackedHost>> packed;
     size_t total = 0, scratchTotal = 0;

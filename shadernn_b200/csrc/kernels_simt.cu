@@ -63,7 +63,19 @@ struct FeedV { // the compact 4-channel copy of a model input (snnb_tensor::feed
     __half* hi;
     __half* lo;
     int H, W, py, px;
+    int only; // snnb_tensor::feed_only: the regular planes are neither written nor read
 };
+// channels 0..3 of image pixel `pix` back from the stem feed
+__device__ __forceinline__ void load_feed(const FeedV& f, size_t pix, int H, int W, float v[8]) {
+    const int x = (int) (pix % W), y = (int) ((pix / W) % H);
+    const size_t n = pix / ((size_t) W * H);
+    const size_t off = ((n * f.H + y + f.py) * f.W + x + f.px) * 4;
+    const uint2 h = *reinterpret_cast<const uint2*>(f.hi + off);
+    const uint2 l = f.lo ? *reinterpret_cast<const uint2*>(f.lo + off) : make_uint2(0u, 0u);
+    const float2 h0 = h2_to_f2(h.x), h1 = h2_to_f2(h.y), l0 = h2_to_f2(l.x), l1 = h2_to_f2(l.y);
+    v[0] = h0.x + l0.x, v[1] = h0.y + l0.y, v[2] = h1.x + l1.x, v[3] = h1.y + l1.y;
+    v[4] = v[5] = v[6] = v[7] = 0.0f;
+}
 // channels 0..3 of image pixel `pix` (linear n, y, x index of a tensor H x W) into the stem feed (C <= 4: one thread per pixel)
 __device__ __forceinline__ void store_feed(const FeedV& f, size_t pix, int H, int W, const float v[8]) {
     const int x = (int) (pix % W), y = (int) ((pix / W) % H);
@@ -121,7 +133,7 @@ struct TV { // kernel-side tensor view
     int N, H, W, C, Cp;
 };
 static TV view(const snnb_tensor* t) { return TV {t->hi, t->lo, t->n, t->h, t->w, t->c, t->cp}; }
-static FeedV feed_view(const snnb_tensor* t) { return FeedV {t->feed_hi, t->feed_lo, t->feed_h, t->feed_w, t->feed_py, t->feed_px}; }
+static FeedV feed_view(const snnb_tensor* t) { return FeedV {t->feed_hi, t->feed_lo, t->feed_h, t->feed_w, t->feed_py, t->feed_px, t->feed_only ? 1 : 0}; }
 
 #define SNNB_LAUNCH_CHECK(ctx)                                                                          \
     do {                                                                                                \
@@ -1090,7 +1102,7 @@ __global__ void split_kernel(const float* __restrict__ src, TV t, FeedV f) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? __ldg(src + px * t.C + c + j) : 0.0f;
-    store8(t.hi, t.lo, gid * 8, v);
+    if (!f.only) store8(t.hi, t.lo, gid * 8, v);
     if (f.hi) store_feed(f, px, t.H, t.W, v);
 }
 // u8 image (dense pitch C) -> (x - mean[c]) * norm[c] -> split-fp16: the reference's convertToRGBA32FAndNormalize
@@ -1109,10 +1121,10 @@ __global__ void split_u8_kernel(const uint8_t* __restrict__ src, TV t, U8Norm q,
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? ((float) __ldg(src + px * t.C + c + j) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3] : 0.0f;
-    store8(t.hi, t.lo, gid * 8, v);
+    if (!f.only) store8(t.hi, t.lo, gid * 8, v);
     if (f.hi) store_feed(f, px, t.H, t.W, v);
 }
-__global__ void merge_kernel(TV t, float* __restrict__ dst) {
+__global__ void merge_kernel(TV t, float* __restrict__ dst, FeedV f) {
     pdl_wait();
     const size_t total = (size_t) t.N * t.H * t.W * (t.Cp >> 3);
     const size_t gid   = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1121,7 +1133,8 @@ __global__ void merge_kernel(TV t, float* __restrict__ dst) {
     const size_t px = gid / CG;
     const int c     = (int) (gid % CG) * 8;
     float v[8];
-    load8(t.hi, t.lo, gid * 8, v);
+    if (f.only) load_feed(f, px, t.H, t.W, v); // C <= 4: one vector per pixel
+    else load8(t.hi, t.lo, gid * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         if (c + j < t.C) dst[px * t.C + c + j] = v[j];
@@ -1175,7 +1188,7 @@ __global__ void resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (c + j < t.C) ? ((float) __ldg(img + ((size_t) y0 * sw + x0) * t.C + c + j) - q.mean[(c + j) & 3]) * q.norm[(c + j) & 3] : 0.0f;
     }
-    store8(t.hi, t.lo, gid * 8, v);
+    if (!f.only) store8(t.hi, t.lo, gid * 8, v);
     if (f.hi) store_feed(f, px, t.H, t.W, v);
 }
 int launch_resize_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, int src_h, int src_w, snnb_tensor* t, const float mean[4], const float norm[4], bool linear) {
@@ -1207,7 +1220,7 @@ int launch_merge_u8(snnb_context* ctx, const snnb_tensor* t, uint8_t* dev_nhwc_u
     return 0;
 }
 int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc) {
-    launch_k(merge_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, view(t), dev_nhwc);
+    launch_k(merge_kernel, dim3(vec_blocks(t, 256)), dim3(256), 0, ctx->stream, view(t), dev_nhwc, feed_view(t));
     SNNB_LAUNCH_CHECK(ctx);
     return 0;
 }

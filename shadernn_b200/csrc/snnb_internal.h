@@ -104,6 +104,9 @@ struct snnb_tensor {
     __half* feed_hi = nullptr;
     __half* feed_lo = nullptr;
     int feed_h = 0, feed_w = 0, feed_py = 0, feed_px = 0;
+    // Every consumer of this tensor reads the feed: the input kernels then skip the regular planes (51 of 87 MB written per ResNet-18
+    // batch) and read-backs of the tensor (layer output, dumps) are served from the feed.
+    bool feed_only = false;
     size_t pixels() const { return (size_t) n * h * w; }
 };
 
