@@ -613,7 +613,21 @@ __global__ void __launch_bounds__(GD_THREADS) gap_dense_kernel(TV in, TV out, co
         float part[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) part[k] = 0.0f;
-        for (int c = warp; c < in.C; c += nwarps) {
+        int c = warp;
+        for (; c + 3 * nwarps < in.C; c += 4 * nwarps) { // four weight rows in flight per lane (each an L2 round trip), summed in channel order
+            float wv[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wv[u][k] = (lane + 32 * k < out.C) ? __ldg(w + (size_t) (c + u * nwarps) * ocw + lane + 32 * k) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float xv = xs[c + u * nwarps];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) part[k] = fmaf(xv, wv[u][k], part[k]);
+            }
+        }
+        for (; c < in.C; c += nwarps) {
             const float xv    = xs[c];
             const float* wrow = w + (size_t) c * ocw;
 #pragma unroll

@@ -1957,7 +1957,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
 // Outputs go straight to global memory: a warp writes 4 full 128-byte lines per plane.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DW_THREADS = 256;
-constexpr int DW_STAGES  = 3;
+constexpr int DW_STAGES  = 2;
 template <int S> struct DwTile {
     static constexpr int TW = S == 1 ? 16 : 8, TH = S == 1 ? 8 : 4; // output pixels per tile: 128 / 32
     static constexpr int TXT = S == 1 ? 4 : 1;                      // output columns per thread
@@ -1979,7 +1979,7 @@ struct DwTmaParams {
 };
 
 template <int S>
-__global__ void __launch_bounds__(DW_THREADS, 1) depthwise_tma_kernel(const __grid_constant__ CUtensorMap tmI_hi, const __grid_constant__ CUtensorMap tmI_lo, const DwTmaParams p) {
+__global__ void __launch_bounds__(DW_THREADS, 2) depthwise_tma_kernel(const __grid_constant__ CUtensorMap tmI_hi, const __grid_constant__ CUtensorMap tmI_lo, const DwTmaParams p) {
     using T = DwTile<S>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -2158,7 +2158,7 @@ template <int S> static int launch_depthwise_tma_s(snnb_context* ctx, const Conv
         ctx->func_attr_mask |= attr_bit;
     }
     const long long total = (long long) p.N * p.tiles_y * p.tiles_x * p.chunks;
-    const int grid        = (int) std::min<long long>(total, ctx->sm_count);
+    const int grid        = (int) std::min<long long>(total, 2 * ctx->sm_count); // two CTAs per SM (128 registers, <= 93 KB of shared memory each)
     const cudaError_t le  = launch_k_pdl(depthwise_tma_kernel<S>, dim3(grid), dim3(DW_THREADS), T::SMEM_BYTES, ctx->stream, tmI[0], tmI[1], p);
     cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
     if (e != cudaSuccess) {
