@@ -281,6 +281,10 @@ int snnb_unregister_layer(const char* type_name);
 /* Raw device planes of a tensor for custom kernels: NHWC, channel pitch `cp` (a multiple of 8), fp16 hi plane and lo plane
  * (value = hi + lo; lo is NULL in the half-precision storage mode). */
 int snnb_tensor_planes(const snnb_tensor* t, void** hi, void** lo, int* cp);
+/* Diagnostics: the work decomposition SNNB_ALGO_TCGEN05_STREAMK would use for `tiles` output tiles of `num_kb` K blocks on `sms` SMs,
+ * evaluated on the host with the kernel's own arithmetic. rows = capacity x 6 ints {cta, tile, kb0, kb1, piece, pieces} in each CTA's
+ * order; returns the number of rows (may exceed capacity), -1 when the tile count is a multiple of `sms` or too small to cut. No GPU needed. */
+int snnb_debug_streamk_schedule(int tiles, int num_kb, int sms, int* rows, int capacity);
 
 #ifdef __cplusplus
 }

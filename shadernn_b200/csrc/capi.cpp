@@ -140,6 +140,10 @@ int snnb_tensor_free(snnb_tensor* t) {
     delete t;
     return 0;
 }
+int snnb_debug_streamk_schedule(int tiles, int num_kb, int sms, int* rows, int capacity) {
+    SNNB_REQUIRE(rows || capacity == 0, "snnb_debug_streamk_schedule: null buffer");
+    return streamk_schedule(tiles, num_kb, sms, rows, capacity);
+}
 int snnb_tensor_planes(const snnb_tensor* t, void** hi, void** lo, int* cp) {
     SNNB_REQUIRE(t && hi && lo && cp, "snnb_tensor_planes: null argument");
     *hi = t->hi, *lo = t->lo, *cp = t->cp;

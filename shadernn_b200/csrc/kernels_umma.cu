@@ -543,11 +543,11 @@ struct WorkItem {
     int tile, kb0, kb1, piece, pieces, slot;
 };
 template <bool SK> // compile-time: the stream-K arithmetic (64-bit divisions) stays out of every other instantiation's issue loops
-__device__ __forceinline__ WorkItem decode_work(const UmmaParams& p, int work, int total_tiles, int num_kb) {
+__host__ __device__ __forceinline__ WorkItem decode_work(const UmmaParams& p, int work, int total_tiles, int num_kb) {
     WorkItem w;
     if constexpr (!SK) {
         const int split = work / total_tiles;
-        w.tile = work - split * total_tiles, w.kb0 = split * p.kb_per_split, w.kb1 = min(num_kb, w.kb0 + p.kb_per_split);
+        w.tile = work - split * total_tiles, w.kb0 = split * p.kb_per_split, w.kb1 = w.kb0 + p.kb_per_split < num_kb ? w.kb0 + p.kb_per_split : num_kb;
         w.piece = split, w.pieces = p.ksplit, w.slot = w.tile;
     } else if (work < p.sk_dp) {
         w.tile = work, w.kb0 = 0, w.kb1 = num_kb, w.piece = 0, w.pieces = 1, w.slot = 0;
@@ -557,7 +557,7 @@ __device__ __forceinline__ WorkItem decode_work(const UmmaParams& p, int work, i
         const int jt = (int) (b0 / num_kb) + j; // tile (counted from sk_dp) of the CTA's j-th piece
         const long long t0 = (long long) jt * num_kb, t1 = t0 + num_kb;
         w.tile = p.sk_dp + jt, w.slot = jt;
-        w.kb0 = (int) (max(b0, t0) - t0), w.kb1 = (int) (min(b1, t1) - t0);
+        w.kb0 = (int) ((b0 > t0 ? b0 : t0) - t0), w.kb1 = (int) ((b1 < t1 ? b1 : t1) - t0);
         // CTA holding unit u: ((u + 1) * ctas - 1) / units
         const int c_first = (int) (((t0 + 1) * p.sk_ctas - 1) / p.sk_units), c_last = (int) ((t1 * p.sk_ctas - 1) / p.sk_units);
         w.piece = c - c_first, w.pieces = c_last - c_first + 1;
@@ -567,14 +567,14 @@ __device__ __forceinline__ WorkItem decode_work(const UmmaParams& p, int work, i
 // Static schedule of a stream-K launch: CTA `cta` first works off the pieces of its K-block range, then its whole tiles cta, cta + grid, ...
 // (pieces first: a cut tile's last arriver sums the partials while the other CTAs are busy with whole tiles, not at the very end of the
 // launch with everybody waiting). Returns the work id after `work` (`end` when there is none) / the first one.
-__device__ __forceinline__ int sk_next_work(const UmmaParams& p, int work, int cta, int grid, int num_kb, int end) {
+__host__ __device__ __forceinline__ int sk_next_work(const UmmaParams& p, int work, int cta, int grid, int num_kb, int end) {
     if (work < p.sk_dp) return work + grid < p.sk_dp ? work + grid : end;
     const int c = (work - p.sk_dp) >> 2, j = ((work - p.sk_dp) & 3) + 1;
     const long long b0 = (long long) c * p.sk_units / p.sk_ctas, b1 = (long long) (c + 1) * p.sk_units / p.sk_ctas;
     if (j < 4 && b0 / num_kb + j <= (b1 - 1) / num_kb) return work + 1;
     return cta < p.sk_dp ? cta : end;
 }
-__device__ __forceinline__ int sk_first_work(const UmmaParams& p, int cta, int end) {
+__host__ __device__ __forceinline__ int sk_first_work(const UmmaParams& p, int cta, int end) {
     return cta < p.sk_ctas ? p.sk_dp + 4 * cta : (cta < p.sk_dp ? cta : end);
 }
 
@@ -1553,6 +1553,17 @@ static TilePlan plan_tiles(int N, int OH, int OW, int stride) {
 // another ~7 k clk of ramp-up + last epilogue. A layer takes rounds x that, rounds = ceil(work items / SMs). A narrower
 // n_blk re-reads A for more oc tiles but fills more SMs; splitting K (work item = tile x K range, fp32 partials reduced by
 // the last arriver, +~9 k clk) fills the GPU when a layer has few tiles and a long K (7x7x512: 128 tiles x 72 K blocks).
+// Stream-K split of `tiles` tiles of `num_kb` K blocks over `sms` CTAs: dp whole tiles (full waves), the K blocks of the rest (`units`)
+// in `ctas` equal ranges of at least a third of a tile each, so that no tile is cut into more than 4 pieces. False: nothing to cut.
+static bool streamk_split(long long tiles, int num_kb, int sms, int& dp, long long& units, int& ctas) {
+    dp    = (int) (tiles / sms) * sms;
+    units = (tiles - dp) * num_kb;
+    const int umin = (num_kb + 2) / 3;
+    if (units < umin) return false;
+    ctas = (int) std::min<long long>(sms, units / umin);
+    return true;
+}
+
 struct OcPlan {
     int n_blk = 0, tiles_oc = 0, ksplit = 1, kb_per_split = 0;
     double cost = 1e300; // modelled clocks of the launch
@@ -1598,11 +1609,9 @@ static OcPlan plan_oc_ksplit(int OC, int m_tiles, int rows_used, int tile_w, int
         static const int env_sk = getenv("SNNB_SK") != nullptr;
         const long long tiles = (long long) m_tiles * t;
         if ((stream_k || env_sk) && !no_split && !halo && num_kb >= 6 && tiles % sm_count != 0) {
-            const int dp          = (int) (tiles / sm_count) * sm_count;
-            const long long units = (tiles - dp) * num_kb;
-            const int umin        = (num_kb + 2) / 3; // >= a third of a tile per CTA: no tile in more than 4 pieces
-            if (units >= umin) {
-                const int ctas    = (int) std::min<long long>(sm_count, units / umin);
+            int dp = 0, ctas = 0;
+            long long units = 0;
+            if (streamk_split(tiles, num_kb, sm_count, dp, units, ctas)) {
                 const double u    = std::ceil((double) units / ctas);
                 const double cost = (double) (dp / sm_count) * (num_kb * kb_cost + 7000.0) + u * kb_cost + 7000.0 + 4000.0;
                 if (cost < best_cost * 0.95 - 1e-9)
@@ -2173,6 +2182,29 @@ int launch_depthwise_tma(snnb_context* ctx, const ConvArgs& a) {
     EncodeTiledFn encode = get_encode(ctx);
     SNNB_REQUIRE(encode, "launch_depthwise_tma: cuTensorMapEncodeTiled is unavailable in this driver");
     return a.stride == 1 ? launch_depthwise_tma_s<1>(ctx, a, encode) : launch_depthwise_tma_s<2>(ctx, a, encode);
+}
+
+// The stream-K schedule exactly as the kernel's roles derive it (decode_work / sk_first_work / sk_next_work run on the host here), one row
+// {cta, tile, kb0, kb1, piece, pieces} per work item in each CTA's order: lets the CPU test suite check the integer arithmetic
+// (coverage, piece numbering, balance) without a GPU. Returns the number of rows, or -1 when nothing would be cut.
+int streamk_schedule(int tiles, int num_kb, int sms, int* rows, int capacity) {
+    UmmaParams p {};
+    int dp = 0, ctas = 0;
+    long long units = 0;
+    if (tiles <= 0 || num_kb <= 0 || sms <= 0 || tiles % sms == 0 || !streamk_split(tiles, num_kb, sms, dp, units, ctas)) return -1;
+    p.sk = 1, p.sk_dp = dp, p.sk_ctas = ctas, p.sk_units = units, p.ksplit = 1, p.kb_per_split = num_kb;
+    const int grid = dp > 0 ? sms : ctas, end = dp + 4 * ctas;
+    int n = 0;
+    for (int cta = 0; cta < grid; ++cta)
+        for (int work = sk_first_work(p, cta, end); work < end; work = sk_next_work(p, work, cta, grid, num_kb, end)) {
+            const WorkItem w = decode_work<true>(p, work, tiles, num_kb);
+            if (n < capacity) {
+                int* r = rows + 6 * (size_t) n;
+                r[0] = cta, r[1] = w.tile, r[2] = w.kb0, r[3] = w.kb1, r[4] = w.piece, r[5] = w.pieces;
+            }
+            ++n;
+        }
+    return n;
 }
 
 } // namespace snnb

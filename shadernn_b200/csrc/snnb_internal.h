@@ -192,6 +192,7 @@ struct ConvArgs {
 int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a);
 int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a); // kernels_umma.cu (tcgen05 + TMA)
 bool conv2d_umma_supported(const ConvArgs& a);
+int streamk_schedule(int tiles, int num_kb, int sms, int* rows, int capacity); // host evaluation of the stream-K work decomposition (tests)
 int launch_depthwise(snnb_context* ctx, const ConvArgs& a);
 bool depthwise_tma_supported(const ConvArgs& a);          // 3x3 stride 1/2: TMA-staged, register-tiled (kernels_umma.cu)
 int launch_depthwise_tma(snnb_context* ctx, const ConvArgs& a);
