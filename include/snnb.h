@@ -285,6 +285,11 @@ int snnb_tensor_planes(const snnb_tensor* t, void** hi, void** lo, int* cp);
  * evaluated on the host with the kernel's own arithmetic. rows = capacity x 6 ints {cta, tile, kb0, kb1, piece, pieces} in each CTA's
  * order; returns the number of rows (may exceed capacity), -1 when the tile count is a multiple of `sms` or too small to cut. No GPU needed. */
 int snnb_debug_streamk_schedule(int tiles, int num_kb, int sms, int* rows, int capacity);
+/* Diagnostics: the K layout of the stem kernel's feed mode for a k x k stride-`stride` convolution with `ic` input channels and x padding
+ * `pad_x`: out = {px (left margin of the compact input copy), d (pixel offset of tap 0 in the window), nch (16-byte chunks per window),
+ * ksteps (K = 16 steps per filter row), rows_per_panel (filter rows sharing one 128-byte weight row)}. Returns 1 if the layer can use
+ * the feed mode, 0 if not. No GPU needed. */
+int snnb_debug_feed_plan(int k, int stride, int pad_x, int ic, int out[5]);
 
 #ifdef __cplusplus
 }

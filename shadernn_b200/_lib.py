@@ -143,6 +143,7 @@ SIGNATURES = {
     "snnb_layer_json_numbers": (C.c_int, [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_size_t)]),
     "snnb_tensor_planes": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), c_int_p]),
     "snnb_debug_streamk_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, C.c_int]),
+    "snnb_debug_feed_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_int_p]),
 }
 
 _lib = None

@@ -140,6 +140,12 @@ int snnb_tensor_free(snnb_tensor* t) {
     delete t;
     return 0;
 }
+int snnb_debug_feed_plan(int k, int stride, int pad_x, int ic, int out[5]) {
+    FeedPlan fp;
+    if (!out || !make_feed_plan(k, stride, pad_x, ic, fp)) return 0;
+    out[0] = fp.px, out[1] = fp.d, out[2] = fp.nch, out[3] = fp.ksteps, out[4] = fp.rows_per_panel;
+    return 1;
+}
 int snnb_debug_streamk_schedule(int tiles, int num_kb, int sms, int* rows, int capacity) {
     SNNB_REQUIRE(rows || capacity == 0, "snnb_debug_streamk_schedule: null buffer");
     return streamk_schedule(tiles, num_kb, sms, rows, capacity);

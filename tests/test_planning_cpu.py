@@ -1,4 +1,4 @@
-"""CPU test of the stream-K work decomposition (csrc/kernels_umma.cu: streamk_split / decode_work / sk_first_work / sk_next_work),
+"""CPU tests of the launch planning arithmetic. (1) The stream-K work decomposition (csrc/kernels_umma.cu: streamk_split / decode_work / sk_first_work / sk_next_work),
 evaluated on the host through snnb_debug_streamk_schedule with the very functions the kernel's roles call: every K block of every
 tile is computed exactly once, a cut tile's pieces are numbered 0 .. pieces-1 in K order with pieces <= 4 (the reducer's limit), every
 CTA walks its pieces before its whole tiles, and the cut ranges are balanced to one K block."""
@@ -54,3 +54,31 @@ def test_streamk_schedule_covers_every_k_block_once(tiles, num_kb, sms):
 def test_streamk_declines_when_there_is_nothing_to_cut():
     assert schedule(296, 18, 148) is None   # whole waves only
     assert lib().snnb_debug_streamk_schedule(0, 18, 148, None, 0) == -1
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("pad_x", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("ic", [1, 3, 4])
+def test_feed_plan_invariants(k, pad_x, ic):
+    # FeedPlan (csrc/snnb_internal.h): the window of output pixel m starts at pixel 2 m of the compact copy, whose image is shifted right by
+    # px; tap t sits at window pixel d + t. What the kernel and the packer rely on:
+    out = (C.c_int * 5)()
+    ok = lib().snnb_debug_feed_plan(k, 2, pad_x, ic, out)
+    px, d, nch, ksteps, rpp = list(out)
+    if not ok:
+        assert (k + (pad_x & 1) + 1) // 2 > 8  # only windows that need more than four K steps are refused for stride 2, ic <= 4
+        return
+    assert px % 2 == 0 and px >= pad_x and d == px - pad_x and d in (0, 1)   # 16-byte chunks start on even pixels
+    assert nch % 2 == 0 and 2 * nch >= d + k and ksteps == nch // 2 and 1 <= ksteps <= 4   # every tap inside the window, whole K steps
+    assert 2 * (nch - 2) < d + k + 2                                        # and no K step more than needed
+    assert rpp * 16 * ksteps <= 64 and rpp in (1, 2, 4)                      # filter rows sharing a 128-byte weight row fit its 64 K columns
+    # window pixel -> tap, as pack_feed_host maps it: every tap exactly once, the rest padding
+    taps = [off - d for off in range(2 * nch) if 0 <= off - d < k]
+    assert taps == list(range(k))
+
+
+def test_feed_plan_refuses_other_layers():
+    out = (C.c_int * 5)()
+    assert lib().snnb_debug_feed_plan(7, 1, 3, 3, out) == 0    # stride 1: windows start on odd pixels
+    assert lib().snnb_debug_feed_plan(7, 2, 3, 8, out) == 0    # more than 4 channels per pixel
+    assert lib().snnb_debug_feed_plan(1, 2, 0, 3, out) == 0    # 1x1
