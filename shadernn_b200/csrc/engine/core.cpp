@@ -1,6 +1,7 @@
 // MixedInferenceCore: init (tensor plan, weight arena, fusion, CUDA-graph capture) and run.
 // Counterpart of core/src/ic2/core.cpp:294-410 (init) and :97-245 (run).
 #include <algorithm>
+#include <cstring>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -32,6 +33,7 @@ MixedInferenceCore::~MixedInferenceCore() {
         if (sl.stageIn) cudaFree(sl.stageIn);
         if (sl.stageResize) cudaFree(sl.stageResize);
         if (sl.stageOut) cudaFree(sl.stageOut);
+        if (sl.smallHost) cudaFreeHost(sl.smallHost);
         if (sl.argmax) cudaFree(sl.argmax);
         if (sl.h2dDone) cudaEventDestroy(sl.h2dDone);
         if (sl.stageFree) cudaEventDestroy(sl.stageFree);
@@ -522,6 +524,8 @@ int MixedInferenceCore::ensureStreaming() {
         SNNB_CUDA_OK(cudaMalloc(&sl.stageIn, ioStageBytes));
         SNNB_CUDA_OK(cudaMalloc(&sl.stageOut, ioStageBytes));
         SNNB_CUDA_OK(cudaMalloc(&sl.argmax, sizeof(int) * options.batch));
+        SNNB_CUDA_OK(cudaHostAlloc(&sl.smallHost, SMALL_RESULT_BYTES, cudaHostAllocMapped));
+        SNNB_CUDA_OK(cudaHostGetDevicePointer(&sl.smallDev, sl.smallHost, 0));
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.h2dDone, cudaEventDisableTiming));
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.stageFree, cudaEventDisableTiming));
         SNNB_CUDA_OK(cudaEventCreateWithFlags(&sl.resultReady, cudaEventDisableTiming));
@@ -583,6 +587,18 @@ int MixedInferenceCore::submitImpl(const void* hostInput, bool u8, const float* 
     }
     SNNB_CUDA_OK(cudaEventRecord(sl.stageFree, ctx->stream));
     if (forward()) return 1;
+    sl.userOut = nullptr, sl.userClasses = nullptr, sl.userFloats = 0;
+    // a small classifier result (values + classes) is written straight into mapped pinned memory by ONE kernel; wait() copies it out
+    static const bool noSmall = getenv("SNNB_NO_SMALL_RESULT") != nullptr;
+    const bool small = !noSmall && isClassifier && !(io && io->output_u8) && (hostOutput || classes1) &&
+                       outFloats * sizeof(float) + options.batch * sizeof(int) <= SMALL_RESULT_BYTES;
+    if (small) {
+        float* vals = static_cast<float*>(sl.smallDev);
+        int* cls    = reinterpret_cast<int*>(static_cast<char*>(sl.smallDev) + outFloats * sizeof(float));
+        if (launch_result_small(ctx, out, hostOutput ? vals : nullptr, classes1 ? cls : nullptr)) return 1;
+        sl.userOut = hostOutput, sl.userClasses = classes1, sl.userFloats = outFloats;
+        hostOutput = nullptr, classes1 = nullptr; // served
+    }
     if (hostOutput) {
         if (launch_merge_f32(ctx, out, sl.stageOut)) return 1;
         SNNB_CUDA_OK(cudaMemcpyAsync(hostOutput, sl.stageOut, outFloats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -609,6 +625,12 @@ int MixedInferenceCore::wait(int ticket) {
     Slot& sl = slots[ticket & 1];
     SNNB_REQUIRE(sl.busy, "wait: ticket %d was already waited for", ticket);
     SNNB_CUDA_OK(cudaEventSynchronize(sl.resultReady));
+    if (sl.userOut) std::memcpy(sl.userOut, sl.smallHost, sl.userFloats * sizeof(float));
+    if (sl.userClasses) {
+        const int* cls = reinterpret_cast<const int*>(static_cast<const char*>(sl.smallHost) + sl.userFloats * sizeof(float));
+        for (uint32_t i = 0; i < options.batch; ++i) sl.userClasses[i] = cls[i] + 1; // core.cpp:228-233: argmax + 1
+    }
+    sl.userOut = nullptr, sl.userClasses = nullptr;
     if (sl.classesHost)
         for (uint32_t i = 0; i < options.batch; ++i) sl.classesHost[i] += 1; // core.cpp:228-233: argmax + 1
     sl.busy = false;

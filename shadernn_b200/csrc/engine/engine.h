@@ -380,6 +380,7 @@ private:
     void* yoloHost = nullptr; // pinned host mirror
     int decodeYolo(void* dev, void* host, bool sync); // candidates kernel + D2H (+ sync + host NMS into `boxes`)
     // streaming state
+    static constexpr size_t SMALL_RESULT_BYTES = 64 * 1024;
     struct Slot {
         void* stageResize = nullptr; // device staging of a differently-sized u8 input (grown on demand)
         size_t stageResizeBytes = 0;
@@ -388,6 +389,13 @@ private:
         int* argmax = nullptr;
         cudaEvent_t h2dDone = nullptr, stageFree = nullptr, resultReady = nullptr;
         int* classesHost = nullptr;
+        // small classifier results bypass the copy engine: one kernel writes values + arg-max into this mapped pinned block, wait() hands
+        // them to the caller's buffers (two ~10 us device->host copy commands less per batch)
+        void* smallHost = nullptr;      // cudaHostAlloc'ed, SMALL_RESULT_BYTES
+        void* smallDev  = nullptr;      // its device alias
+        float* userOut = nullptr;       // where wait() copies the values
+        int* userClasses = nullptr;     // ... and the 1-based classes
+        size_t userFloats = 0;
         void* yoloDev = nullptr;
         void* yoloHost = nullptr;
         bool busy = false, everUsed = false;

@@ -809,6 +809,35 @@ __global__ void __launch_bounds__(128) argmax_kernel(TV in, int* __restrict__ id
     }
     if (lane == 0) idx[n] = bi;
 }
+// Classifier result in one launch: fp32 values of a 1x1xC tensor and/or the arg-max per image, written wherever the pointers point -
+// the streaming path hands in MAPPED PINNED HOST memory, so a small result needs no device->host copy commands at all.
+__global__ void __launch_bounds__(128) result_small_kernel(TV in, float* __restrict__ values, int* __restrict__ idx) {
+    pdl_wait();
+    const int n    = (int) (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= in.N) return;
+    const size_t base = (size_t) n * in.Cp; // H = W = 1
+    float best = -3.402823466e+38f;
+    int bi     = 0x7fffffff;
+    for (int c = lane; c < in.C; c += 32) {
+        const float v = load1(in.hi, in.lo, base + c);
+        if (values) values[(size_t) n * in.C + c] = v;
+        if (v > best) best = v, bi = c;
+    }
+    if (!idx) return;
+    for (int o = 16; o > 0; o >>= 1) { // same order as argmax_kernel: the larger value, on ties the smaller index
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi   = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
+    }
+    if (lane == 0) idx[n] = bi;
+}
+int launch_result_small(snnb_context* ctx, const snnb_tensor* in, float* values, int* idx) {
+    SNNB_REQUIRE(in->h == 1 && in->w == 1, "launch_result_small: a 1x1 tensor is expected");
+    launch_k(result_small_kernel, dim3((unsigned) (((long long) in->n * 32 + 127) / 128)), dim3(128), 0, ctx->stream, view(in), values, idx);
+    SNNB_LAUNCH_CHECK(ctx);
+    return 0;
+}
 int launch_argmax(snnb_context* ctx, const snnb_tensor* in, int* dev_idx) {
     launch_k(argmax_kernel, dim3((unsigned) (((long long) in->n * 32 + 127) / 128)), dim3(128), 0, ctx->stream, view(in), dev_idx);
     SNNB_LAUNCH_CHECK(ctx);

@@ -219,6 +219,7 @@ int launch_subpixel(snnb_context* ctx, const snnb_tensor* in, snnb_tensor* out, 
 int launch_split_f32(snnb_context* ctx, const float* dev_nhwc, snnb_tensor* t);       // fp32 NHWC (pitch C) -> hi/lo
 int launch_split_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, snnb_tensor* t, const float mean[4], const float norm[4]); // (u8 - mean[c&3]) * norm[c&3]
 int launch_merge_f32(snnb_context* ctx, const snnb_tensor* t, float* dev_nhwc);       // hi/lo -> fp32 NHWC (pitch C)
+int launch_result_small(snnb_context* ctx, const snnb_tensor* t, float* values, int* idx); // 1x1xC tensor -> fp32 values and/or arg-max per image (pointers may be mapped host memory)
 // u8 NHWC image of size src_h x src_w -> resized (linear / nearest, vk_resize.comp) + normalised -> t
 int launch_resize_u8(snnb_context* ctx, const uint8_t* dev_nhwc_u8, int src_h, int src_w, snnb_tensor* t, const float mean[4], const float norm[4], bool linear);
 int launch_merge_u8(snnb_context* ctx, const snnb_tensor* t, uint8_t* dev_nhwc_u8, float scale, float offset); // clamp(round(v*scale+offset), 0, 255)
