@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(128) conv2d_simt_kernel(const ConvKParams p) {
 }
 
 int launch_conv2d_simt(snnb_context* ctx, const ConvArgs& a) {
+    SNNB_REQUIRE(!a.in->feed_only, "launch_conv2d_simt: the input tensor only exists as a stem feed, which this kernel cannot read");
     ctx->last_kernel = "conv2d_simt_kernel";
     ConvKParams p;
     p.in      = view(a.in);

@@ -1707,6 +1707,7 @@ static int launch_conv2d_rowwin(snnb_context* ctx, const ConvArgs& a, EncodeTile
     SNNB_REQUIRE(make_row_plan(a.k, a.stride, a.pad_x, rp), "launch_conv2d_rowwin: no row plan");
     FeedPlan fp;
     const bool feed = feed_usable(a, fp);
+    SNNB_REQUIRE(feed || !in->feed_only, "launch_conv2d_rowwin: the input tensor only exists as a stem feed, which this launch cannot read");
     if (feed) { // one dense segment per plane, K steps at consecutive 32-byte offsets
         rp.parities = 1, rp.ksteps = fp.ksteps;
         for (int q = 0; q < fp.ksteps; ++q) rp.ks_parity[q] = 0, rp.ks_erel[q] = 2 * q;
@@ -1801,6 +1802,7 @@ int launch_conv2d_umma(snnb_context* ctx, const ConvArgs& a) {
     EncodeTiledFn encode = get_encode(ctx);
     SNNB_REQUIRE(encode, "launch_conv2d_umma: cuTensorMapEncodeTiled is unavailable in this driver");
     if (rowwin_supported(a)) return launch_conv2d_rowwin(ctx, a, encode);
+    SNNB_REQUIRE(!a.in->feed_only, "launch_conv2d_umma: the input tensor only exists as a stem feed, which this launch cannot read");
     const snnb_tensor* in = a.in;
     snnb_tensor* out      = a.out;
     UmmaParams p;
